@@ -1,0 +1,533 @@
+"""Pure-Python big-int restatement of the kzg-rs verification path (TEST INFRASTRUCTURE ONLY).
+
+This module is part of the oracle: it may be imported by tests/, by
+``__graft_entry__.smoke()`` and by the golden-vector generators under
+``tests/golden/`` -- never by the product package ``kzg_rs_b200``.
+
+It restates, with Python integers, the algorithm of
+  /root/reference/src/kzg_proof.rs:17-525   (protocol logic, error order)
+  /root/reference/src/pairings.rs:5-9       (2-pair pairing check)
+  /root/reference/src/dtypes.rs:48-57       (Blob::as_polynomial)
+  /root/reference/build.rs:89-105,131-170   (roots-of-unity table order)
+and the subset of the un-vendored dependency ``sp1_bls12_381 =0.8.0-sp1-6.0.0``
+(/root/reference/Cargo.toml:13) that the path calls: Fr/Fp arithmetic, G1/G2 group law,
+ZCash compressed point encoding with subgroup checks, optimal-ate pairing.  The dependency's
+source is not under /root/reference, so the published BLS12-381 definitions are restated;
+every compared output is a canonical field element, an affine point or a boolean, so any
+correct implementation is bit-identical.
+
+It is slow (a pairing check is ~0.3-1 s) and is used for small cases: pinning the C oracle's
+intermediates (z, y, r, r-powers, MSM partial sums) and deriving constants.
+"""
+import hashlib
+
+# ----------------------------------------------------------------------------- fields
+P = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+Q = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001  # consts.rs:213-219
+BLS_X = 0xd201000000010000  # |x|; the curve parameter is -BLS_X
+BLS_X_IS_NEG = True
+
+FIELD_ELEMENTS_PER_BLOB = 4096          # consts.rs:7
+BYTES_PER_BLOB = 4096 * 32              # consts.rs:8
+FIAT_SHAMIR_PROTOCOL_DOMAIN = b"FSBLOBVERIFY_V1_"       # consts.rs:14
+RANDOM_CHALLENGE_KZG_BATCH_DOMAIN = b"RCKZGBATCH___V1_"  # consts.rs:15
+# consts.rs:90-95, SCALE2_ROOT_OF_UNITY[12] (little-endian u64 limbs there)
+ROOT_OF_UNITY_4096 = 0x564c0a11a0f704f4fc3e8acfe0f8245f0ad1347b378fbf96e206da11a5d36306
+
+
+def fp_inv(a):
+    return pow(a, P - 2, P)
+
+
+def fp_sqrt(a):
+    """p = 3 mod 4 -> candidate a^((p+1)/4); returns None when a is a non-residue."""
+    s = pow(a, (P + 1) // 4, P)
+    return s if s * s % P == a % P else None
+
+
+# Fp2 = Fp[u]/(u^2+1): tuples (c0, c1)
+def f2_add(a, b): return ((a[0] + b[0]) % P, (a[1] + b[1]) % P)
+def f2_sub(a, b): return ((a[0] - b[0]) % P, (a[1] - b[1]) % P)
+def f2_neg(a): return ((-a[0]) % P, (-a[1]) % P)
+def f2_mul(a, b): return ((a[0] * b[0] - a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P)
+def f2_sqr(a): return f2_mul(a, a)
+def f2_scale(a, k): return (a[0] * k % P, a[1] * k % P)
+def f2_conj(a): return (a[0], (-a[1]) % P)
+
+
+def f2_inv(a):
+    n = fp_inv((a[0] * a[0] + a[1] * a[1]) % P)
+    return (a[0] * n % P, (-a[1]) * n % P)
+
+
+def f2_pow(a, e):
+    r = (1, 0)
+    while e:
+        if e & 1:
+            r = f2_mul(r, a)
+        a = f2_sqr(a)
+        e >>= 1
+    return r
+
+
+def f2_sqrt(a):
+    """Square root in Fp2 (p = 3 mod 4, 'complex method'); None for non-residues."""
+    if a == (0, 0):
+        return (0, 0)
+    a1 = f2_pow(a, (P - 3) // 4)
+    alpha = f2_mul(f2_sqr(a1), a)
+    x0 = f2_mul(a1, a)
+    if alpha == (P - 1, 0):
+        r = f2_mul((0, 1), x0)
+    else:
+        b = f2_pow(f2_add((1, 0), alpha), (P - 1) // 2)
+        r = f2_mul(b, x0)
+    return r if f2_sqr(r) == (a[0] % P, a[1] % P) else None
+
+
+F2_ZERO, F2_ONE = (0, 0), (1, 0)
+XI = (1, 1)  # v^3 = xi = 1 + u
+
+
+def f2_mul_xi(a):
+    return ((a[0] - a[1]) % P, (a[0] + a[1]) % P)
+
+
+# Fp6 = Fp2[v]/(v^3 - xi): tuples of 3 Fp2 ; Fp12 = Fp6[w]/(w^2 - v): tuples of 2 Fp6
+def f6_add(a, b): return tuple(f2_add(x, y) for x, y in zip(a, b))
+def f6_sub(a, b): return tuple(f2_sub(x, y) for x, y in zip(a, b))
+def f6_neg(a): return tuple(f2_neg(x) for x in a)
+
+
+def f6_mul(a, b):
+    a0, a1, a2 = a
+    b0, b1, b2 = b
+    t0, t1, t2 = f2_mul(a0, b0), f2_mul(a1, b1), f2_mul(a2, b2)
+    c0 = f2_add(t0, f2_mul_xi(f2_sub(f2_mul(f2_add(a1, a2), f2_add(b1, b2)), f2_add(t1, t2))))
+    c1 = f2_add(f2_sub(f2_mul(f2_add(a0, a1), f2_add(b0, b1)), f2_add(t0, t1)), f2_mul_xi(t2))
+    c2 = f2_add(f2_sub(f2_mul(f2_add(a0, a2), f2_add(b0, b2)), f2_add(t0, t2)), t1)
+    return (c0, c1, c2)
+
+
+def f6_mul_v(a):
+    return (f2_mul_xi(a[2]), a[0], a[1])
+
+
+def f6_inv(a):
+    a0, a1, a2 = a
+    c0 = f2_sub(f2_sqr(a0), f2_mul_xi(f2_mul(a1, a2)))
+    c1 = f2_sub(f2_mul_xi(f2_sqr(a2)), f2_mul(a0, a1))
+    c2 = f2_sub(f2_sqr(a1), f2_mul(a0, a2))
+    t = f2_add(f2_mul(a0, c0), f2_mul_xi(f2_add(f2_mul(a2, c1), f2_mul(a1, c2))))
+    ti = f2_inv(t)
+    return (f2_mul(c0, ti), f2_mul(c1, ti), f2_mul(c2, ti))
+
+
+F6_ZERO = (F2_ZERO, F2_ZERO, F2_ZERO)
+F6_ONE = (F2_ONE, F2_ZERO, F2_ZERO)
+F12_ONE = (F6_ONE, F6_ZERO)
+
+
+def f12_mul(a, b):
+    a0, a1 = a
+    b0, b1 = b
+    t0, t1 = f6_mul(a0, b0), f6_mul(a1, b1)
+    c1 = f6_sub(f6_mul(f6_add(a0, a1), f6_add(b0, b1)), f6_add(t0, t1))
+    return (f6_add(t0, f6_mul_v(t1)), c1)
+
+
+def f12_sqr(a): return f12_mul(a, a)
+def f12_conj(a): return (a[0], f6_neg(a[1]))
+
+
+def f12_inv(a):
+    a0, a1 = a
+    t = f6_inv(f6_sub(f6_mul(a0, a0), f6_mul_v(f6_mul(a1, a1))))
+    return (f6_mul(a0, t), f6_neg(f6_mul(a1, t)))
+
+
+def f12_pow(a, e):
+    r = F12_ONE
+    while e:
+        if e & 1:
+            r = f12_mul(r, a)
+        a = f12_sqr(a)
+        e >>= 1
+    return r
+
+
+# Frobenius: (sum a_ij v^i w^j)^p ; v^p = v * xi^((p-1)/3), w^p = w * xi^((p-1)/6)
+_G6 = [f2_pow(XI, k * (P - 1) // 6) for k in range(6)]  # xi^(k(p-1)/6)
+
+
+def f12_frob(a):
+    (a00, a01, a02), (a10, a11, a12) = a
+    # basis element v^i w^j = w^(2i+j) -> multiply conj(coeff) by _G6[2i+j]
+    c = lambda x, k: f2_mul(f2_conj(x), _G6[k])
+    return ((c(a00, 0), c(a01, 2), c(a02, 4)), (c(a10, 1), c(a11, 3), c(a12, 5)))
+
+
+# ----------------------------------------------------------------------------- curves
+# G1: y^2 = x^3 + 4 over Fp ; G2: y^2 = x^3 + 4(1+u) over Fp2.  Points: None = identity, else (x, y)
+G1_GEN = (
+    0x17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb,
+    0x08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1,
+)
+G2_GEN = (
+    (0x024aa2b2f08f0a91260805272dc51051c6e47ad4fa403b02b4510b647ae3d1770bac0326a805bbefd48056c8c121bdb8,
+     0x13e02b6052719f607dacd3a088274f65596bd0d09920b61ab5da61bbdc7f5049334cf11213945d57e5ac7d055d042b7e),
+    (0x0ce5d527727d6e118cc9cdc6da2e351aadfd9baa8cbdd3a76d429a695160d12c923ac9cc3baca289e193548608b82801,
+     0x0606c4a02ea734cc32acd2b02bc28b99cb3e287e85a763af267492ab572e99ab3f370d275cec1da1aaa9075ff05f79be),
+)
+B2 = (4, 4)
+
+
+def g1_on_curve(pt):
+    return pt is None or (pt[1] * pt[1] - pt[0] ** 3 - 4) % P == 0
+
+
+def g1_neg(a):
+    return None if a is None else (a[0], (-a[1]) % P)
+
+
+def g1_add(a, b):
+    if a is None: return b
+    if b is None: return a
+    if a[0] == b[0]:
+        if (a[1] + b[1]) % P == 0:
+            return None
+        lam = 3 * a[0] * a[0] * fp_inv(2 * a[1]) % P
+    else:
+        lam = (b[1] - a[1]) * fp_inv(b[0] - a[0]) % P
+    x = (lam * lam - a[0] - b[0]) % P
+    return (x, (lam * (a[0] - x) - a[1]) % P)
+
+
+def _jac_dbl(X, Y, Z):
+    if Y == 0: return (1, 1, 0)
+    A = X * X % P; B = Y * Y % P; C = B * B % P
+    D = 2 * ((X + B) ** 2 - A - C) % P
+    E = 3 * A % P
+    X3 = (E * E - 2 * D) % P
+    return (X3, (E * (D - X3) - 8 * C) % P, 2 * Y * Z % P)
+
+
+def _jac_add_affine(X, Y, Z, x2, y2):
+    if Z == 0: return (x2, y2, 1)
+    Z2 = Z * Z % P
+    U2 = x2 * Z2 % P; S2 = y2 * Z2 * Z % P
+    H = (U2 - X) % P; R = (S2 - Y) % P
+    if H == 0:
+        return _jac_dbl(X, Y, Z) if R == 0 else (1, 1, 0)
+    H2 = H * H % P; H3 = H2 * H % P
+    X3 = (R * R - H3 - 2 * X * H2) % P
+    return (X3, (R * (X * H2 - X3) - Y * H3) % P, Z * H % P)
+
+
+def g1_mul(pt, k):
+    """[k]pt for integer k >= 0 (Jacobian double-and-add; result affine)."""
+    if pt is None or k == 0: return None
+    X, Y, Z = 1, 1, 0
+    for bit in bin(k)[2:]:
+        X, Y, Z = _jac_dbl(X, Y, Z)
+        if bit == '1':
+            X, Y, Z = _jac_add_affine(X, Y, Z, pt[0], pt[1])
+    if Z == 0: return None
+    zi = fp_inv(Z); zi2 = zi * zi % P
+    return (X * zi2 % P, Y * zi2 * zi % P)
+
+
+def g1_in_subgroup(pt):
+    return g1_mul(pt, Q) is None
+
+
+def g2_neg(a):
+    return None if a is None else (a[0], f2_neg(a[1]))
+
+
+def g2_add(a, b):
+    if a is None: return b
+    if b is None: return a
+    if a[0] == b[0]:
+        if f2_add(a[1], b[1]) == F2_ZERO:
+            return None
+        lam = f2_mul(f2_scale(f2_sqr(a[0]), 3), f2_inv(f2_scale(a[1], 2)))
+    else:
+        lam = f2_mul(f2_sub(b[1], a[1]), f2_inv(f2_sub(b[0], a[0])))
+    x = f2_sub(f2_sub(f2_sqr(lam), a[0]), b[0])
+    return (x, f2_sub(f2_mul(lam, f2_sub(a[0], x)), a[1]))
+
+
+def g2_mul(pt, k):
+    r = None
+    for bit in bin(k)[2:] if k else '':
+        r = g2_add(r, r)
+        if bit == '1':
+            r = g2_add(r, pt)
+    return r
+
+
+def g2_on_curve(pt):
+    return pt is None or f2_sub(f2_sqr(pt[1]), f2_add(f2_mul(f2_sqr(pt[0]), pt[0]), B2)) == F2_ZERO
+
+
+# ----------------------------------------------------------------------------- ZCash encodings
+def g1_from_compressed(b, check_subgroup=True):
+    """bls12_381 G1Affine::from_compressed [dep]: returns (ok, point)."""
+    if len(b) != 48: return (False, None)
+    comp, inf, sort = b[0] >> 7 & 1, b[0] >> 6 & 1, b[0] >> 5 & 1
+    x = int.from_bytes(bytes([b[0] & 0x1f]) + bytes(b[1:]), 'big')
+    if not comp: return (False, None)
+    if inf:
+        return (x == 0 and not sort, None)
+    if x >= P: return (False, None)
+    y = fp_sqrt((x ** 3 + 4) % P)
+    if y is None: return (False, None)
+    if (y > (P - 1) // 2) != bool(sort):
+        y = P - y
+    pt = (x, y)
+    if check_subgroup and not g1_in_subgroup(pt): return (False, None)
+    return (True, pt)
+
+
+def g1_to_compressed(pt):
+    if pt is None:
+        return bytes([0xc0]) + bytes(47)
+    out = bytearray(pt[0].to_bytes(48, 'big'))
+    out[0] |= 0x80
+    if pt[1] > (P - 1) // 2:
+        out[0] |= 0x20
+    return bytes(out)
+
+
+def _f2_lex_largest(y):
+    return y[1] > (P - 1) // 2 or (y[1] == 0 and y[0] > (P - 1) // 2)
+
+
+def g2_from_compressed(b, check_subgroup=False):
+    if len(b) != 96: return (False, None)
+    comp, inf, sort = b[0] >> 7 & 1, b[0] >> 6 & 1, b[0] >> 5 & 1
+    x1 = int.from_bytes(bytes([b[0] & 0x1f]) + bytes(b[1:48]), 'big')
+    x0 = int.from_bytes(bytes(b[48:96]), 'big')
+    if not comp: return (False, None)
+    if inf: return (x0 == 0 and x1 == 0 and not sort, None)
+    if x0 >= P or x1 >= P: return (False, None)
+    x = (x0, x1)
+    y = f2_sqrt(f2_add(f2_mul(f2_sqr(x), x), B2))
+    if y is None: return (False, None)
+    if _f2_lex_largest(y) != bool(sort):
+        y = f2_neg(y)
+    pt = (x, y)
+    if check_subgroup and g2_mul(pt, Q) is not None: return (False, None)
+    return (True, pt)
+
+
+# ----------------------------------------------------------------------------- pairing
+def _line_coeffs_affine(T, Qp, doubling):
+    """Line through T (tangent, or chord T-Qp) on the twist, as (A, B) with the line value at
+    P=(xP,yP) equal to A + (B*xP) v + yP vw (sparse positions 0,1,4); returns (coeffs, T')"""
+    if doubling:
+        lam = f2_mul(f2_scale(f2_sqr(T[0]), 3), f2_inv(f2_scale(T[1], 2)))
+        R = g2_add(T, T)
+    else:
+        lam = f2_mul(f2_sub(Qp[1], T[1]), f2_inv(f2_sub(Qp[0], T[0])))
+        R = g2_add(T, Qp)
+    A = f2_sub(f2_mul(lam, T[0]), T[1])
+    return (A, f2_neg(lam)), R
+
+
+def _ell(f, coeffs, Ppt):
+    A, B = coeffs
+    line = ((A, f2_scale(B, Ppt[0]), F2_ZERO), (F2_ZERO, (Ppt[1], 0), F2_ZERO))
+    return f12_mul(f, line)
+
+
+def miller_loop(pairs):
+    """prod of Miller functions f_{|x|,Q}(P) (conjugated since x<0) for (P in G1, Q in G2) pairs;
+    pairs with an identity member are skipped, as multi_miller_loop [dep] does."""
+    pairs = [(p_, q_) for p_, q_ in pairs if p_ is not None and q_ is not None]
+    f = F12_ONE
+    Ts = [q_ for _, q_ in pairs]
+    bits = bin(BLS_X)[3:]
+    for bit in bits:
+        f = f12_sqr(f)
+        for i, (p_, q_) in enumerate(pairs):
+            c, Ts[i] = _line_coeffs_affine(Ts[i], None, True)
+            f = _ell(f, c, p_)
+        if bit == '1':
+            for i, (p_, q_) in enumerate(pairs):
+                c, Ts[i] = _line_coeffs_affine(Ts[i], q_, False)
+                f = _ell(f, c, p_)
+    return f12_conj(f) if BLS_X_IS_NEG else f
+
+
+def _exp_by_x(a):
+    r = f12_pow(a, BLS_X)
+    return f12_conj(r) if BLS_X_IS_NEG else r
+
+
+def final_exponentiation(f):
+    """f^((p^12-1)/r * 3): easy part then hard part via
+    3(p^4-p^2+1)/r = (x-1)^2 (x+p)(x^2+p^2-1) + 3."""
+    f = f12_mul(f12_conj(f), f12_inv(f))              # ^(p^6-1)
+    f = f12_mul(f12_frob(f12_frob(f)), f)             # ^(p^2+1)
+    a = f12_mul(_exp_by_x(f), f12_conj(f))            # f^(x-1)
+    a = f12_mul(_exp_by_x(a), f12_conj(a))            # ^(x-1)
+    b = f12_mul(_exp_by_x(a), f12_frob(a))            # ^(x+p)
+    c = f12_mul(f12_mul(_exp_by_x(_exp_by_x(b)), f12_frob(f12_frob(b))), f12_conj(b))
+    return f12_mul(c, f12_mul(f12_sqr(f), f))
+
+
+def pairings_verify(a1, a2, b1, b2):
+    """pairings.rs:5-9: e(-a1, a2) * e(b1, b2) == 1."""
+    return final_exponentiation(miller_loop([(g1_neg(a1), a2), (b1, b2)])) == F12_ONE
+
+
+# ----------------------------------------------------------------------------- setup tables
+def bit_reverse(i, bits=12):
+    return int(format(i, '0%db' % bits)[::-1], 2)
+
+
+_ROOTS = None
+
+
+def roots_of_unity():
+    """build.rs:131-170: powers of the primitive 4096-th root, bit-reversal permuted."""
+    global _ROOTS
+    if _ROOTS is None:
+        pw = [1] * 4096
+        for i in range(1, 4096):
+            pw[i] = pw[i - 1] * ROOT_OF_UNITY_4096 % Q
+        _ROOTS = [pw[bit_reverse(i)] for i in range(4096)]
+    return _ROOTS
+
+
+def load_trusted_setup(path):
+    """build.rs:23-87 -> (g1_lagrange bit-reversed [compressed bytes], g2_monomial [compressed bytes])"""
+    with open(path) as fh:
+        lines = fh.read().split()
+    n1, n2 = int(lines[0]), int(lines[1])
+    g1 = [bytes.fromhex(x) for x in lines[2:2 + n1]]
+    g2 = [bytes.fromhex(x) for x in lines[2 + n1:2 + n1 + n2]]
+    g1 = [g1[bit_reverse(i)] for i in range(n1)]
+    return g1, g2
+
+
+# ----------------------------------------------------------------------------- kzg_proof.rs
+class KzgError(Exception):
+    def __init__(self, kind, msg=""):
+        super().__init__("%s: %s" % (kind, msg))
+        self.kind = kind
+
+
+def safe_g1_affine_from_bytes(b):  # kzg_proof.rs:17-25
+    ok, pt = g1_from_compressed(bytes(b))
+    if not ok:
+        raise KzgError("BadArgs", "Failed to parse G1Affine from bytes")
+    return pt
+
+
+def safe_scalar_affine_from_bytes(b):  # kzg_proof.rs:27-43
+    v = int.from_bytes(bytes(b), 'big')
+    if len(b) != 32 or v >= Q:
+        raise KzgError("BadArgs", "Failed to parse G1Affine from bytes")
+    return v
+
+
+def blob_as_polynomial(blob):  # dtypes.rs:48-57
+    return [safe_scalar_affine_from_bytes(blob[i:i + 32]) for i in range(0, BYTES_PER_BLOB, 32)]
+
+
+def compute_challenge(blob, commitment_pt):  # kzg_proof.rs:46-72
+    msg = (FIAT_SHAMIR_PROTOCOL_DOMAIN + (0).to_bytes(8, 'big')
+           + FIELD_ELEMENTS_PER_BLOB.to_bytes(8, 'big') + bytes(blob) + g1_to_compressed(commitment_pt))
+    assert len(msg) == 131152
+    return int.from_bytes(hashlib.sha256(msg).digest(), 'big') % Q   # :74-91
+
+
+def evaluate_polynomial_in_evaluation_form(poly, x):  # kzg_proof.rs:94-133
+    roots = roots_of_unity()
+    for i in range(4096):
+        if x == roots[i]:
+            return poly[i]
+    out = 0
+    for i in range(4096):
+        out += pow(x - roots[i], Q - 2, Q) * roots[i] % Q * poly[i]
+    out = out % Q * pow(4096, Q - 2, Q) % Q
+    return out * (pow(x, 4096, Q) - 1) % Q
+
+
+def compute_r_powers(commitments, zs, ys, proofs):  # kzg_proof.rs:291-348
+    n = len(commitments)
+    msg = RANDOM_CHALLENGE_KZG_BATCH_DOMAIN + (4096).to_bytes(8, 'big') + n.to_bytes(8, 'big')
+    for i in range(n):
+        msg += g1_to_compressed(commitments[i]) + zs[i].to_bytes(32, 'little') \
+            + ys[i].to_bytes(32, 'little') + g1_to_compressed(proofs[i])
+    r = int.from_bytes(hashlib.sha256(msg).digest(), 'big') % Q
+    out, acc = [], 1
+    for _ in range(n):
+        out.append(acc)
+        acc = acc * r % Q
+    return out
+
+
+def verify_kzg_proof_impl(C, z, y, proof, tau_g2):  # kzg_proof.rs:203-223 / :385-396
+    x_minus_z = g2_add(tau_g2, g2_neg(g2_mul(G2_GEN, z)))
+    p_minus_y = g1_add(C, g1_neg(g1_mul(G1_GEN, y)))
+    return pairings_verify(p_minus_y, G2_GEN, proof, x_minus_z)
+
+
+def verify_kzg_proof(cb, zb, yb, pb, tau_g2):  # kzg_proof.rs:353-397
+    z = safe_scalar_affine_from_bytes(zb)
+    y = safe_scalar_affine_from_bytes(yb)
+    C = safe_g1_affine_from_bytes(cb)
+    pr = safe_g1_affine_from_bytes(pb)
+    return verify_kzg_proof_impl(C, z, y, pr, tau_g2)
+
+
+def verify_blob_kzg_proof(blob, cb, pb, tau_g2, trace=None):  # kzg_proof.rs:446-470
+    C = safe_g1_affine_from_bytes(cb)
+    poly = blob_as_polynomial(blob)
+    pr = safe_g1_affine_from_bytes(pb)
+    z = compute_challenge(blob, C)
+    y = evaluate_polynomial_in_evaluation_form(poly, z)
+    if trace is not None:
+        trace.update(z=[z], y=[y])
+    return verify_kzg_proof_impl(C, z, y, pr, tau_g2)
+
+
+def verify_kzg_proof_batch(Cs, zs, ys, proofs, tau_g2, trace=None):  # kzg_proof.rs:399-444
+    n = len(Cs)
+    rp = compute_r_powers(Cs, zs, ys, proofs)
+    proof_lincomb = proof_z_lincomb = c_minus_y_lincomb = None
+    for i in range(n):
+        proof_lincomb = g1_add(proof_lincomb, g1_mul(proofs[i], rp[i]))
+        c_minus_y = g1_add(Cs[i], g1_neg(g1_mul(G1_GEN, ys[i])))
+        proof_z_lincomb = g1_add(proof_z_lincomb, g1_mul(proofs[i], rp[i] * zs[i] % Q))
+        c_minus_y_lincomb = g1_add(c_minus_y_lincomb, g1_mul(c_minus_y, rp[i]))
+    rhs = g1_add(c_minus_y_lincomb, proof_z_lincomb)
+    if trace is not None:
+        trace.update(r_powers=rp, proof_lincomb=proof_lincomb, rhs_g1=rhs)
+    return pairings_verify(proof_lincomb, tau_g2, rhs, G2_GEN)
+
+
+def verify_blob_kzg_proof_batch(blobs, cbs, pbs, tau_g2, trace=None):  # kzg_proof.rs:472-525
+    if len(blobs) == 0:
+        return True
+    if len(blobs) == 1:
+        return verify_blob_kzg_proof(blobs[0], cbs[0], pbs[0], tau_g2, trace)
+    if len(blobs) != len(cbs):
+        raise KzgError("InvalidBytesLength", "Invalid commitments length")
+    if len(blobs) != len(pbs):
+        raise KzgError("InvalidBytesLength", "Invalid proofs length")
+    Cs = [safe_g1_affine_from_bytes(b) for b in cbs]
+    prs = [safe_g1_affine_from_bytes(b) for b in pbs]
+    zs, ys = [], []
+    for i in range(len(blobs)):
+        poly = blob_as_polynomial(blobs[i])
+        z = compute_challenge(blobs[i], Cs[i])
+        zs.append(z)
+        ys.append(evaluate_polynomial_in_evaluation_form(poly, z))
+    if trace is not None:
+        trace.update(z=zs, y=ys)
+    return verify_kzg_proof_batch(Cs, zs, ys, prs, tau_g2, trace)
