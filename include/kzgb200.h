@@ -1,0 +1,104 @@
+/* kzgb200 -- C ABI of the B200-native (sm_100a) replacement for the EIP-4844 verification hot path of
+ * succinctlabs/kzg-rs v0.2.8.  This is the boundary a Rust (extern "C"), cgo, or ctypes binding binds;
+ * INTEGRATION.md shows the Rust shim that keeps kzg-rs's public API unchanged on top of it.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the library never frees or retains caller memory past return;
+ *   - "host" entry points take host memory (pageable or pinned) and do their own staging;
+ *     "_device" entry points take device pointers on the context's GPU (inputs already resident in HBM);
+ *   - return codes map 1:1 onto kzg-rs's KzgError (reference src/enums.rs:6-18):
+ *         KZGB200_OK                 Ok(verdict), verdict in *ok (1 = true, 0 = false)
+ *         KZGB200_BAD_ARGS           Err(KzgError::BadArgs)            -- unparsable scalar / G1 point
+ *         KZGB200_INTERNAL_ERROR     Err(KzgError::InternalError)      -- CUDA failure
+ *         KZGB200_INVALID_LENGTH     Err(KzgError::InvalidBytesLength) -- vector length mismatch
+ *         KZGB200_INVALID_SETUP      Err(KzgError::InvalidTrustedSetup)
+ *   - a context is bound to one GPU; calls on one context are serialised by an internal lock, use one
+ *     context per thread (or per GPU) for concurrency.  There is no CPU fallback: every entry point fails
+ *     with KZGB200_INTERNAL_ERROR when no sm_100 device / kernel image is available.
+ */
+#ifndef KZGB200_H
+#define KZGB200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KZGB200_OK 0
+#define KZGB200_BAD_ARGS 1
+#define KZGB200_INTERNAL_ERROR 2
+#define KZGB200_INVALID_LENGTH 3
+#define KZGB200_INVALID_SETUP 5
+
+#define KZGB200_BYTES_PER_BLOB 131072       /* reference src/consts.rs:8 */
+#define KZGB200_BYTES_PER_COMMITMENT 48     /* src/consts.rs:9 */
+#define KZGB200_BYTES_PER_PROOF 48          /* src/consts.rs:10 */
+#define KZGB200_BYTES_PER_FIELD_ELEMENT 32  /* src/consts.rs:3 */
+#define KZGB200_PARTIAL_BYTES 352           /* per-rank partial of the sharded batch (see below) */
+
+typedef struct kzgb200_ctx kzgb200_ctx;
+
+/* Replaces KzgSettings::load_trusted_setup_file (reference src/trusted_setup.rs:94-98) + the table building
+ * of build.rs:131-170: uploads / derives the device-resident tables (roots of unity in Montgomery form,
+ * Miller-loop line coefficients of g2_points[0] and g2_points[1]).  g2_points = the first two G2 points of
+ * the trusted setup, ZCash-compressed, 2 x 96 bytes (trusted_setup.txt lines 4099-4100).  The verification
+ * path reads nothing else from the setup. */
+int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_points, size_t g2_points_len);
+void kzgb200_destroy(kzgb200_ctx* ctx);
+/* last CUDA error string of the context ("" if none); valid until the next call */
+const char* kzgb200_last_error(const kzgb200_ctx* ctx);
+
+/* KzgProof::verify_kzg_proof (reference src/kzg_proof.rs:353-397). */
+int kzgb200_verify_kzg_proof(kzgb200_ctx* ctx, const uint8_t* commitment48, const uint8_t* z32, const uint8_t* y32,
+                             const uint8_t* proof48, int* ok);
+
+/* KzgProof::verify_blob_kzg_proof (reference src/kzg_proof.rs:446-470).  z_out / y_out (32 bytes, big-endian,
+ * nullable) receive the Fiat-Shamir challenge and the evaluation -- intermediates that must be bit-exact. */
+int kzgb200_verify_blob_kzg_proof(kzgb200_ctx* ctx, const uint8_t* blob, const uint8_t* commitment48,
+                                  const uint8_t* proof48, int* ok, uint8_t* z_out, uint8_t* y_out);
+
+/* KzgProof::verify_blob_kzg_proof_batch (reference src/kzg_proof.rs:472-525).  The three lengths are the
+ * lengths of the three Vec arguments; n == 0 -> Ok(true); n == 1 -> single path; mismatch -> INVALID_LENGTH.
+ * blobs = n_blobs x 131072 bytes contiguous (a Vec<Blob> is exactly that), commitments / proofs = n x 48.
+ * z_out / y_out: n_blobs x 32 bytes big-endian, nullable. */
+int kzgb200_verify_blob_kzg_proof_batch(kzgb200_ctx* ctx, const uint8_t* blobs, size_t n_blobs,
+                                        const uint8_t* commitments, size_t n_commitments,
+                                        const uint8_t* proofs, size_t n_proofs, int* ok,
+                                        uint8_t* z_out, uint8_t* y_out);
+/* Same, inputs (and z_out / y_out, nullable) are device pointers on the context's GPU; n >= 1. */
+int kzgb200_verify_blob_kzg_proof_batch_device(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t* d_commitments,
+                                               const uint8_t* d_proofs, size_t n, int* ok,
+                                               uint8_t* d_z_out, uint8_t* d_y_out);
+
+/* m independent verify_kzg_proof tuples (BASELINE config 5); verdicts[i] = 0 false, 1 true, 2 BadArgs.
+ * Host pointers. */
+int kzgb200_verify_kzg_proof_many(kzgb200_ctx* ctx, const uint8_t* commitments, const uint8_t* zs, const uint8_t* ys,
+                                  const uint8_t* proofs, size_t m, uint8_t* verdicts);
+
+/* ---- sharded batch: one context (= one rank) per GPU, blobs partitioned by contiguous ranges -------------
+ * The batch is verified as   phase 1 (per rank)  -> exchange (z,y)  -> r  -> phase 2 (per rank partial sums)
+ * -> allgather of KZGB200_PARTIAL_BYTES per rank -> one final pairing check.  All pointers are device
+ * pointers on the rank's GPU; the caller moves the small payloads between ranks (NCCL allgather).
+ *
+ * phase 1: parse C/pi, canonicity, z_i, y_i for this rank's n_local blobs.  d_zy_out = n_local x 64 bytes:
+ *          z_i then y_i as 32-byte little-endian canonical scalars (the byte order the batch transcript
+ *          hashes, reference src/kzg_proof.rs:320-328). */
+int kzgb200_shard_evaluate(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t* d_commitments,
+                           const uint8_t* d_proofs, size_t n_local, uint8_t* d_zy_out);
+/* r = SHA-256 transcript over ALL n_total blobs in global order (reference src/kzg_proof.rs:291-348), from the
+ * gathered commitments (n_total x 48), zy (n_total x 64, as produced by phase 1) and proofs (n_total x 48). */
+int kzgb200_shard_challenge(kzgb200_ctx* ctx, const uint8_t* d_all_commitments, const uint8_t* d_all_zy,
+                            const uint8_t* d_all_proofs, size_t n_total);
+/* phase 2: this rank's partial sums with r_i = r^(global_offset + i); writes KZGB200_PARTIAL_BYTES to d_partial_out. */
+int kzgb200_shard_lincomb(kzgb200_ctx* ctx, size_t global_offset, uint8_t* d_partial_out);
+/* final: sum the gathered partials (n_ranks x KZGB200_PARTIAL_BYTES) and run the single pairing check. */
+int kzgb200_shard_finalize(kzgb200_ctx* ctx, const uint8_t* d_partials, size_t n_ranks, int* ok);
+
+/* pinned host memory helpers for callers that want full-rate host->device copies */
+void* kzgb200_alloc_pinned(size_t bytes);
+void kzgb200_free_pinned(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

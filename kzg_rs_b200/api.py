@@ -1,0 +1,269 @@
+"""Python mirror of kzg-rs's public API for the verification path, bound to libkzgb200.so with ctypes.
+
+Same names, argument meaning and error behaviour as the reference:
+  KzgProof.verify_kzg_proof / verify_blob_kzg_proof / verify_blob_kzg_proof_batch   src/kzg_proof.rs:353-525
+  KzgSettings.load_trusted_setup_file                                               src/trusted_setup.rs:94-98
+  Blob / Bytes32 / Bytes48 (.from_slice length check, .as_slice)                    src/dtypes.rs:7-46
+  KzgError                                                                          src/enums.rs:6-18
+`Result<bool, KzgError>` becomes "return bool or raise KzgError".
+
+There is no CPU path: loading fails loudly when the CUDA library has not been built, and every call
+fails with KzgError(InternalError) when no sm_100 GPU is usable.
+"""
+import ctypes as C
+import os
+import struct
+import threading
+
+BYTES_PER_BLOB = 131072          # src/consts.rs:8
+BYTES_PER_COMMITMENT = 48        # src/consts.rs:9
+BYTES_PER_PROOF = 48             # src/consts.rs:10
+BYTES_PER_FIELD_ELEMENT = 32     # src/consts.rs:3
+PARTIAL_BYTES = 352
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_RC_KIND = {1: "BadArgs", 2: "InternalError", 3: "InvalidBytesLength", 5: "InvalidTrustedSetup"}
+_RC_MSG = {1: "Failed to parse G1Affine from bytes", 2: "Internal error", 3: "Invalid commitments length",
+           5: "Invalid trusted setup"}
+
+
+class KzgError(Exception):
+    """src/enums.rs:6-18.  .kind is one of BadArgs, InternalError, InvalidBytesLength, InvalidHexFormat,
+    InvalidTrustedSetup."""
+
+    def __init__(self, kind, msg=""):
+        super().__init__(msg or kind)
+        self.kind = kind
+
+
+def lib_path():
+    return os.path.join(_HERE, "libkzgb200.so")
+
+
+class Library:
+    """The C ABI (include/kzgb200.h).  One process-wide instance."""
+    _inst = None
+    _lock = threading.Lock()
+
+    @classmethod
+    def get(cls):
+        with cls._lock:
+            if cls._inst is None:
+                cls._inst = cls()
+            return cls._inst
+
+    def __init__(self):
+        path = lib_path()
+        if not os.path.exists(path):
+            raise RuntimeError("libkzgb200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "or `make -C kzg_rs_b200/csrc`); there is no CPU fallback")
+        self.dll = d = C.CDLL(path)
+        p, sz, ip = C.c_void_p, C.c_size_t, C.POINTER(C.c_int)
+        d.kzgb200_create.argtypes = [C.POINTER(p), C.c_int, C.c_char_p, sz]
+        d.kzgb200_destroy.argtypes = [p]
+        d.kzgb200_last_error.argtypes = [p]
+        d.kzgb200_last_error.restype = C.c_char_p
+        d.kzgb200_verify_kzg_proof.argtypes = [p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, ip]
+        d.kzgb200_verify_blob_kzg_proof.argtypes = [p, p, C.c_char_p, C.c_char_p, ip, p, p]
+        d.kzgb200_verify_blob_kzg_proof_batch.argtypes = [p, p, sz, p, sz, p, sz, ip, p, p]
+        d.kzgb200_verify_blob_kzg_proof_batch_device.argtypes = [p, p, p, p, sz, ip, p, p]
+        d.kzgb200_verify_kzg_proof_many.argtypes = [p, p, p, p, p, sz, p]
+        d.kzgb200_shard_evaluate.argtypes = [p, p, p, p, sz, p]
+        d.kzgb200_shard_challenge.argtypes = [p, p, p, p, sz]
+        d.kzgb200_shard_lincomb.argtypes = [p, sz, p]
+        d.kzgb200_shard_finalize.argtypes = [p, p, sz, ip]
+        d.kzgb200_alloc_pinned.argtypes = [sz]
+        d.kzgb200_alloc_pinned.restype = p
+        d.kzgb200_free_pinned.argtypes = [p]
+
+
+def _raise(rc, ctx=None, msg=None):
+    kind = _RC_KIND.get(rc, "InternalError")
+    if msg is None:
+        msg = _RC_MSG.get(rc, "Internal error")
+        if kind == "InternalError" and ctx is not None:
+            detail = Library.get().dll.kzgb200_last_error(ctx)
+            if detail:
+                msg += ": " + detail.decode(errors="replace")
+    raise KzgError(kind, msg)
+
+
+class _BytesN:
+    SIZE = 0
+
+    def __init__(self, data):
+        self._b = bytes(data)
+
+    @classmethod
+    def from_slice(cls, data):
+        if len(data) != cls.SIZE:   # src/dtypes.rs:20-24
+            raise KzgError("InvalidBytesLength", "Invalid slice length")
+        return cls(data)
+
+    @classmethod
+    def from_hex(cls, s):
+        try:
+            raw = bytes.fromhex(s[2:] if s.startswith("0x") else s)
+        except ValueError as e:
+            raise KzgError("InvalidHexFormat", "Failed to decode hex: %s" % e)
+        return cls.from_slice(raw)
+
+    def as_slice(self):
+        return self._b
+
+    def __bytes__(self):
+        return self._b
+
+    def __len__(self):
+        return len(self._b)
+
+
+class Bytes32(_BytesN):
+    SIZE = 32
+
+
+class Bytes48(_BytesN):
+    SIZE = 48
+
+
+class Blob(_BytesN):
+    SIZE = BYTES_PER_BLOB
+
+
+class KzgSettings:
+    """src/trusted_setup.rs:44-50.  Holds the setup and one device context per GPU (created on first use:
+    the device-resident tables -- roots of unity, Miller-loop lines of g2_points[0..2] -- are built there)."""
+    _default = None
+    _dlock = threading.Lock()
+
+    def __init__(self, g1_lagrange_bytes, g2_monomial_bytes):
+        self.g1_lagrange_bytes = g1_lagrange_bytes      # 4096 x 48 (file order); unused by verification
+        self.g2_monomial_bytes = g2_monomial_bytes      # 65 x 96; verification reads [0] and [1]
+        self._ctx = {}
+        self._lock = threading.Lock()
+
+    @classmethod
+    def load_trusted_setup_file(cls, path=None):
+        """Default: the embedded mainnet setup (the reference embeds it at build time, build.rs:23-87)."""
+        if path is None:
+            with cls._dlock:
+                if cls._default is None:
+                    cls._default = cls._load(os.path.join(_HERE, "data", "mainnet_setup.bin"))
+                return cls._default
+        return cls._load(path)
+
+    @classmethod
+    def _load(cls, path):
+        with open(path, "rb") as fh:
+            raw = fh.read()
+        if raw[:4] == b"KZGS":
+            n1, n2 = struct.unpack("<II", raw[4:12])
+            if len(raw) != 12 + n1 * 48 + n2 * 96 or n2 < 2:
+                raise KzgError("InvalidTrustedSetup", "Invalid trusted setup")
+            return cls(raw[12:12 + n1 * 48], raw[12 + n1 * 48:])
+        # c-kzg text format: n1, n2, then hex lines
+        try:
+            tok = raw.decode().split()
+            n1, n2 = int(tok[0]), int(tok[1])
+            g1 = b"".join(bytes.fromhex(x) for x in tok[2:2 + n1])
+            g2 = b"".join(bytes.fromhex(x) for x in tok[2 + n1:2 + n1 + n2])
+        except (ValueError, IndexError):
+            raise KzgError("InvalidTrustedSetup", "Invalid trusted setup")
+        if len(g1) != n1 * 48 or len(g2) != n2 * 96 or n2 < 2:
+            raise KzgError("InvalidTrustedSetup", "Invalid trusted setup")
+        return cls(g1, g2)
+
+    def context(self, device=0):
+        with self._lock:
+            if device not in self._ctx:
+                lib = Library.get().dll
+                h = C.c_void_p()
+                rc = lib.kzgb200_create(C.byref(h), device, self.g2_monomial_bytes[:192], 192)
+                if rc:
+                    _raise(rc, msg="kzgb200_create failed (rc=%d): no usable sm_100 GPU or invalid setup" % rc if rc == 2 else None)
+                self._ctx[device] = h
+            return self._ctx[device]
+
+    def close(self):
+        with self._lock:
+            for h in self._ctx.values():
+                Library.get().dll.kzgb200_destroy(h)
+            self._ctx = {}
+
+
+def _b(x, size, what):
+    b = x.as_slice() if isinstance(x, _BytesN) else bytes(x)
+    if len(b) != size:
+        raise KzgError("InvalidBytesLength", "Invalid slice length")
+    return b
+
+
+class KzgProof:
+    """src/kzg_proof.rs:350-526."""
+
+    @staticmethod
+    def verify_kzg_proof(commitment_bytes, z_bytes, y_bytes, proof_bytes, kzg_settings, device=0):
+        c, z = _b(commitment_bytes, 48, "commitment"), _b(z_bytes, 32, "z")
+        y, p = _b(y_bytes, 32, "y"), _b(proof_bytes, 48, "proof")
+        ctx, ok = kzg_settings.context(device), C.c_int(0)
+        rc = Library.get().dll.kzgb200_verify_kzg_proof(ctx, c, z, y, p, C.byref(ok))
+        if rc:
+            _raise(rc, ctx)
+        return bool(ok.value)
+
+    @staticmethod
+    def verify_blob_kzg_proof(blob, commitment_bytes, proof_bytes, kzg_settings, device=0, want_zy=False):
+        b, c, p = _b(blob, BYTES_PER_BLOB, "blob"), _b(commitment_bytes, 48, "commitment"), _b(proof_bytes, 48, "proof")
+        ctx, ok = kzg_settings.context(device), C.c_int(0)
+        z, y = C.create_string_buffer(32), C.create_string_buffer(32)
+        rc = Library.get().dll.kzgb200_verify_blob_kzg_proof(ctx, b, c, p, C.byref(ok), z, y)
+        if rc:
+            _raise(rc, ctx)
+        return (bool(ok.value), z.raw, y.raw) if want_zy else bool(ok.value)
+
+    @staticmethod
+    def verify_blob_kzg_proof_batch(blobs, commitments_bytes, proofs_bytes, kzg_settings, device=0, want_zy=False):
+        """blobs / commitments_bytes / proofs_bytes: sequences (the reference's three Vecs)."""
+        bl = [_b(x, BYTES_PER_BLOB, "blob") for x in blobs]
+        cs = [_b(x, 48, "commitment") for x in commitments_bytes]
+        ps = [_b(x, 48, "proof") for x in proofs_bytes]
+        return KzgProof.verify_blob_kzg_proof_batch_raw(b"".join(bl), len(bl), b"".join(cs), len(cs), b"".join(ps), len(ps),
+                                                        kzg_settings, device, want_zy)
+
+    @staticmethod
+    def verify_blob_kzg_proof_batch_raw(blobs, n_blobs, commitments, n_commitments, proofs, n_proofs, kzg_settings,
+                                        device=0, want_zy=False):
+        """Contiguous host buffers (bytes / ctypes arrays / integer addresses), exactly what the C ABI takes."""
+        ctx, ok = kzg_settings.context(device), C.c_int(0)
+        z = C.create_string_buffer(32 * max(n_blobs, 1)) if want_zy else None
+        y = C.create_string_buffer(32 * max(n_blobs, 1)) if want_zy else None
+        rc = Library.get().dll.kzgb200_verify_blob_kzg_proof_batch(ctx, _ptr(blobs), n_blobs, _ptr(commitments), n_commitments,
+                                                                   _ptr(proofs), n_proofs, C.byref(ok), z, y)
+        if rc:
+            _raise(rc, ctx, "Invalid commitments length" if rc == 3 and n_blobs != n_commitments else
+                   ("Invalid proofs length" if rc == 3 else None))
+        if want_zy:
+            zs = [z.raw[32 * i:32 * i + 32] for i in range(n_blobs)]
+            ys = [y.raw[32 * i:32 * i + 32] for i in range(n_blobs)]
+            return bool(ok.value), zs, ys
+        return bool(ok.value)
+
+    @staticmethod
+    def verify_kzg_proof_many(commitments, zs, ys, proofs, m, kzg_settings, device=0):
+        """m independent (C, z, y, proof) tuples in contiguous buffers -> bytes of m verdicts (0/1/2=BadArgs)."""
+        ctx = kzg_settings.context(device)
+        out = C.create_string_buffer(max(m, 1))
+        rc = Library.get().dll.kzgb200_verify_kzg_proof_many(ctx, _ptr(commitments), _ptr(zs), _ptr(ys), _ptr(proofs), m, out)
+        if rc:
+            _raise(rc, ctx)
+        return out.raw[:m]
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    if isinstance(x, (bytes, bytearray)):
+        return C.cast(C.c_char_p(bytes(x)), C.c_void_p) if isinstance(x, bytes) else C.cast((C.c_char * len(x)).from_buffer(x), C.c_void_p)
+    return C.cast(x, C.c_void_p)

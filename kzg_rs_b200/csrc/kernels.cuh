@@ -1,0 +1,355 @@
+// CUDA kernels of the kzg-rs verification hot path for sm_100a (K1..K8 of SURVEY.md section 2.1).
+// Included only by kzgb200.cu (single translation unit).
+#pragma once
+#include <cuda_runtime.h>
+#include "sha256.cuh"
+#include "verify.cuh"
+
+namespace kzgb200 {
+
+constexpr int kFieldElementsPerBlob = 4096;       // reference src/consts.rs:7
+constexpr int kBytesPerBlob = 4096 * 32;          // src/consts.rs:8
+constexpr uint32_t kErrBlob = 1, kErrCommitment = 2, kErrProof = 4, kErrScalar = 8;
+// canonical (non-Montgomery) z_i, y_i; the memory image is 2 x 32 little-endian bytes, which is exactly what
+// the batch transcript hashes (reference src/kzg_proof.rs:320-328) and what ranks exchange
+struct ZY { Fr z, y; };
+
+// Device-resident trusted-setup tables (K8; replaces KzgSettings::load_trusted_setup_file,
+// reference src/trusted_setup.rs:94-98 and build.rs:131-170).
+struct DeviceTables {
+    // twiddle[g] = roots_of_unity[2g] = omega^bitrev12(2g), Montgomery form.  In the bit-reversed domain the
+    // group of 2^(k+1) consecutive points starting at index a has prod (z - w_i) = z^(2^(k+1)) - w_a^(2^(k+1)),
+    // and w_a^(2^k) = roots_of_unity[2g] for g = a >> (k+1), independent of the level k.
+    Fr twiddle[2048];
+    PairingTables pairing;
+    uint32_t setup_ok;
+};
+
+// ------------------------------------------------------------------------------------------------ K8
+__global__ void setup_tables_kernel(DeviceTables* T, const uint8_t* g2_points /* 2 x 96 B: g2[0], g2[1] */) {
+    int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < 2048) {
+        // bitrev12(2g)
+        uint32_t i = 2u * tid, e = 0;
+        for (int b = 0; b < 12; b++) e |= ((i >> b) & 1u) << (11 - b);
+        const uint32_t om[8] = KZG_FR_OMEGA_M;
+        uint32_t ee[1] = {e};
+        T->twiddle[tid] = fr_const(om).pow(ee, 12);
+    }
+    if (tid == 2048) {
+        G2Affine gen, tau;
+        bool ok = g2_from_compressed_unchecked(gen, g2_points) && g2_from_compressed_unchecked(tau, g2_points + 96);
+        ok = ok && !gen.inf && !tau.inf;
+        if (ok) {
+            prepare_g2(T->pairing.g2_gen, gen);
+            prepare_g2(T->pairing.tau_g2, tau);
+        }
+        T->setup_ok = ok ? 1u : 0u;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K2
+// Fiat-Shamir challenge (reference src/kzg_proof.rs:46-72): z = SHA-256("FSBLOBVERIFY_V1_" | u64be 0 |
+// u64be 4096 | blob | commitment) mod q.  One thread per blob: the 2050-block chain is serial per blob, so
+// throughput comes from hashing many blobs at once.  The commitment bytes hashed are the caller's: for
+// every encoding from_compressed accepts, to_compressed(from_compressed(b)) == b.
+__global__ void __launch_bounds__(64) challenge_kernel(const uint8_t* __restrict__ blobs, const uint8_t* __restrict__ commitments,
+                                                       int n, Fr* __restrict__ z_mont, ZY* __restrict__ zy) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4* bp = reinterpret_cast<const uint4*>(blobs + (size_t)i * kBytesPerBlob);
+    const uint32_t* cp = reinterpret_cast<const uint32_t*>(commitments + (size_t)i * 48);
+    uint32_t st[8], w[16];
+    sha256_init(st);
+    // block 0: domain | 0 | 4096 | blob[0..32)
+    w[0] = 0x4653424c; w[1] = 0x4f425645; w[2] = 0x52494659; w[3] = 0x5f56315f;   // "FSBLOBVERIFY_V1_"
+    w[4] = 0; w[5] = 0; w[6] = 0; w[7] = 4096;
+    {
+        uint4 a = __ldg(bp), b = __ldg(bp + 1);
+        w[8] = sha_bswap(a.x); w[9] = sha_bswap(a.y); w[10] = sha_bswap(a.z); w[11] = sha_bswap(a.w);
+        w[12] = sha_bswap(b.x); w[13] = sha_bswap(b.y); w[14] = sha_bswap(b.z); w[15] = sha_bswap(b.w);
+    }
+    sha256_compress(st, w);
+    // blocks 1..2047: blob[64k-32 .. 64k+32)
+    for (int k = 1; k < 2048; k++) {
+        const uint4* p = bp + (4 * k - 2);
+        uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+        w[0] = sha_bswap(a.x); w[1] = sha_bswap(a.y); w[2] = sha_bswap(a.z); w[3] = sha_bswap(a.w);
+        w[4] = sha_bswap(b.x); w[5] = sha_bswap(b.y); w[6] = sha_bswap(b.z); w[7] = sha_bswap(b.w);
+        w[8] = sha_bswap(c.x); w[9] = sha_bswap(c.y); w[10] = sha_bswap(c.z); w[11] = sha_bswap(c.w);
+        w[12] = sha_bswap(d.x); w[13] = sha_bswap(d.y); w[14] = sha_bswap(d.z); w[15] = sha_bswap(d.w);
+        sha256_compress(st, w);
+    }
+    // block 2048: blob[131040..131072) | commitment[0..32)
+    {
+        uint4 a = __ldg(bp + 8190), b = __ldg(bp + 8191);
+        w[0] = sha_bswap(a.x); w[1] = sha_bswap(a.y); w[2] = sha_bswap(a.z); w[3] = sha_bswap(a.w);
+        w[4] = sha_bswap(b.x); w[5] = sha_bswap(b.y); w[6] = sha_bswap(b.z); w[7] = sha_bswap(b.w);
+        for (int j = 0; j < 8; j++) w[8 + j] = sha_bswap(__ldg(cp + j));
+    }
+    sha256_compress(st, w);
+    // block 2049: commitment[32..48) | 0x80 | 0.. | bit length 131152*8
+    for (int j = 0; j < 4; j++) w[j] = sha_bswap(__ldg(cp + 8 + j));
+    w[4] = 0x80000000u;
+    for (int j = 5; j < 15; j++) w[j] = 0;
+    w[15] = 131152u * 8u;
+    sha256_compress(st, w);
+    // scalar_from_bytes_unchecked (kzg_proof.rs:74-91): big-endian 256-bit value reduced mod q
+    Fr raw;
+    for (int j = 0; j < 8; j++) raw.l[j] = st[7 - j];
+    Fr zm = Fr::from_raw(raw);
+    z_mont[i] = zm;
+    zy[i].z = zm.to_raw();
+}
+
+// ------------------------------------------------------------------------------------------------ K1+K3
+// Barycentric evaluation y = p(z) (reference src/kzg_proof.rs:94-133 with batch_inversion :155-201), fused
+// with the canonicity check of Blob::as_polynomial (src/dtypes.rs:48-57).
+//
+// Inversion-free form.  With S = sum_i f_i / (z - w_i) = N / D over the common denominator
+// D = prod (z - w_i) = z^4096 - 1, the reference's value is
+//     y = (z^n - 1)/n * sum_i f_i w_i / (z - w_i) = (z * N - (z^n - 1) * sum_i f_i) / n        (w/(z-w) = z/(z-w) - 1)
+// and N is built by a binary tree over the bit-reversed domain, where the two halves of a node have
+// denominators z^(2^k) -+ w:   N = z^(2^k) (Na + Nb) + w (Na - Nb)   -- one fused dual Montgomery product.
+// 4095 dual products per blob instead of ~5*4096 products + an inversion, no branch for z in the domain
+// (then D = 0 and the formula collapses to f_k exactly), and the result is the same canonical field element.
+// Blob elements stay in normal form: MontMul(aR, f) = a f.
+constexpr int kEvalThreads = 128;
+constexpr int kLeavesPerThread = kFieldElementsPerBlob / kEvalThreads;  // 32
+
+__device__ __forceinline__ Fr load_fe_be(const uint4* p) {
+    uint4 hi = __ldg(p), lo = __ldg(p + 1);   // 32 big-endian bytes: hi holds the most significant 16
+    Fr f;
+    f.l[7] = sha_bswap(hi.x); f.l[6] = sha_bswap(hi.y); f.l[5] = sha_bswap(hi.z); f.l[4] = sha_bswap(hi.w);
+    f.l[3] = sha_bswap(lo.x); f.l[2] = sha_bswap(lo.y); f.l[1] = sha_bswap(lo.z); f.l[0] = sha_bswap(lo.w);
+    return f;
+}
+
+__global__ void __launch_bounds__(kEvalThreads) eval_kernel(const uint8_t* __restrict__ blobs, int n, const Fr* __restrict__ z_mont,
+                                                            const DeviceTables* __restrict__ T, ZY* __restrict__ zy,
+                                                            uint32_t* __restrict__ status) {
+    __shared__ Fr s_pow[13];              // z^(2^k), Montgomery
+    __shared__ Fr s_n[kEvalThreads];
+    __shared__ Fr s_f[kEvalThreads];
+    int blob = blockIdx.x, t = threadIdx.x;
+    if (blob >= n) return;
+    if (t == 0) {
+        Fr s = z_mont[blob];
+        s_pow[0] = s;
+        for (int k = 1; k <= 12; k++) { s = s.mul_inl(s); s_pow[k] = s; }
+    }
+    const uint4* base = reinterpret_cast<const uint4*>(blobs + (size_t)blob * kBytesPerBlob) + (size_t)t * kLeavesPerThread * 2;
+    // in-thread subtree over 32 consecutive leaves, binary-counter stack
+    Fr stack[5];
+    Fr fsum = Fr::zero();
+    bool bad = false;
+    __syncthreads();
+#pragma unroll 1
+    for (int j = 0; j < kLeavesPerThread; j++) {
+        Fr cur = load_fe_be(base + 2 * j);
+        bad |= cur.geq_modulus();
+        fsum = fsum.add_inl(cur);
+        int leaf = t * kLeavesPerThread + j, k = 0;
+#pragma unroll 1
+        for (; (j >> k) & 1; k++) {
+            // merge stack[k] (left, earlier leaves) with cur (right) at level k
+            Fr w = T->twiddle[leaf >> (k + 1)];
+            Fr sum = stack[k].add_inl(cur), dif = stack[k].sub_inl(cur);
+            cur = Fr::mul_dual_inl(s_pow[k], sum, w, dif);
+        }
+        stack[k < 5 ? k : 0] = cur;   // k = trailing ones of j; j == 31 leaves the finished subtree in stack[0]
+    }
+    s_n[t] = stack[0];
+    s_f[t] = fsum;
+    __syncthreads();
+    // cross-thread levels 5..11
+    for (int k = 5; k < 12; k++) {
+        int span = 1 << (k - 5);
+        if ((t & (2 * span - 1)) == 0) {
+            Fr a = s_n[t], b = s_n[t + span];
+            Fr w = T->twiddle[(t * kLeavesPerThread) >> (k + 1)];
+            s_n[t] = Fr::mul_dual_inl(s_pow[k], a.add_inl(b), w, a.sub_inl(b));
+            s_f[t] = s_f[t].add_inl(s_f[t + span]);
+        }
+        __syncthreads();
+    }
+    if (bad) atomicOr(&status[blob], kErrBlob);
+    if (t == 0) {
+        const uint32_t invn[8] = KZG_FR_INV4096_M;
+        Fr zn1 = s_pow[12].sub_inl(Fr::one());                              // z^4096 - 1 (Montgomery)
+        Fr num = s_pow[0].mul_inl(s_n[0]).sub_inl(zn1.mul_inl(s_f[0]));    // z N - (z^n - 1) sum f   (normal form)
+        zy[blob].y = fr_const(invn).mul_inl(num);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K4
+// G1 decompression + subgroup check for commitments and proofs (reference src/kzg_proof.rs:17-25).
+// One thread per point; points [0,n) are commitments, [n,2n) proofs.
+__global__ void __launch_bounds__(128) g1_parse_kernel(const uint8_t* __restrict__ commitments, const uint8_t* __restrict__ proofs, int n,
+                                                       G1Affine* __restrict__ C, G1Affine* __restrict__ P, uint32_t* __restrict__ status) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * n) return;
+    bool is_proof = i >= n;
+    int j = is_proof ? i - n : i;
+    const uint8_t* src = (is_proof ? proofs : commitments) + (size_t)j * 48;
+    uint8_t b[48];
+    for (int k = 0; k < 12; k++) {
+        uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(src) + k);
+        b[4 * k] = (uint8_t)v; b[4 * k + 1] = (uint8_t)(v >> 8); b[4 * k + 2] = (uint8_t)(v >> 16); b[4 * k + 3] = (uint8_t)(v >> 24);
+    }
+    G1Affine pt;
+    bool ok = g1_from_compressed(pt, b, true);
+    (is_proof ? P : C)[j] = pt;
+    if (!ok) atomicOr(&status[j], is_proof ? kErrProof : kErrCommitment);
+}
+
+// ------------------------------------------------------------------------------------------------ K5
+// Batch challenge r (reference src/kzg_proof.rs:291-348): SHA-256 over
+//   "RCKZGBATCH___V1_" | u64be 4096 | u64be n | for each i: C_i[48] | z_i LE[32] | y_i LE[32] | pi_i[48]
+// reduced mod q.  The hash is one serial chain over all blobs of the batch (every rank's), so it is a
+// single-thread kernel; the message bytes are produced on the fly from the device-resident pieces.
+__device__ __forceinline__ uint8_t transcript_byte(size_t pos, uint64_t n, const uint8_t* C, const ZY* zy, const uint8_t* P) {
+    if (pos < 32) {
+        const char* dom = "RCKZGBATCH___V1_";
+        if (pos < 16) return (uint8_t)dom[pos];
+        if (pos < 24) return (uint8_t)(4096ull >> (8 * (23 - pos)));
+        return (uint8_t)(n >> (8 * (31 - pos)));
+    }
+    size_t q = (pos - 32) / 160, o = (pos - 32) % 160;
+    if (o < 48) return C[q * 48 + o];
+    if (o < 80) { size_t k = o - 48; return (uint8_t)(zy[q].z.l[k >> 2] >> (8 * (k & 3))); }
+    if (o < 112) { size_t k = o - 80; return (uint8_t)(zy[q].y.l[k >> 2] >> (8 * (k & 3))); }
+    return P[q * 48 + (o - 112)];
+}
+__global__ void transcript_kernel(const uint8_t* __restrict__ commitments, const ZY* __restrict__ zy,
+                                  const uint8_t* __restrict__ proofs, uint64_t n, Fr* __restrict__ r_mont) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    size_t len = 32 + (size_t)n * 160;
+    uint32_t st[8], w[16];
+    sha256_init(st);
+    size_t nblk = (len + 9 + 63) / 64;
+    for (size_t blk = 0; blk < nblk; blk++) {
+        for (int j = 0; j < 16; j++) {
+            uint32_t v = 0;
+            for (int b = 0; b < 4; b++) {
+                size_t pos = blk * 64 + 4 * j + b;
+                uint8_t byte = pos < len ? transcript_byte(pos, n, commitments, zy, proofs) : (pos == len ? 0x80 : 0);
+                v = (v << 8) | byte;
+            }
+            w[j] = v;
+        }
+        if (blk == nblk - 1) { w[14] = (uint32_t)(((uint64_t)len * 8) >> 32); w[15] = (uint32_t)((uint64_t)len * 8); }
+        sha256_compress(st, w);
+    }
+    Fr raw;
+    for (int j = 0; j < 8; j++) raw.l[j] = st[7 - j];
+    *r_mont = Fr::from_raw(raw);
+}
+
+// ------------------------------------------------------------------------------------------------ K6
+// Random linear combination (reference src/kzg_proof.rs:399-433), regrouped so that it needs no per-blob
+// [y_i]G:   A = sum r_i pi_i ,  B = sum (r_i C_i + (r_i z_i) pi_i) - [sum r_i y_i] G ,  r_i = r^(offset+i).
+// v1: one thread per blob does its scalar multiplications (Shamir's trick for the pair), results are then
+// tree-summed by pair_sum_kernel.
+struct LincombTerm { G1 a, b; };
+__global__ void __launch_bounds__(128) lincomb_terms_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P,
+                                                            const Fr* __restrict__ z_mont, const ZY* __restrict__ zy,
+                                                            const Fr* __restrict__ r_mont, uint64_t offset, int n,
+                                                            LincombTerm* __restrict__ terms, Fr* __restrict__ ry) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t e = offset + (uint64_t)i;
+    uint32_t ee[2] = {(uint32_t)e, (uint32_t)(e >> 32)};
+    Fr ri = r_mont->pow(ee, 64);              // r^(offset+i), Montgomery   (compute_powers, kzg_proof.rs:279-289)
+    Fr ri_raw = ri.to_raw();
+    Fr rz_raw = (ri * z_mont[i]).to_raw();    // r_i z_i   (kzg_proof.rs:425)
+    ry[i] = ri * zy[i].y;                     // r_i y_i in normal form
+    G1Affine c = C[i], p = P[i];
+    G1 cp = G1::from_affine(c).add_mixed(p);  // C_i + pi_i for the joint ladder
+    G1 a = G1::identity(), b = G1::identity();
+    for (int bit = 254; bit >= 0; bit--) {
+        a = a.dbl(); b = b.dbl();
+        uint32_t br = (ri_raw.l[bit >> 5] >> (bit & 31)) & 1, bz = (rz_raw.l[bit >> 5] >> (bit & 31)) & 1;
+        if (br) a = a.add_mixed(p);
+        if (br && bz) b = b.add(cp); else if (br) b = b.add_mixed(c); else if (bz) b = b.add_mixed(p);
+    }
+    terms[i].a = a; terms[i].b = b;
+}
+// terms[i] += terms[i + half] for i < half (and the Fr sums likewise)
+__global__ void __launch_bounds__(128) pair_sum_kernel(LincombTerm* __restrict__ terms, Fr* __restrict__ ry, int count, int half) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= half || i + half >= count) return;
+    terms[i].a = terms[i].a.add(terms[i + half].a);
+    terms[i].b = terms[i].b.add(terms[i + half].b);
+    ry[i] = ry[i] + ry[i + half];
+}
+// per-rank partial result exchanged between ranks (the payload of the allgather)
+struct Partial {
+    G1 a, b;          // sum r_i pi_i ; sum (r_i C_i + r_i z_i pi_i)
+    Fr ry;            // sum r_i y_i (normal form)
+    uint32_t err;     // OR of the per-blob error flags of this rank
+    uint32_t pad[7];
+};
+__global__ void finish_partial_kernel(const LincombTerm* __restrict__ terms, const Fr* __restrict__ ry, const uint32_t* __restrict__ status, int n,
+                                      Partial* __restrict__ out) {
+    __shared__ uint32_t s_err;
+    if (threadIdx.x == 0) s_err = 0;
+    __syncthreads();
+    uint32_t e = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) e |= status[i];
+    if (e) atomicOr(&s_err, e);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        out->a = terms[0].a; out->b = terms[0].b; out->ry = ry[0]; out->err = s_err;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K7
+// Final pairing check over the gathered per-rank partials (reference src/kzg_proof.rs:436-441):
+//   e(sum_k A_k, [tau]G2) == e(sum_k B_k - [sum_k s_k]G, G2).
+// result: 0 = false, 1 = true, 2 = BadArgs (some rank flagged an unparsable input)
+__global__ void batch_final_kernel(const Partial* __restrict__ parts, int nparts, const DeviceTables* __restrict__ T, uint32_t* __restrict__ result) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    G1 A = G1::identity(), B = G1::identity();
+    Fr s = Fr::zero();
+    uint32_t err = 0;
+    for (int k = 0; k < nparts; k++) { A = A.add(parts[k].a); B = B.add(parts[k].b); s = s + parts[k].ry; err |= parts[k].err; }
+    if (err) { result[0] = kBadArgs; result[1] = err; return; }
+    B = B.add(scalar_mul_affine(g1_generator(), s.l, 255).neg());
+    G1Affine Aa = g1_to_affine(A), Ba = g1_to_affine(B);
+    if (!Aa.inf) Aa.y = Aa.y.neg();
+    result[0] = pairing_product_is_one(Ba, T->pairing.g2_gen, Aa, T->pairing.tau_g2) ? kTrue : kFalse;
+    result[1] = 0;
+}
+// Single-blob path (reference src/kzg_proof.rs:446-470 -> verify_kzg_proof_impl :203-223) after z, y and the
+// points have been produced by the kernels above.
+__global__ void single_final_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P, const ZY* __restrict__ zy,
+                                    const uint32_t* __restrict__ status,
+                                    const DeviceTables* __restrict__ T, uint32_t* __restrict__ result) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    if (status[0]) { result[0] = kBadArgs; result[1] = status[0]; return; }
+    G1Affine X = kzg_lhs_point(C[0], zy[0].z, zy[0].y, P[0]);
+    result[0] = kzg_pairing_check(X, P[0], &T->pairing) ? kTrue : kFalse;
+    result[1] = 0;
+}
+// m independent verify_kzg_proof tuples, one thread each (reference src/kzg_proof.rs:353-397)
+__global__ void __launch_bounds__(64) verify_many_kernel(const uint8_t* __restrict__ c, const uint8_t* __restrict__ z, const uint8_t* __restrict__ y,
+                                                         const uint8_t* __restrict__ p, size_t m, const DeviceTables* __restrict__ T,
+                                                         uint8_t* __restrict__ verdicts) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    uint8_t cb[48], zb[32], yb[32], pb[48];
+    for (int k = 0; k < 48; k++) { cb[k] = c[i * 48 + k]; pb[k] = p[i * 48 + k]; }
+    for (int k = 0; k < 32; k++) { zb[k] = z[i * 32 + k]; yb[k] = y[i * 32 + k]; }
+    verdicts[i] = verify_kzg_proof_one(cb, zb, yb, pb, &T->pairing);
+}
+// z / y as 32-byte big-endian strings for the caller (intermediates are part of the parity contract)
+__global__ void export_scalars_kernel(const ZY* __restrict__ zy, int n, uint8_t* __restrict__ z_out, uint8_t* __restrict__ y_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (z_out) limbs_to_be32(z_out + (size_t)i * 32, zy[i].z.l);
+    if (y_out) limbs_to_be32(y_out + (size_t)i * 32, zy[i].y.l);
+}
+// z_mont from gathered canonical scalars is not needed: phase 2 only uses this rank's own z_mont.
+
+}  // namespace kzgb200
