@@ -94,6 +94,19 @@ int kzgb200_shard_lincomb(kzgb200_ctx* ctx, size_t global_offset, uint8_t* d_par
 /* final: sum the gathered partials (n_ranks x KZGB200_PARTIAL_BYTES) and run the single pairing check. */
 int kzgb200_shard_finalize(kzgb200_ctx* ctx, const uint8_t* d_partials, size_t n_ranks, int* ok);
 
+/* ---- harness (test / bench data; kzg-rs itself has no commit/prove path) ---------------------------------
+ * Fills device buffers with n synthetic blobs (evaluation form of seeded random polynomials of degree <
+ * `degree`, 2 <= degree <= 16) and their valid commitments and proofs over the trusted setup whose
+ * [tau^j]G1, j < degree, are given compressed in tau_powers48 (host, degree x 48 bytes). */
+int kzgb200_harness_generate(kzgb200_ctx* ctx, uint64_t seed, size_t n, int degree, const uint8_t* tau_powers48,
+                             uint8_t* d_blobs, uint8_t* d_commitments, uint8_t* d_proofs);
+/* per-phase device timing of single-GPU batch calls (CUDA events on the context stream).  out7 = milliseconds of
+ * {parse G1, challenge, evaluate, transcript r, lincomb terms, reduce, final pairing} of the last call. */
+int kzgb200_set_profiling(kzgb200_ctx* ctx, int on);
+int kzgb200_get_phase_ms(kzgb200_ctx* ctx, float* out7);
+/* the cudaStream_t all work of this context is issued on (for CUDA-event timing by the caller) */
+void* kzgb200_stream(kzgb200_ctx* ctx);
+
 /* pinned host memory helpers for callers that want full-rate host->device copies */
 void* kzgb200_alloc_pinned(size_t bytes);
 void kzgb200_free_pinned(void* p);

@@ -72,6 +72,11 @@ class Library:
         d.kzgb200_shard_challenge.argtypes = [p, p, p, p, sz]
         d.kzgb200_shard_lincomb.argtypes = [p, sz, p]
         d.kzgb200_shard_finalize.argtypes = [p, p, sz, ip]
+        d.kzgb200_harness_generate.argtypes = [p, C.c_uint64, sz, C.c_int, C.c_char_p, p, p, p]
+        d.kzgb200_set_profiling.argtypes = [p, C.c_int]
+        d.kzgb200_get_phase_ms.argtypes = [p, C.POINTER(C.c_float)]
+        d.kzgb200_stream.argtypes = [p]
+        d.kzgb200_stream.restype = p
         d.kzgb200_alloc_pinned.argtypes = [sz]
         d.kzgb200_alloc_pinned.restype = p
         d.kzgb200_free_pinned.argtypes = [p]

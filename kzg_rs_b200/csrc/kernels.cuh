@@ -221,29 +221,95 @@ __device__ __forceinline__ uint8_t transcript_byte(size_t pos, uint64_t n, const
     if (o < 112) { size_t k = o - 80; return (uint8_t)(zy[q].y.l[k >> 2] >> (8 * (k & 3))); }
     return P[q * 48 + (o - 112)];
 }
-__global__ void transcript_kernel(const uint8_t* __restrict__ commitments, const ZY* __restrict__ zy,
-                                  const uint8_t* __restrict__ proofs, uint64_t n, Fr* __restrict__ r_mont) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+// K5a (parallel): one thread per 64-byte block of the transcript builds the block from the device-resident
+// pieces, expands the SHA-256 message schedule and stores W[t] + K[t], t < 64 -- everything about a block that
+// does not depend on the chaining value.
+__global__ void __launch_bounds__(128) transcript_schedule_kernel(const uint8_t* __restrict__ commitments, const ZY* __restrict__ zy,
+                                                                  const uint8_t* __restrict__ proofs, uint64_t n, uint32_t* __restrict__ wk) {
     size_t len = 32 + (size_t)n * 160;
-    uint32_t st[8], w[16];
-    sha256_init(st);
     size_t nblk = (len + 9 + 63) / 64;
-    for (size_t blk = 0; blk < nblk; blk++) {
-        for (int j = 0; j < 16; j++) {
-            uint32_t v = 0;
-            for (int b = 0; b < 4; b++) {
-                size_t pos = blk * 64 + 4 * j + b;
-                uint8_t byte = pos < len ? transcript_byte(pos, n, commitments, zy, proofs) : (pos == len ? 0x80 : 0);
-                v = (v << 8) | byte;
-            }
-            w[j] = v;
+    size_t blk = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (blk >= nblk) return;
+    uint32_t w[16];
+    for (int j = 0; j < 16; j++) {
+        uint32_t v = 0;
+        for (int b = 0; b < 4; b++) {
+            size_t pos = blk * 64 + 4 * j + b;
+            uint8_t byte = pos < len ? transcript_byte(pos, n, commitments, zy, proofs) : (pos == len ? 0x80 : 0);
+            v = (v << 8) | byte;
         }
-        if (blk == nblk - 1) { w[14] = (uint32_t)(((uint64_t)len * 8) >> 32); w[15] = (uint32_t)((uint64_t)len * 8); }
-        sha256_compress(st, w);
+        w[j] = v;
     }
-    Fr raw;
-    for (int j = 0; j < 8; j++) raw.l[j] = st[7 - j];
-    *r_mont = Fr::from_raw(raw);
+    if (blk == nblk - 1) { w[14] = (uint32_t)(((uint64_t)len * 8) >> 32); w[15] = (uint32_t)((uint64_t)len * 8); }
+    uint4* dst = reinterpret_cast<uint4*>(wk + blk * 64);
+#pragma unroll
+    for (int i = 0; i < 64; i += 4) {
+        uint32_t o[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            int t = i + u;
+            if (t >= 16) {
+                uint32_t w15 = w[(t + 1) & 15], w2 = w[(t + 14) & 15];
+                uint32_t s0 = sha_rotr(w15, 7) ^ sha_rotr(w15, 18) ^ (w15 >> 3);
+                uint32_t s1 = sha_rotr(w2, 17) ^ sha_rotr(w2, 19) ^ (w2 >> 10);
+                w[t & 15] = w[t & 15] + s0 + w[(t + 9) & 15] + s1;
+            }
+            o[u] = w[t & 15] + sha_k(t);
+        }
+        dst[i / 4] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+// K5b (serial): the chaining part, 64 rounds per block over the precomputed W+K.  One warp: the lanes stage
+// the next blocks into shared memory with coalesced loads, every lane then runs the same rounds on
+// broadcast reads (SIMT makes the redundant lanes free); lane 0 publishes r.
+constexpr int kTranscriptStage = 8;   // blocks per shared-memory stage
+__global__ void __launch_bounds__(32) transcript_chain_kernel(const uint32_t* __restrict__ wk, uint64_t n, Fr* __restrict__ r_mont) {
+    __shared__ uint4 stage[2][kTranscriptStage * 16];
+    size_t len = 32 + (size_t)n * 160;
+    size_t nblk = (len + 9 + 63) / 64;
+    int lane = threadIdx.x;
+    const uint4* src = reinterpret_cast<const uint4*>(wk);
+    uint32_t st[8];
+    sha256_init(st);
+    size_t nstage = (nblk + kTranscriptStage - 1) / kTranscriptStage;
+    auto load_stage = [&](size_t sidx, int buf) {
+        size_t base = sidx * kTranscriptStage * 16, total = nblk * 16;
+#pragma unroll
+        for (int k = 0; k < kTranscriptStage * 16 / 32; k++) {
+            size_t idx = base + k * 32 + lane;
+            stage[buf][k * 32 + lane] = idx < total ? __ldg(src + idx) : make_uint4(0, 0, 0, 0);
+        }
+    };
+    load_stage(0, 0);
+    __syncwarp();
+    for (size_t sidx = 0; sidx < nstage; sidx++) {
+        int buf = sidx & 1;
+        if (sidx + 1 < nstage) load_stage(sidx + 1, buf ^ 1);
+        size_t blocks_here = nblk - sidx * kTranscriptStage;
+        if (blocks_here > kTranscriptStage) blocks_here = kTranscriptStage;
+        for (size_t bi = 0; bi < blocks_here; bi++) {
+            const uint4* wv = &stage[buf][bi * 16];
+            uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                uint4 q = wv[i];
+                uint32_t kw[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    uint32_t t1 = h + (sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25)) + ((e & f) ^ (~e & g)) + kw[u];
+                    uint32_t t2 = (sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+                    h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+                }
+            }
+            st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        Fr raw;
+        for (int j = 0; j < 8; j++) raw.l[j] = st[7 - j];
+        *r_mont = Fr::from_raw(raw);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ K6
@@ -351,5 +417,88 @@ __global__ void export_scalars_kernel(const ZY* __restrict__ zy, int n, uint8_t*
     if (y_out) limbs_to_be32(y_out + (size_t)i * 32, zy[i].y.l);
 }
 // z_mont from gathered canonical scalars is not needed: phase 2 only uses this rank's own z_mont.
+
+
+// ================================================================================================ harness
+// Workload generator (harness side; kzg-rs has no commit/prove path).  Blob b is the evaluation form of a
+// random polynomial p_b of degree < D over the bit-reversed 4096-point domain; its commitment and proof are
+// C = sum_j c_j [tau^j]G1 and pi = sum_j q_j [tau^j]G1 with q = (p - p(z)) / (X - z) by synthetic division,
+// over the mainnet setup's [tau^j]G1 (kzg_rs_b200/data/tau_powers_g1.bin).  The verifier never sees the
+// structure: it does the same work as for any blob.
+constexpr int kHarnessMaxDegree = 16;
+__device__ __forceinline__ uint64_t splitmix64(uint64_t& s) {
+    uint64_t z = (s += 0x9e3779b97f4a7c15ull);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+// coefficient j of blob b, Montgomery form of a uniform 256-bit value mod q
+__device__ __noinline__ Fr harness_coeff(uint64_t seed, uint64_t blob, int j) {
+    uint64_t s = seed ^ ((blob * kHarnessMaxDegree + (uint64_t)j) * 0xd1342543de82ef95ull);
+    Fr raw;
+    for (int k = 0; k < 4; k++) { uint64_t v = splitmix64(s); raw.l[2 * k] = (uint32_t)v; raw.l[2 * k + 1] = (uint32_t)(v >> 32); }
+    return Fr::from_raw(raw);
+}
+__device__ __noinline__ void g1_to_compressed(uint8_t* out, const G1Affine& a) {
+    if (a.inf) { for (int i = 0; i < 48; i++) out[i] = 0; out[0] = 0xc0; return; }
+    Fp x = a.x.to_raw();
+    for (int i = 0; i < 12; i++) {
+        uint8_t* p = out + 4 * (11 - i);
+        p[0] = (uint8_t)(x.l[i] >> 24); p[1] = (uint8_t)(x.l[i] >> 16); p[2] = (uint8_t)(x.l[i] >> 8); p[3] = (uint8_t)x.l[i];
+    }
+    out[0] |= 0x80;
+    if (fp_lex_largest(a.y)) out[0] |= 0x20;
+}
+__global__ void harness_parse_points_kernel(const uint8_t* bytes, int n, G1Affine* out, uint32_t* bad) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t b[48];
+    for (int k = 0; k < 48; k++) b[k] = bytes[i * 48 + k];
+    if (!g1_from_compressed(out[i], b, true)) atomicOr(bad, 1u);
+}
+__global__ void __launch_bounds__(128) harness_blob_kernel(uint64_t seed, int n, int D, const DeviceTables* __restrict__ T, uint8_t* __restrict__ blobs) {
+    __shared__ Fr coef[kHarnessMaxDegree];
+    int blob = blockIdx.x, t = threadIdx.x;
+    if (blob >= n) return;
+    if (t < D) coef[t] = harness_coeff(seed, blob, t);
+    __syncthreads();
+    for (int j = 0; j < 32; j++) {
+        int i = t * 32 + j;
+        Fr w = T->twiddle[i >> 1];
+        if (i & 1) w = w.neg();
+        Fr f = coef[D - 1];
+        for (int k = D - 2; k >= 0; k--) f = f * w + coef[k];
+        Fr raw = f.to_raw();
+        uint4 hi, lo;
+        hi.x = sha_bswap(raw.l[7]); hi.y = sha_bswap(raw.l[6]); hi.z = sha_bswap(raw.l[5]); hi.w = sha_bswap(raw.l[4]);
+        lo.x = sha_bswap(raw.l[3]); lo.y = sha_bswap(raw.l[2]); lo.z = sha_bswap(raw.l[1]); lo.w = sha_bswap(raw.l[0]);
+        uint4* dst = reinterpret_cast<uint4*>(blobs + (size_t)blob * kBytesPerBlob) + 2 * i;
+        dst[0] = hi; dst[1] = lo;
+    }
+}
+// proofs == nullptr: commitments C = sum c_j M_j ; else proofs pi = sum q_j M_j using z_mont
+__global__ void __launch_bounds__(64) harness_commit_kernel(uint64_t seed, int n, int D, const G1Affine* __restrict__ M, const Fr* __restrict__ z_mont,
+                                                            uint8_t* __restrict__ out, int want_proof) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    Fr c[kHarnessMaxDegree];
+    for (int j = 0; j < D; j++) c[j] = harness_coeff(seed, b, j);
+    int terms = D;
+    if (want_proof) {   // synthetic division by (X - z): q_{D-2} = c_{D-1}, q_{j-1} = c_j + z q_j
+        Fr z = z_mont[b], q[kHarnessMaxDegree];
+        q[D - 2] = c[D - 1];
+        for (int j = D - 2; j >= 1; j--) q[j - 1] = c[j] + z * q[j];
+        for (int j = 0; j < D - 1; j++) c[j] = q[j];
+        terms = D - 1;
+    }
+    G1 acc = G1::identity();
+    for (int j = 0; j < terms; j++) {
+        Fr raw = c[j].to_raw();
+        acc = acc.add(scalar_mul_affine(M[j], raw.l, 255));
+    }
+    uint8_t enc[48];
+    g1_to_compressed(enc, g1_to_affine(acc));
+    for (int k = 0; k < 48; k++) out[(size_t)b * 48 + k] = enc[k];
+}
 
 }  // namespace kzgb200

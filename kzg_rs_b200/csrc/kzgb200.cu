@@ -33,13 +33,24 @@ struct kzgb200_ctx {
     uint32_t* d_result = nullptr;
     uint8_t *d_zout = nullptr, *d_yout = nullptr;
     uint8_t *d_many = nullptr;
+    uint32_t* d_wk = nullptr;       // transcript W+K words, 64 per SHA block
+    size_t wk_cap = 0;
     uint32_t* h_result = nullptr;   // pinned
     // inputs of the current shard (device pointers owned by the caller or by the staging buffers)
     const uint8_t *cur_c = nullptr, *cur_p = nullptr;
     size_t cur_n = 0;
+    // optional per-phase timing (CUDA events on the context stream)
+    bool profile = false;
+    cudaEvent_t ev[9] = {nullptr};
+    int ev_used = 0;
+    float phase_ms[8] = {0};
     std::mutex lock;
     char err[256] = {0};
 };
+enum Phase { kPhParse = 0, kPhChallenge, kPhEval, kPhTranscript, kPhLincomb, kPhReduce, kPhFinal, kPhCount };
+static void mark(kzgb200_ctx* ctx, int idx) {
+    if (ctx->profile && ctx->ev[idx]) { cudaEventRecord(ctx->ev[idx], ctx->stream); if (idx + 1 > ctx->ev_used) ctx->ev_used = idx + 1; }
+}
 
 #define CK(expr)                                                                                   \
     do {                                                                                           \
@@ -111,7 +122,7 @@ extern "C" void kzgb200_destroy(kzgb200_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->tables, ctx->d_blobs, ctx->d_c, ctx->d_p, ctx->d_z_mont, ctx->d_zy, ctx->d_C, ctx->d_P, ctx->d_status,
-                    ctx->d_terms, ctx->d_ry, ctx->d_r, ctx->d_partial, ctx->d_result, ctx->d_zout, ctx->d_yout, ctx->d_many};
+                    ctx->d_terms, ctx->d_ry, ctx->d_r, ctx->d_partial, ctx->d_result, ctx->d_zout, ctx->d_yout, ctx->d_many, ctx->d_wk};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -125,16 +136,25 @@ extern "C" const char* kzgb200_last_error(const kzgb200_ctx* ctx) { return ctx ?
 static int launch_phase1(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t* d_c, const uint8_t* d_p, size_t n) {
     int ni = (int)n;
     CK(cudaMemsetAsync(ctx->d_status, 0, n * sizeof(uint32_t), ctx->stream));
+    ctx->ev_used = 0;
+    mark(ctx, 0);
     g1_parse_kernel<<<(2 * ni + 127) / 128, 128, 0, ctx->stream>>>(d_c, d_p, ni, ctx->d_C, ctx->d_P, ctx->d_status);
+    mark(ctx, 1);
     challenge_kernel<<<(ni + 63) / 64, 64, 0, ctx->stream>>>(d_blobs, d_c, ni, ctx->d_z_mont, ctx->d_zy);
+    mark(ctx, 2);
     eval_kernel<<<ni, kEvalThreads, 0, ctx->stream>>>(d_blobs, ni, ctx->d_z_mont, ctx->tables, ctx->d_zy, ctx->d_status);
+    mark(ctx, 3);
     CK(cudaGetLastError());
     ctx->cur_c = d_c; ctx->cur_p = d_p; ctx->cur_n = n;
     return KZGB200_OK;
 }
 // K5
 static int launch_transcript(kzgb200_ctx* ctx, const uint8_t* d_all_c, const ZY* d_all_zy, const uint8_t* d_all_p, size_t n_total) {
-    transcript_kernel<<<1, 32, 0, ctx->stream>>>(d_all_c, d_all_zy, d_all_p, (uint64_t)n_total, ctx->d_r);
+    size_t nblk = (32 + n_total * 160 + 9 + 63) / 64;
+    if (nblk > ctx->wk_cap) { CK(regrow(ctx->d_wk, nblk * 64)); ctx->wk_cap = nblk; }
+    transcript_schedule_kernel<<<(unsigned)((nblk + 127) / 128), 128, 0, ctx->stream>>>(d_all_c, d_all_zy, d_all_p, (uint64_t)n_total, ctx->d_wk);
+    transcript_chain_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_wk, (uint64_t)n_total, ctx->d_r);
+    mark(ctx, 4);
     CK(cudaGetLastError());
     return KZGB200_OK;
 }
@@ -143,12 +163,14 @@ static int launch_lincomb(kzgb200_ctx* ctx, size_t offset, Partial* d_out) {
     int n = (int)ctx->cur_n;
     lincomb_terms_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_C, ctx->d_P, ctx->d_z_mont, ctx->d_zy, ctx->d_r,
                                                                   (uint64_t)offset, n, ctx->d_terms, ctx->d_ry);
+    mark(ctx, 5);
     for (int count = n; count > 1;) {
         int half = (count + 1) / 2;
         pair_sum_kernel<<<(half + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_terms, ctx->d_ry, count, half);
         count = half;
     }
     finish_partial_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_terms, ctx->d_ry, ctx->d_status, n, d_out);
+    mark(ctx, 6);
     CK(cudaGetLastError());
     return KZGB200_OK;
 }
@@ -179,8 +201,12 @@ static int batch_device_locked(kzgb200_ctx* ctx, const uint8_t* d_blobs, const u
     if ((rc = launch_transcript(ctx, d_c, ctx->d_zy, d_p, n))) return rc;
     if ((rc = launch_lincomb(ctx, 0, ctx->d_partial))) return rc;
     batch_final_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_partial, 1, ctx->tables, ctx->d_result);
+    mark(ctx, 7);
     CK(cudaGetLastError());
-    return read_result(ctx, ok);
+    rc = read_result(ctx, ok);
+    if (ctx->profile && ctx->ev_used == 8)
+        for (int i = 0; i < 7; i++) cudaEventElapsedTime(&ctx->phase_ms[i], ctx->ev[i], ctx->ev[i + 1]);
+    return rc;
 }
 
 extern "C" int kzgb200_verify_blob_kzg_proof_batch_device(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t* d_commitments,
@@ -297,6 +323,47 @@ extern "C" int kzgb200_shard_finalize(kzgb200_ctx* ctx, const uint8_t* d_partial
     CK(cudaGetLastError());
     return read_result(ctx, ok);
 }
+
+// ---- harness: synthetic workload with valid commitments / proofs (device outputs) ---------------------------
+extern "C" int kzgb200_harness_generate(kzgb200_ctx* ctx, uint64_t seed, size_t n, int degree, const uint8_t* tau_powers48,
+                                        uint8_t* d_blobs, uint8_t* d_commitments, uint8_t* d_proofs) {
+    if (!ctx || n == 0 || degree < 2 || degree > kHarnessMaxDegree || !tau_powers48) return KZGB200_BAD_ARGS;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_capacity(ctx, n, false);
+    if (rc) return rc;
+    uint8_t* d_bytes = nullptr; G1Affine* d_M = nullptr; uint32_t* d_bad = nullptr; uint32_t bad = 0;
+    CK(cudaMalloc(&d_bytes, degree * 48)); CK(cudaMalloc(&d_M, degree * sizeof(G1Affine))); CK(cudaMalloc(&d_bad, 4));
+    CK(cudaMemsetAsync(d_bad, 0, 4, ctx->stream));
+    CK(cudaMemcpyAsync(d_bytes, tau_powers48, degree * 48, cudaMemcpyHostToDevice, ctx->stream));
+    harness_parse_points_kernel<<<1, 32, 0, ctx->stream>>>(d_bytes, degree, d_M, d_bad);
+    int ni = (int)n;
+    harness_blob_kernel<<<ni, 128, 0, ctx->stream>>>(seed, ni, degree, ctx->tables, d_blobs);
+    harness_commit_kernel<<<(ni + 63) / 64, 64, 0, ctx->stream>>>(seed, ni, degree, d_M, nullptr, d_commitments, 0);
+    challenge_kernel<<<(ni + 63) / 64, 64, 0, ctx->stream>>>(d_blobs, d_commitments, ni, ctx->d_z_mont, ctx->d_zy);
+    harness_commit_kernel<<<(ni + 63) / 64, 64, 0, ctx->stream>>>(seed, ni, degree, d_M, ctx->d_z_mont, d_proofs, 1);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_bytes); cudaFree(d_M); cudaFree(d_bad);
+    return bad ? KZGB200_BAD_ARGS : KZGB200_OK;
+}
+// per-phase device times of the last single-GPU batch call: parse, challenge, eval, transcript, lincomb, reduce, final
+extern "C" int kzgb200_set_profiling(kzgb200_ctx* ctx, int on) {
+    if (!ctx) return KZGB200_BAD_ARGS;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    CK(cudaSetDevice(ctx->device));
+    if (on) for (auto& e : ctx->ev) if (!e) CK(cudaEventCreate(&e));
+    ctx->profile = on != 0;
+    return KZGB200_OK;
+}
+extern "C" int kzgb200_get_phase_ms(kzgb200_ctx* ctx, float* out7) {
+    if (!ctx || !out7) return KZGB200_BAD_ARGS;
+    for (int i = 0; i < 7; i++) out7[i] = ctx->phase_ms[i];
+    return KZGB200_OK;
+}
+// the stream every call of this context is issued on (cudaStream_t), for event timing by the caller
+extern "C" void* kzgb200_stream(kzgb200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 extern "C" void* kzgb200_alloc_pinned(size_t bytes) {
     void* p = nullptr;
