@@ -220,6 +220,8 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    step_resident()
+    zy_sample = plan.last_zy_host(min(n, args.cpu_sample)) if world == 1 else None
     # negatives on the same workload (verdict only, untimed)
     neg = plan.check_negatives(d_blobs, d_cs, d_ps)
 
@@ -267,8 +269,7 @@ def main():
                                "sample": "first %d of the %d blobs, %d threads (blob-parallel); single thread on %d blobs: %.1f blobs/s; SHA-NI=%d"
                                          % (m, n, cores, m1, m1 / dt1, O.lib().kzgo_sha256_uses_shani())}
         # bit-exactness of z, y on the sample against the oracle
-        zy = plan.last_zy_host(m)
-        out["parity_sample"] = {"blobs": m, "z_y_bit_exact": zy == (z, y)}
+        out["parity_sample"] = {"blobs": m, "z_y_bit_exact": zy_sample == (z, y)}
     if rank == 0:
         print(json.dumps(out))
     if dist is not None:

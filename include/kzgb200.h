@@ -94,6 +94,23 @@ int kzgb200_shard_lincomb(kzgb200_ctx* ctx, size_t global_offset, uint8_t* d_par
 /* final: sum the gathered partials (n_ranks x KZGB200_PARTIAL_BYTES) and run the single pairing check. */
 int kzgb200_shard_finalize(kzgb200_ctx* ctx, const uint8_t* d_partials, size_t n_ranks, int* ok);
 
+/* ---- transcript mode of the batch challenge r -----------------------------------------------------------------
+ * EXACT (default): r = SHA-256 over the serial transcript exactly as compute_r_powers (reference
+ *   src/kzg_proof.rs:291-348) -- r, its powers and both MSM sums are bit-identical to kzg-rs.  The hash is one
+ *   serial chain of 2.5 SHA-256 blocks per blob.
+ * TREE (opt-in): same transcript bytes hashed as a two-level tree (64-entry leaves in parallel).  r differs from
+ *   kzg-rs's; verdicts do not (z, y are unaffected).  For throughput at large n / many GPUs. */
+#define KZGB200_TRANSCRIPT_EXACT 0
+#define KZGB200_TRANSCRIPT_TREE 1
+int kzgb200_set_transcript_mode(kzgb200_ctx* ctx, int mode);
+/* canonical big-endian r of the last batch verified on this context (n >= 2) */
+int kzgb200_last_r(kzgb200_ctx* ctx, uint8_t* r_out32);
+
+/* raw partial of the last single-GPU batch (n >= 2), KZGB200_PARTIAL_BYTES: Jacobian A = sum r_i pi_i and
+ * B' = sum r_i C_i + r_i z_i pi_i as 3 x 12 little-endian u32 Montgomery limbs each (R = 2^384), then
+ * s = sum r_i y_i (8 limbs, canonical), then the error flags.  For parity tests of the MSM intermediates. */
+int kzgb200_last_partial(kzgb200_ctx* ctx, uint8_t* out352);
+
 /* ---- harness (test / bench data; kzg-rs itself has no commit/prove path) ---------------------------------
  * Fills device buffers with n synthetic blobs (evaluation form of seeded random polynomials of degree <
  * `degree`, 2 <= degree <= 16) and their valid commitments and proofs over the trusted setup whose

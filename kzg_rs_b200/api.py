@@ -77,6 +77,9 @@ class Library:
         d.kzgb200_get_phase_ms.argtypes = [p, C.POINTER(C.c_float)]
         d.kzgb200_stream.argtypes = [p]
         d.kzgb200_stream.restype = p
+        d.kzgb200_set_transcript_mode.argtypes = [p, C.c_int]
+        d.kzgb200_last_r.argtypes = [p, C.c_char_p]
+        d.kzgb200_last_partial.argtypes = [p, C.c_char_p]
         d.kzgb200_alloc_pinned.argtypes = [sz]
         d.kzgb200_alloc_pinned.restype = p
         d.kzgb200_free_pinned.argtypes = [p]
@@ -262,6 +265,39 @@ class KzgProof:
         if rc:
             _raise(rc, ctx)
         return out.raw[:m]
+
+
+TRANSCRIPT_EXACT, TRANSCRIPT_TREE = 0, 1
+
+
+def set_transcript_mode(kzg_settings, mode, device=0):
+    """EXACT (default, r bit-identical to kzg-rs) or TREE (parallel hash, same verdicts)."""
+    rc = Library.get().dll.kzgb200_set_transcript_mode(kzg_settings.context(device), mode)
+    if rc:
+        _raise(rc)
+
+
+def last_batch_intermediates(kzg_settings, device=0):
+    """(r, proof_lincomb, rhs_g1) of the last n >= 2 batch on this device, as the oracle's trace gives them:
+    r 32-byte big-endian; the two sums as affine integer pairs (or None for the identity)."""
+    ctx = kzg_settings.context(device)
+    r, part = C.create_string_buffer(32), C.create_string_buffer(PARTIAL_BYTES)
+    lib = Library.get().dll
+    for rc in (lib.kzgb200_last_r(ctx, r), lib.kzgb200_last_partial(ctx, part)):
+        if rc:
+            _raise(rc, ctx)
+    P = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+    rinv = pow(1 << 384, -1, P)
+    fe = lambda off: int.from_bytes(part.raw[off:off + 48], "little") * rinv % P
+
+    def affine(off):
+        x, y, z = fe(off), fe(off + 48), fe(off + 96)
+        if z == 0:
+            return None
+        zi = pow(z, -1, P)
+        return (x * zi * zi % P, y * zi * zi * zi % P)
+    s = int.from_bytes(part.raw[288:320], "little")
+    return {"r": r.raw, "A": affine(0), "B_prime": affine(144), "sum_r_y": s}
 
 
 def _ptr(x):

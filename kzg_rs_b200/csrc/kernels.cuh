@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include "sha256.cuh"
 #include "verify.cuh"
+#include "vliw.cuh"
 
 namespace kzgb200 {
 
@@ -22,6 +23,8 @@ struct DeviceTables {
     // and w_a^(2^k) = roots_of_unity[2g] for g = a >> (k+1), independent of the level k.
     Fr twiddle[2048];
     PairingTables pairing;
+    // fixed-base table of the G1 generator: gen_table[w][d-1] = [d * 16^w] G, d = 1..15, w < 64
+    G1Affine gen_table[64][15];
     uint32_t setup_ok;
 };
 
@@ -35,6 +38,12 @@ __global__ void setup_tables_kernel(DeviceTables* T, const uint8_t* g2_points /*
         const uint32_t om[8] = KZG_FR_OMEGA_M;
         uint32_t ee[1] = {e};
         T->twiddle[tid] = fr_const(om).pow(ee, 12);
+    }
+    if (tid >= 4096 && tid < 4096 + 960) {
+        int w = (tid - 4096) / 15, d = (tid - 4096) % 15 + 1;
+        uint32_t k[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        k[w / 8] = (uint32_t)d << (4 * (w % 8));
+        T->gen_table[w][d - 1] = g1_to_affine(scalar_mul_affine(g1_generator(), k, 256));
     }
     if (tid == 2048) {
         G2Affine gen, tau;
@@ -296,9 +305,17 @@ __global__ void __launch_bounds__(32) transcript_chain_kernel(const uint32_t* __
                 uint32_t kw[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    uint32_t t1 = h + (sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25)) + ((e & f) ^ (~e & g)) + kw[u];
-                    uint32_t t2 = (sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
-                    h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+                    // shortest dependent chain: only sigma1(e)/ch(e) and sigma0(a)/maj(a) sit between e_i -> e_(i+1), a_i -> a_(i+1)
+                    uint32_t y = h + kw[u];                 // off the chain (h, kw known early)
+                    uint32_t x = y + d;                     // off the chain
+                    uint32_t s1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
+                    uint32_t ch = (e & f) ^ (~e & g);
+                    uint32_t s0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22);
+                    uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+                    uint32_t e2 = x + s1 + ch;
+                    uint32_t t1 = y + s1 + ch;
+                    uint32_t a2 = t1 + s0 + mj;
+                    h = g; g = f; f = e; e = e2; d = c; c = b; b = a; a = a2;
                 }
             }
             st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
@@ -312,42 +329,113 @@ __global__ void __launch_bounds__(32) transcript_chain_kernel(const uint32_t* __
     }
 }
 
+// K5' (optional, opt-in): the same transcript hashed as a two-level tree.  Leaf j = SHA-256 of entries
+// [64 j, 64 j + 64) (each entry = C_i | z_i LE | y_i LE | pi_i, 160 bytes); root = SHA-256(domain | u64be 4096 |
+// u64be n | leaf digests).  The leaves hash in parallel, so the serial part shrinks from 2.5 to 0.008 SHA blocks
+// per blob.  r then differs from kzg-rs's r (the verdict does not: both are Fiat-Shamir challenges over the
+// same data), so this mode is NOT the default; see DESIGN.md "transcript modes".
+constexpr int kTreeGroup = 64;
+__global__ void __launch_bounds__(64) transcript_tree_leaf_kernel(const uint8_t* __restrict__ commitments, const ZY* __restrict__ zy,
+                                                                  const uint8_t* __restrict__ proofs, uint64_t n, uint32_t* __restrict__ digests) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t ngroups = (n + kTreeGroup - 1) / kTreeGroup;
+    if (g >= ngroups) return;
+    uint64_t first = g * kTreeGroup, cnt = n - first < (uint64_t)kTreeGroup ? n - first : (uint64_t)kTreeGroup;
+    size_t len = (size_t)cnt * 160, nblk = (len + 9 + 63) / 64;
+    uint32_t st[8], w[16];
+    sha256_init(st);
+    for (size_t blk = 0; blk < nblk; blk++) {
+        for (int j = 0; j < 16; j++) {
+            uint32_t v = 0;
+            for (int b = 0; b < 4; b++) {
+                size_t pos = blk * 64 + 4 * j + b;
+                // entry bytes start at transcript offset 32 of a batch whose first entry is `first`
+                uint8_t byte = pos < len ? transcript_byte(32 + pos, 0, commitments + first * 48, zy + first, proofs + first * 48)
+                                         : (pos == len ? 0x80 : 0);
+                v = (v << 8) | byte;
+            }
+            w[j] = v;
+        }
+        if (blk == nblk - 1) { w[14] = (uint32_t)(((uint64_t)len * 8) >> 32); w[15] = (uint32_t)((uint64_t)len * 8); }
+        sha256_compress(st, w);
+    }
+    for (int j = 0; j < 8; j++) digests[g * 8 + j] = st[j];
+}
+__global__ void transcript_tree_root_kernel(const uint32_t* __restrict__ digests, uint64_t n, Fr* __restrict__ r_mont) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    uint64_t ngroups = (n + kTreeGroup - 1) / kTreeGroup;
+    size_t len = 32 + (size_t)ngroups * 32, nblk = (len + 9 + 63) / 64;
+    uint32_t st[8], w[16];
+    sha256_init(st);
+    for (size_t blk = 0; blk < nblk; blk++) {
+        for (int j = 0; j < 16; j++) {
+            size_t pos = blk * 64 + 4 * j;    // word-aligned: header is 8 words, digests are whole words
+            uint32_t v;
+            if (pos < 32) {
+                const uint32_t hdr[8] = {0x52434b5a, 0x47424154, 0x43485f5f, 0x5f56315f, 0, 4096, (uint32_t)(n >> 32), (uint32_t)n};  // "RCKZGBATCH___V1_"
+                v = hdr[pos / 4];
+            } else if (pos < len) v = digests[(pos - 32) / 4];
+            else v = pos == len ? 0x80000000u : 0;
+            w[j] = v;
+        }
+        if (blk == nblk - 1) { w[14] = (uint32_t)(((uint64_t)len * 8) >> 32); w[15] = (uint32_t)((uint64_t)len * 8); }
+        sha256_compress(st, w);
+    }
+    Fr raw;
+    for (int j = 0; j < 8; j++) raw.l[j] = st[7 - j];
+    *r_mont = Fr::from_raw(raw);
+}
+
 // ------------------------------------------------------------------------------------------------ K6
 // Random linear combination (reference src/kzg_proof.rs:399-433), regrouped so that it needs no per-blob
 // [y_i]G:   A = sum r_i pi_i ,  B = sum (r_i C_i + (r_i z_i) pi_i) - [sum r_i y_i] G ,  r_i = r^(offset+i).
 // v1: one thread per blob does its scalar multiplications (Shamir's trick for the pair), results are then
 // tree-summed by pair_sum_kernel.
+// One thread per (blob, 32-bit chunk of the scalars): chunk j of blob i yields [r_i^(j)] pi_i and
+// [r_i^(j)] C_i + [(r_i z_i)^(j)] pi_i, where s^(j) is the j-th 32-bit limb of s.  Chunk sums over the blobs are
+// formed by pair_sum_kernel; the weights 2^(32 j) are applied once per batch (finish_partial_kernel), so the
+// per-blob ladders are 32 steps deep instead of 255.
+constexpr int kChunks = 8;
 struct LincombTerm { G1 a, b; };
-__global__ void __launch_bounds__(128) lincomb_terms_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P,
-                                                            const Fr* __restrict__ z_mont, const ZY* __restrict__ zy,
-                                                            const Fr* __restrict__ r_mont, uint64_t offset, int n,
-                                                            LincombTerm* __restrict__ terms, Fr* __restrict__ ry) {
+__global__ void __launch_bounds__(128) lincomb_scalars_kernel(const Fr* __restrict__ z_mont, const ZY* __restrict__ zy, const Fr* __restrict__ r_mont,
+                                                              uint64_t offset, int n, Fr* __restrict__ ri_raw, Fr* __restrict__ rz_raw,
+                                                              Fr* __restrict__ ry) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t e = offset + (uint64_t)i;
     uint32_t ee[2] = {(uint32_t)e, (uint32_t)(e >> 32)};
     Fr ri = r_mont->pow(ee, 64);              // r^(offset+i), Montgomery   (compute_powers, kzg_proof.rs:279-289)
-    Fr ri_raw = ri.to_raw();
-    Fr rz_raw = (ri * z_mont[i]).to_raw();    // r_i z_i   (kzg_proof.rs:425)
+    ri_raw[i] = ri.to_raw();
+    rz_raw[i] = (ri * z_mont[i]).to_raw();    // r_i z_i   (kzg_proof.rs:425)
     ry[i] = ri * zy[i].y;                     // r_i y_i in normal form
+}
+// terms layout: [chunk][blob]
+__global__ void __launch_bounds__(128) lincomb_terms_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P,
+                                                            const Fr* __restrict__ ri_raw, const Fr* __restrict__ rz_raw, int n,
+                                                            LincombTerm* __restrict__ terms) {
+    int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n * kChunks) return;
+    int i = tid % n, j = tid / n;
+    uint32_t kr = ri_raw[i].l[j], kz = rz_raw[i].l[j];
     G1Affine c = C[i], p = P[i];
     G1 cp = G1::from_affine(c).add_mixed(p);  // C_i + pi_i for the joint ladder
     G1 a = G1::identity(), b = G1::identity();
-    for (int bit = 254; bit >= 0; bit--) {
+    for (int bit = 31; bit >= 0; bit--) {
         a = a.dbl(); b = b.dbl();
-        uint32_t br = (ri_raw.l[bit >> 5] >> (bit & 31)) & 1, bz = (rz_raw.l[bit >> 5] >> (bit & 31)) & 1;
+        uint32_t br = (kr >> bit) & 1, bz = (kz >> bit) & 1;
         if (br) a = a.add_mixed(p);
         if (br && bz) b = b.add(cp); else if (br) b = b.add_mixed(c); else if (bz) b = b.add_mixed(p);
     }
-    terms[i].a = a; terms[i].b = b;
+    terms[tid].a = a; terms[tid].b = b;
 }
-// terms[i] += terms[i + half] for i < half (and the Fr sums likewise)
-__global__ void __launch_bounds__(128) pair_sum_kernel(LincombTerm* __restrict__ terms, Fr* __restrict__ ry, int count, int half) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+// terms[j][i] += terms[j][i + half] for i < half, every chunk j (grid.y = chunk); Fr sums on chunk 0
+__global__ void __launch_bounds__(128) pair_sum_kernel(LincombTerm* __restrict__ terms, Fr* __restrict__ ry, int n, int count, int half) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
     if (i >= half || i + half >= count) return;
-    terms[i].a = terms[i].a.add(terms[i + half].a);
-    terms[i].b = terms[i].b.add(terms[i + half].b);
-    ry[i] = ry[i] + ry[i + half];
+    LincombTerm* t = terms + (size_t)j * n;
+    t[i].a = t[i].a.add(t[i + half].a);
+    t[i].b = t[i].b.add(t[i + half].b);
+    if (j == 0) ry[i] = ry[i] + ry[i + half];
 }
 // per-rank partial result exchanged between ranks (the payload of the allgather)
 struct Partial {
@@ -356,6 +444,7 @@ struct Partial {
     uint32_t err;     // OR of the per-blob error flags of this rank
     uint32_t pad[7];
 };
+// chunk sums S_j -> sum_j 2^(32 j) S_j (Horner), thread 0 for A and thread 32 for B; all threads OR the error flags
 __global__ void finish_partial_kernel(const LincombTerm* __restrict__ terms, const Fr* __restrict__ ry, const uint32_t* __restrict__ status, int n,
                                       Partial* __restrict__ out) {
     __shared__ uint32_t s_err;
@@ -364,39 +453,96 @@ __global__ void finish_partial_kernel(const LincombTerm* __restrict__ terms, con
     uint32_t e = 0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) e |= status[i];
     if (e) atomicOr(&s_err, e);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        out->a = terms[0].a; out->b = terms[0].b; out->ry = ry[0]; out->err = s_err;
+    if (threadIdx.x == 0 || threadIdx.x == 32) {
+        bool is_b = threadIdx.x == 32;
+        G1 acc = G1::identity();
+        for (int j = kChunks - 1; j >= 0; j--) {
+            if (j != kChunks - 1) for (int k = 0; k < 32; k++) acc = acc.dbl();
+            const LincombTerm& t = terms[(size_t)j * n];
+            acc = acc.add(is_b ? t.b : t.a);
+        }
+        if (is_b) out->b = acc; else out->a = acc;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) { out->ry = ry[0]; out->err = s_err; }
 }
 
 // ------------------------------------------------------------------------------------------------ K7
+constexpr int kFinalThreads = 64;
+// [s]G from the fixed-base table: thread t < 64 takes the t-th 4-bit digit of s, then a shared-memory tree sum.
+// All kFinalThreads threads call it; the result is returned to every thread.
+__device__ __noinline__ G1 coop_fixed_base_mul(const Fr& s_raw, const DeviceTables* T, G1* sm /* kFinalThreads */) {
+    int t = threadIdx.x;
+    uint32_t d = (s_raw.l[t / 8] >> (4 * (t % 8))) & 15u;
+    sm[t] = d ? G1::from_affine(T->gen_table[t][d - 1]) : G1::identity();
+    __syncthreads();
+    for (int span = kFinalThreads / 2; span >= 1; span >>= 1) {
+        if (t < span) sm[t] = sm[t].add(sm[t + span]);
+        __syncthreads();
+    }
+    return sm[0];
+}
 // Final pairing check over the gathered per-rank partials (reference src/kzg_proof.rs:436-441):
-//   e(sum_k A_k, [tau]G2) == e(sum_k B_k - [sum_k s_k]G, G2).
+//   e(sum_k A_k, [tau]G2) == e(sum_k B_k - [sum_k s_k]G, G2)
+// one CTA of kFinalThreads threads: the G1 prelude on a few threads, the pairing on the cooperative engine.
 // result: 0 = false, 1 = true, 2 = BadArgs (some rank flagged an unparsable input)
-__global__ void batch_final_kernel(const Partial* __restrict__ parts, int nparts, const DeviceTables* __restrict__ T, uint32_t* __restrict__ result) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    G1 A = G1::identity(), B = G1::identity();
-    Fr s = Fr::zero();
-    uint32_t err = 0;
-    for (int k = 0; k < nparts; k++) { A = A.add(parts[k].a); B = B.add(parts[k].b); s = s + parts[k].ry; err |= parts[k].err; }
-    if (err) { result[0] = kBadArgs; result[1] = err; return; }
-    B = B.add(scalar_mul_affine(g1_generator(), s.l, 255).neg());
-    G1Affine Aa = g1_to_affine(A), Ba = g1_to_affine(B);
-    if (!Aa.inf) Aa.y = Aa.y.neg();
-    result[0] = pairing_product_is_one(Ba, T->pairing.g2_gen, Aa, T->pairing.tau_g2) ? kTrue : kFalse;
-    result[1] = 0;
+__global__ void __launch_bounds__(kFinalThreads) batch_final_kernel(const Partial* __restrict__ parts, int nparts, const DeviceTables* __restrict__ T,
+                                                                    uint32_t* __restrict__ result) {
+    __shared__ Fp regs[vliw::kTotalRegs];
+    __shared__ G1 sm[kFinalThreads];
+    __shared__ G1Affine pts[2];
+    __shared__ Fr s_sum;
+    __shared__ uint32_t s_err;
+    __shared__ vliw::SharedTables stab;
+    int t = threadIdx.x;
+    vliw::Tables tab = vliw::load_tables(&stab, t, kFinalThreads);
+    if (t == 0) {
+        Fr s = Fr::zero(); uint32_t err = 0;
+        for (int k = 0; k < nparts; k++) { s = s.add_inl(parts[k].ry); err |= parts[k].err; }
+        s_sum = s; s_err = err;
+    }
+    __syncthreads();
+    if (s_err) { if (t == 0) { result[0] = kBadArgs; result[1] = s_err; } return; }
+    G1 sg = coop_fixed_base_mul(s_sum, T, sm);
+    if (t < 2) {
+        G1 acc = G1::identity();
+        for (int k = 0; k < nparts; k++) acc = acc.add(t == 0 ? parts[k].a : parts[k].b);
+        if (t == 1) acc = acc.add(sg.neg());
+        Fp zi = vliw::fp_inv_bingcd(acc.z), zi2 = zi.sqr();
+        G1Affine a = acc.is_identity() ? G1Affine{Fp::zero(), Fp::zero(), 1} : G1Affine{acc.x * zi2, acc.y * zi2 * zi, 0};
+        if (t == 0 && !a.inf) a.y = a.y.neg();     // -A
+        pts[t] = a;
+    }
+    __syncthreads();
+    vliw::Lanes L{t, kFinalThreads, tab};
+    bool ok = vliw::coop_pairing_product_is_one(regs, pts[1], T->pairing.g2_gen, pts[0], T->pairing.tau_g2, L);
+    if (t == 0) { result[0] = ok ? kTrue : kFalse; result[1] = 0; }
 }
 // Single-blob path (reference src/kzg_proof.rs:446-470 -> verify_kzg_proof_impl :203-223) after z, y and the
-// points have been produced by the kernels above.
-__global__ void single_final_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P, const ZY* __restrict__ zy,
-                                    const uint32_t* __restrict__ status,
-                                    const DeviceTables* __restrict__ T, uint32_t* __restrict__ result) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    if (status[0]) { result[0] = kBadArgs; result[1] = status[0]; return; }
-    G1Affine X = kzg_lhs_point(C[0], zy[0].z, zy[0].y, P[0]);
-    result[0] = kzg_pairing_check(X, P[0], &T->pairing) ? kTrue : kFalse;
-    result[1] = 0;
+// points have been produced by the kernels above:  e(C - [y]G + [z]pi, G2) e(-pi, [tau]G2) == 1.
+__global__ void __launch_bounds__(kFinalThreads) single_final_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P, const ZY* __restrict__ zy,
+                                                                     const uint32_t* __restrict__ status, const DeviceTables* __restrict__ T,
+                                                                     uint32_t* __restrict__ result) {
+    __shared__ Fp regs[vliw::kTotalRegs];
+    __shared__ G1 sm[kFinalThreads];
+    __shared__ G1Affine pts[2];
+    __shared__ vliw::SharedTables stab;
+    int t = threadIdx.x;
+    vliw::Tables tab = vliw::load_tables(&stab, t, kFinalThreads);
+    if (status[0]) { if (t == 0) { result[0] = kBadArgs; result[1] = status[0]; } return; }
+    G1 yg = coop_fixed_base_mul(zy[0].y, T, sm);
+    if (t == 0) {
+        G1 acc = yg.neg().add_mixed(C[0]).add(scalar_mul_affine(P[0], zy[0].z.l, 255));
+        Fp zi = vliw::fp_inv_bingcd(acc.z), zi2 = zi.sqr();
+        pts[0] = acc.is_identity() ? G1Affine{Fp::zero(), Fp::zero(), 1} : G1Affine{acc.x * zi2, acc.y * zi2 * zi, 0};
+        G1Affine np = P[0];
+        if (!np.inf) np.y = np.y.neg();
+        pts[1] = np;
+    }
+    __syncthreads();
+    vliw::Lanes L{t, kFinalThreads, tab};
+    bool ok = vliw::coop_pairing_product_is_one(regs, pts[0], T->pairing.g2_gen, pts[1], T->pairing.tau_g2, L);
+    if (t == 0) { result[0] = ok ? kTrue : kFalse; result[1] = 0; }
 }
 // m independent verify_kzg_proof tuples, one thread each (reference src/kzg_proof.rs:353-397)
 __global__ void __launch_bounds__(64) verify_many_kernel(const uint8_t* __restrict__ c, const uint8_t* __restrict__ z, const uint8_t* __restrict__ y,
@@ -416,6 +562,7 @@ __global__ void export_scalars_kernel(const ZY* __restrict__ zy, int n, uint8_t*
     if (z_out) limbs_to_be32(z_out + (size_t)i * 32, zy[i].z.l);
     if (y_out) limbs_to_be32(y_out + (size_t)i * 32, zy[i].y.l);
 }
+__global__ void r_to_raw_kernel(const Fr* __restrict__ r_mont, ZY* __restrict__ out) { out->z = r_mont->to_raw(); out->y = Fr::zero(); }
 // z_mont from gathered canonical scalars is not needed: phase 2 only uses this rank's own z_mont.
 
 

@@ -28,7 +28,7 @@ struct kzgb200_ctx {
     G1Affine *d_C = nullptr, *d_P = nullptr;
     uint32_t* d_status = nullptr;
     LincombTerm* d_terms = nullptr;
-    Fr *d_ry = nullptr, *d_r = nullptr;
+    Fr *d_ry = nullptr, *d_r = nullptr, *d_ri = nullptr, *d_rz = nullptr;
     Partial* d_partial = nullptr;
     uint32_t* d_result = nullptr;
     uint8_t *d_zout = nullptr, *d_yout = nullptr;
@@ -40,6 +40,7 @@ struct kzgb200_ctx {
     const uint8_t *cur_c = nullptr, *cur_p = nullptr;
     size_t cur_n = 0;
     // optional per-phase timing (CUDA events on the context stream)
+    int transcript_mode = KZGB200_TRANSCRIPT_EXACT;
     bool profile = false;
     cudaEvent_t ev[9] = {nullptr};
     int ev_used = 0;
@@ -74,7 +75,8 @@ static int ensure_capacity(kzgb200_ctx* ctx, size_t n, bool need_blob_staging) {
         CK(regrow(ctx->d_c, c * 48)); CK(regrow(ctx->d_p, c * 48));
         CK(regrow(ctx->d_z_mont, c)); CK(regrow(ctx->d_zy, c));
         CK(regrow(ctx->d_C, c)); CK(regrow(ctx->d_P, c));
-        CK(regrow(ctx->d_status, c)); CK(regrow(ctx->d_terms, c)); CK(regrow(ctx->d_ry, c));
+        CK(regrow(ctx->d_status, c)); CK(regrow(ctx->d_terms, c * kChunks)); CK(regrow(ctx->d_ry, c));
+        CK(regrow(ctx->d_ri, c)); CK(regrow(ctx->d_rz, c));
         CK(regrow(ctx->d_zout, c * 32)); CK(regrow(ctx->d_yout, c * 32));
         ctx->cap = c;
     }
@@ -104,7 +106,7 @@ extern "C" int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_p
         uint8_t* d_g2 = nullptr;
         CK(cudaMalloc(&d_g2, 192));
         CK(cudaMemcpyAsync(d_g2, g2_points, 192, cudaMemcpyHostToDevice, ctx->stream));
-        setup_tables_kernel<<<(2049 + 127) / 128, 128, 0, ctx->stream>>>(ctx->tables, d_g2);
+        setup_tables_kernel<<<(4096 + 960 + 127) / 128, 128, 0, ctx->stream>>>(ctx->tables, d_g2);
         CK(cudaGetLastError());
         uint32_t ok = 0;
         CK(cudaMemcpyAsync(&ok, &ctx->tables->setup_ok, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -122,7 +124,7 @@ extern "C" void kzgb200_destroy(kzgb200_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->tables, ctx->d_blobs, ctx->d_c, ctx->d_p, ctx->d_z_mont, ctx->d_zy, ctx->d_C, ctx->d_P, ctx->d_status,
-                    ctx->d_terms, ctx->d_ry, ctx->d_r, ctx->d_partial, ctx->d_result, ctx->d_zout, ctx->d_yout, ctx->d_many, ctx->d_wk};
+                    ctx->d_terms, ctx->d_ry, ctx->d_r, ctx->d_partial, ctx->d_result, ctx->d_zout, ctx->d_yout, ctx->d_many, ctx->d_wk, ctx->d_ri, ctx->d_rz};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -150,6 +152,15 @@ static int launch_phase1(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t
 }
 // K5
 static int launch_transcript(kzgb200_ctx* ctx, const uint8_t* d_all_c, const ZY* d_all_zy, const uint8_t* d_all_p, size_t n_total) {
+    if (ctx->transcript_mode == KZGB200_TRANSCRIPT_TREE) {
+        size_t ngroups = (n_total + kTreeGroup - 1) / kTreeGroup;
+        if (ngroups * 8 > ctx->wk_cap * 64) { CK(regrow(ctx->d_wk, ngroups * 8 + 64)); ctx->wk_cap = (ngroups * 8 + 64) / 64; }
+        transcript_tree_leaf_kernel<<<(unsigned)((ngroups + 63) / 64), 64, 0, ctx->stream>>>(d_all_c, d_all_zy, d_all_p, (uint64_t)n_total, ctx->d_wk);
+        transcript_tree_root_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_wk, (uint64_t)n_total, ctx->d_r);
+        mark(ctx, 4);
+        CK(cudaGetLastError());
+        return KZGB200_OK;
+    }
     size_t nblk = (32 + n_total * 160 + 9 + 63) / 64;
     if (nblk > ctx->wk_cap) { CK(regrow(ctx->d_wk, nblk * 64)); ctx->wk_cap = nblk; }
     transcript_schedule_kernel<<<(unsigned)((nblk + 127) / 128), 128, 0, ctx->stream>>>(d_all_c, d_all_zy, d_all_p, (uint64_t)n_total, ctx->d_wk);
@@ -161,12 +172,13 @@ static int launch_transcript(kzgb200_ctx* ctx, const uint8_t* d_all_c, const ZY*
 // K6: per-blob terms, tree sum, partial
 static int launch_lincomb(kzgb200_ctx* ctx, size_t offset, Partial* d_out) {
     int n = (int)ctx->cur_n;
-    lincomb_terms_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_C, ctx->d_P, ctx->d_z_mont, ctx->d_zy, ctx->d_r,
-                                                                  (uint64_t)offset, n, ctx->d_terms, ctx->d_ry);
+    lincomb_scalars_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_z_mont, ctx->d_zy, ctx->d_r, (uint64_t)offset, n,
+                                                                    ctx->d_ri, ctx->d_rz, ctx->d_ry);
+    lincomb_terms_kernel<<<(n * kChunks + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_C, ctx->d_P, ctx->d_ri, ctx->d_rz, n, ctx->d_terms);
     mark(ctx, 5);
     for (int count = n; count > 1;) {
         int half = (count + 1) / 2;
-        pair_sum_kernel<<<(half + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_terms, ctx->d_ry, count, half);
+        pair_sum_kernel<<<dim3((half + 127) / 128, kChunks), 128, 0, ctx->stream>>>(ctx->d_terms, ctx->d_ry, n, count, half);
         count = half;
     }
     finish_partial_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_terms, ctx->d_ry, ctx->d_status, n, d_out);
@@ -194,13 +206,13 @@ static int batch_device_locked(kzgb200_ctx* ctx, const uint8_t* d_blobs, const u
     if (rc) return rc;
     if ((rc = export_zy(ctx, n, d_z_out, d_y_out))) return rc;
     if (n == 1) {   // single path (reference src/kzg_proof.rs:482-489)
-        single_final_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_C, ctx->d_P, ctx->d_zy, ctx->d_status, ctx->tables, ctx->d_result);
+        single_final_kernel<<<1, kFinalThreads, 0, ctx->stream>>>(ctx->d_C, ctx->d_P, ctx->d_zy, ctx->d_status, ctx->tables, ctx->d_result);
         CK(cudaGetLastError());
         return read_result(ctx, ok);
     }
     if ((rc = launch_transcript(ctx, d_c, ctx->d_zy, d_p, n))) return rc;
     if ((rc = launch_lincomb(ctx, 0, ctx->d_partial))) return rc;
-    batch_final_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_partial, 1, ctx->tables, ctx->d_result);
+    batch_final_kernel<<<1, kFinalThreads, 0, ctx->stream>>>(ctx->d_partial, 1, ctx->tables, ctx->d_result);
     mark(ctx, 7);
     CK(cudaGetLastError());
     rc = read_result(ctx, ok);
@@ -319,7 +331,7 @@ extern "C" int kzgb200_shard_finalize(kzgb200_ctx* ctx, const uint8_t* d_partial
     if (!ctx || !d_partials || !ok || n_ranks == 0) return KZGB200_BAD_ARGS;
     std::lock_guard<std::mutex> g(ctx->lock);
     CK(cudaSetDevice(ctx->device));
-    batch_final_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const Partial*>(d_partials), (int)n_ranks, ctx->tables, ctx->d_result);
+    batch_final_kernel<<<1, kFinalThreads, 0, ctx->stream>>>(reinterpret_cast<const Partial*>(d_partials), (int)n_ranks, ctx->tables, ctx->d_result);
     CK(cudaGetLastError());
     return read_result(ctx, ok);
 }
@@ -347,6 +359,37 @@ extern "C" int kzgb200_harness_generate(kzgb200_ctx* ctx, uint64_t seed, size_t 
     CK(cudaStreamSynchronize(ctx->stream));
     cudaFree(d_bytes); cudaFree(d_M); cudaFree(d_bad);
     return bad ? KZGB200_BAD_ARGS : KZGB200_OK;
+}
+extern "C" int kzgb200_set_transcript_mode(kzgb200_ctx* ctx, int mode) {
+    if (!ctx || (mode != KZGB200_TRANSCRIPT_EXACT && mode != KZGB200_TRANSCRIPT_TREE)) return KZGB200_BAD_ARGS;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    ctx->transcript_mode = mode;
+    return KZGB200_OK;
+}
+// the canonical big-endian r of the last batch (exact mode: bit-identical to compute_r_powers' r)
+extern "C" int kzgb200_last_r(kzgb200_ctx* ctx, uint8_t* r_out32) {
+    if (!ctx || !r_out32) return KZGB200_BAD_ARGS;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    CK(cudaSetDevice(ctx->device));
+    ZY* tmp = nullptr;
+    CK(cudaMalloc(&tmp, sizeof(ZY)));
+    r_to_raw_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_r, tmp);
+    uint8_t* d_out = nullptr;
+    CK(cudaMalloc(&d_out, 32));
+    export_scalars_kernel<<<1, 1, 0, ctx->stream>>>(tmp, 1, d_out, nullptr);
+    CK(cudaMemcpyAsync(r_out32, d_out, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(tmp); cudaFree(d_out);
+    return KZGB200_OK;
+}
+// raw per-rank partial of the last single-GPU batch (Partial struct: Jacobian A, B in Montgomery limbs, sum r_i y_i, flags)
+extern "C" int kzgb200_last_partial(kzgb200_ctx* ctx, uint8_t* out352) {
+    if (!ctx || !out352) return KZGB200_BAD_ARGS;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(out352, ctx->d_partial, sizeof(Partial), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return KZGB200_OK;
 }
 // per-phase device times of the last single-GPU batch call: parse, challenge, eval, transcript, lincomb, reduce, final
 extern "C" int kzgb200_set_profiling(kzgb200_ctx* ctx, int on) {

@@ -105,3 +105,88 @@ def test_reference_batch_harness_shape_n1(K, settings, vectors):
 
 def test_empty_batch_is_true(K, settings):
     assert K.KzgProof.verify_blob_kzg_proof_batch([], [], [], settings) is True   # kzg_proof.rs:478-480
+
+
+def _batch_case(vectors, n):
+    return [c for c in vectors["verify_blob_kzg_proof_batch"] if c["output"] is True and len(c["blobs"]) == n][0]
+
+
+def test_batch_intermediates_r_and_msm_sums_bit_exact(K, settings, vectors, oracle):
+    """Exact transcript mode: r, sum r_i pi_i and rhs_g1 equal the oracle's (kzg_proof.rs:413-433), for n = 2..6."""
+    from kzg_rs_b200 import api
+    from oracle import pyref as R
+    for n in (2, 3, 5, 6):
+        c = _batch_case(vectors, n)
+        blobs = [vectors.blobs[i] for i in c["blobs"]]
+        cs, ps = [unhex(x) for x in c["commitments"]], [unhex(x) for x in c["proofs"]]
+        assert K.KzgProof.verify_blob_kzg_proof_batch(blobs, cs, ps, settings) is True
+        got = api.last_batch_intermediates(settings)
+        ok, rc, zs, ys, tr = oracle.verify_blob_kzg_proof_batch(blobs, cs, ps, want_trace=True)
+        assert got["r"] == tr["r"], n
+        assert R.g1_to_compressed(got["A"]) == tr["proof_lincomb"], n
+        rhs = R.g1_add(got["B_prime"], R.g1_neg(R.g1_mul(R.G1_GEN, got["sum_r_y"])))
+        assert R.g1_to_compressed(rhs) == tr["rhs_g1"], n
+
+
+def test_tree_transcript_mode_same_verdicts(K, settings, vectors, oracle):
+    """Opt-in tree transcript: r differs from kzg-rs's, verdicts and z / y do not."""
+    from kzg_rs_b200 import api
+    api.set_transcript_mode(settings, api.TRANSCRIPT_TREE)
+    try:
+        for c in vectors["verify_blob_kzg_proof_batch"]:
+            def run():
+                return K.KzgProof.verify_blob_kzg_proof_batch([K.Blob.from_slice(vectors.blobs[i]) for i in c["blobs"]],
+                                                              [K.Bytes48.from_hex(x) for x in c["commitments"]],
+                                                              [K.Bytes48.from_hex(x) for x in c["proofs"]], settings)
+            assert tri(run) == c["output"], c["name"]
+        c = _batch_case(vectors, 4)
+        args = ([vectors.blobs[i] for i in c["blobs"]], [unhex(x) for x in c["commitments"]], [unhex(x) for x in c["proofs"]])
+        assert K.KzgProof.verify_blob_kzg_proof_batch(*args, settings) is True
+        r_tree = api.last_batch_intermediates(settings)["r"]
+    finally:
+        api.set_transcript_mode(settings, api.TRANSCRIPT_EXACT)
+    assert K.KzgProof.verify_blob_kzg_proof_batch(*args, settings) is True
+    assert api.last_batch_intermediates(settings)["r"] != r_tree
+
+
+def test_synthetic_batch_64_against_oracle(K, settings, oracle):
+    """BASELINE configs[2]: 64 synthetic blobs (harness generator): verdict, every z_i, y_i, r and both sums vs the
+    oracle; then a corrupted-proof batch (-> false) and a non-canonical element (-> Err)."""
+    import ctypes as C
+    import os
+    import torch
+    from kzg_rs_b200 import api
+    from oracle import pyref as R
+    lib, ctx, n = K.Library.get().dll, settings.context(0), 64
+    tau = open(os.path.join(os.path.dirname(K.__file__), "data", "tau_powers_g1.bin"), "rb").read()
+    blobs = torch.empty(n * 131072, dtype=torch.uint8, device="cuda")
+    cs = torch.empty(n * 48, dtype=torch.uint8, device="cuda")
+    ps = torch.empty(n * 48, dtype=torch.uint8, device="cuda")
+    assert lib.kzgb200_harness_generate(ctx, 0x4B5A47, n, 8, tau, blobs.data_ptr(), cs.data_ptr(), ps.data_ptr()) == 0
+    hb, hc, hp = (t.cpu().numpy().tobytes() for t in (blobs, cs, ps))
+    # the generator itself: commitments and proofs equal the oracle's commit/prove on the same blobs
+    for i in (0, 17, 63):
+        b = hb[i * 131072:(i + 1) * 131072]
+        assert oracle.blob_to_kzg_commitment(b) == hc[i * 48:(i + 1) * 48]
+        assert oracle.compute_blob_kzg_proof(b, hc[i * 48:(i + 1) * 48]) == hp[i * 48:(i + 1) * 48]
+    ok, zs, ys = K.KzgProof.verify_blob_kzg_proof_batch_raw(hb, n, hc, n, hp, n, settings, want_zy=True)
+    split = lambda raw, k: [raw[k * i:k * i + k] for i in range(n)]
+    ok_ref, rc, z_ref, y_ref, tr = oracle.verify_blob_kzg_proof_batch(split(hb, 131072), split(hc, 48), split(hp, 48), nthreads=8, want_trace=True)
+    assert ok is True and ok_ref is True and zs == z_ref and ys == y_ref
+    got = api.last_batch_intermediates(settings)
+    assert got["r"] == tr["r"] and R.g1_to_compressed(got["A"]) == tr["proof_lincomb"]
+    rhs = R.g1_add(got["B_prime"], R.g1_neg(R.g1_mul(R.G1_GEN, got["sum_r_y"])))
+    assert R.g1_to_compressed(rhs) == tr["rhs_g1"]
+    # proof 17 replaced by proof 18 -> false
+    bad = bytearray(hp); bad[17 * 48:18 * 48] = hp[18 * 48:19 * 48]
+    assert K.KzgProof.verify_blob_kzg_proof_batch_raw(hb, n, hc, n, bytes(bad), n, settings) is False
+    # element 9 of blob 5 set to the modulus -> Err(BadArgs)
+    q = bytes.fromhex("73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001")
+    badb = bytearray(hb); badb[5 * 131072 + 9 * 32:5 * 131072 + 10 * 32] = q
+    with pytest.raises(K.KzgError) as e:
+        K.KzgProof.verify_blob_kzg_proof_batch_raw(bytes(badb), n, hc, n, hp, n, settings)
+    assert e.value.kind == "BadArgs"
+    # length mismatch -> InvalidBytesLength (kzg_proof.rs:491-501)
+    with pytest.raises(K.KzgError) as e:
+        K.KzgProof.verify_blob_kzg_proof_batch_raw(hb, n, hc, n - 1, hp, n, settings)
+    assert e.value.kind == "InvalidBytesLength"

@@ -1,0 +1,560 @@
+#!/usr/bin/env python3
+"""Generate kzg_rs_b200/csrc/vliw_programs.cuh: straight-line Fp programs for the cooperative pairing engine.
+
+The serial tails of the batch (one pairing check, the Horner recombination of the MSM) are long chains of
+Fp12 / point operations.  One thread runs them at ~1 us per Fp multiplication; a CTA can run the independent
+Fp multiplications inside each Fp12 / point operation side by side.  This script traces the tower / curve
+formulas symbolically, keeps additions lazy (values are small-integer linear combinations of materialised
+registers), and emits each operation as a short list of LEVELS of independent instructions over a register file
+of Fp values in shared memory:
+    MUL : dst = s0*s1 [+/- s2*s3]      (fused dual Montgomery product)
+    LIN : dst = sum_k (+/-)(1|2) * src_k
+Instruction k of a level is executed by thread k; levels are separated by a barrier (vliw.cuh).
+
+Self-check: every program is interpreted here with Python integers and compared with oracle/pyref.py.
+    python tools/gen_vliw.py
+"""
+import os
+import random
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import pyref as R
+
+P = R.P
+MAX_LIN_TERMS = 24
+
+
+class Val:
+    """small-integer linear combination of registers"""
+    __slots__ = ("t",)
+
+    def __init__(self, t=None):
+        self.t = {k: v for k, v in (t or {}).items() if v != 0}
+
+    def __add__(self, o):
+        t = dict(self.t)
+        for k, v in o.t.items():
+            t[k] = t.get(k, 0) + v
+        return Val(t)
+
+    def __sub__(self, o):
+        t = dict(self.t)
+        for k, v in o.t.items():
+            t[k] = t.get(k, 0) - v
+        return Val(t)
+
+    def __neg__(self):
+        return Val({k: -v for k, v in self.t.items()})
+
+    def scale(self, c):
+        return Val({k: v * c for k, v in self.t.items()})
+
+
+class Builder:
+    def __init__(self, name, n_inputs):
+        self.name = name
+        self.n_inputs = n_inputs
+        self.next_reg = n_inputs
+        self.level_of = {r: 0 for r in range(n_inputs)}   # reg -> level at which it becomes available
+        self.instrs = []                                    # (level, kind, dst, payload)
+        self.cache = {}
+
+    def input(self, i):
+        return Val({i: 1})
+
+    def _new(self, level):
+        r = self.next_reg
+        self.next_reg += 1
+        self.level_of[r] = level
+        return r
+
+    def materialize(self, v):
+        """register holding v (emits a LIN unless v is a plain register)"""
+        if len(v.t) == 1 and list(v.t.values())[0] == 1:
+            return list(v.t.keys())[0]
+        key = tuple(sorted(v.t.items()))
+        if key in self.cache:
+            return self.cache[key]
+        terms = []
+        for r, c in sorted(v.t.items()):
+            neg, c = c < 0, abs(c)
+            while c >= 2:
+                terms.append((r, neg, True))
+                c -= 2
+            if c:
+                terms.append((r, neg, False))
+        if len(terms) > MAX_LIN_TERMS:   # split long sums
+            half = len(v.t) // 2
+            items = sorted(v.t.items())
+            a = self.materialize(Val(dict(items[:half])))
+            b = self.materialize(Val(dict(items[half:])))
+            return self.materialize(Val({a: 1}) + Val({b: 1}))
+        level = 1 + max((self.level_of[r] for r, _, _ in terms), default=0)
+        dst = self._new(level)
+        self.instrs.append((level, "LIN", dst, terms))
+        self.cache[key] = dst
+        return dst
+
+    def mul(self, a, b, c=None, d=None, neg=False):
+        """a*b (+|-) c*d"""
+        ra, rb = self.materialize(a), self.materialize(b)
+        srcs = [ra, rb]
+        if c is not None:
+            srcs += [self.materialize(c), self.materialize(d)]
+        level = 1 + max(self.level_of[r] for r in srcs)
+        dst = self._new(level)
+        self.instrs.append((level, "MUL", dst, (srcs, neg)))
+        return Val({dst: 1})
+
+    def output(self, v, reg):
+        """force v into register `reg` (an input slot being overwritten or a dedicated output slot)"""
+        terms = []
+        for r, c in sorted(v.t.items()):
+            ng, c = c < 0, abs(c)
+            while c >= 2:
+                terms.append((r, ng, True)); c -= 2
+            if c:
+                terms.append((r, ng, False))
+        if len(terms) > MAX_LIN_TERMS:
+            m = self.materialize(v)
+            terms = [(m, False, False)]
+        level = 1 + max((self.level_of[r] for r, _, _ in terms), default=0)
+        self.instrs.append((level, "OUT", reg, terms))
+
+    def finish(self):
+        """Level schedule.  ASAP levels first; then MUL instructions sink to the latest level their consumers
+        allow (so an operation's independent products share ONE multiplication level instead of splitting into
+        "products of raw inputs" and "products of sums"); all OUT instructions form one extra final level, which
+        makes overwriting input registers safe."""
+        body = [list(i) for i in self.instrs if i[1] != "OUT"]
+        outs = [i for i in self.instrs if i[1] == "OUT"]
+        last = max([i[0] for i in body] + [0])
+        by_dst = {i[2]: i for i in body}
+        def srcs_of(i):
+            return i[3][0] if i[1] == "MUL" else [r for r, _, _ in i[3]]
+        changed = True
+        while changed:
+            changed = False
+            limit = {}
+            for i in body:
+                for r in srcs_of(i):
+                    if r in by_dst:
+                        limit[r] = min(limit.get(r, last + 1), i[0])
+            for i in body:
+                if i[1] != "MUL":
+                    continue
+                alap = limit.get(i[2], last + 1) - 1
+                if alap > i[0]:
+                    i[0] = alap
+                    changed = True
+        levels = {}
+        for lv, k, dst, pay in body:
+            levels.setdefault((lv, k), []).append((k, dst, pay))
+        prog = []
+        for lv in range(1, last + 1):
+            for kind in ("LIN", "MUL"):
+                if (lv, kind) in levels:
+                    prog.append((kind, levels[(lv, kind)]))
+        if outs:
+            prog.append(("LIN", [("LIN", dst, pay) for _, _, dst, pay in outs]))
+        return prog
+
+
+def check_hazards(prog, n_inputs):
+    """within a level no instruction may read a register written in the same level"""
+    for kind, ins in prog:
+        written = set(d for _, d, _ in ins)
+        assert len(written) == len(ins), "two instructions of a level write the same register"
+        for _, d, pay in ins:
+            srcs = pay[0] if kind == "MUL" else [r for r, _, _ in pay]
+            assert not ((set(srcs) - {d}) & written), "read/write hazard inside a level"
+
+
+# ------------------------------------------------------------------------------------------ symbolic tower
+class F2:
+    def __init__(self, c0, c1): self.c0, self.c1 = c0, c1
+    def __add__(s, o): return F2(s.c0 + o.c0, s.c1 + o.c1)
+    def __sub__(s, o): return F2(s.c0 - o.c0, s.c1 - o.c1)
+    def neg(s): return F2(-s.c0, -s.c1)
+    def dbl(s): return F2(s.c0.scale(2), s.c1.scale(2))
+    def conj(s): return F2(s.c0, -s.c1)
+    def mul_xi(s): return F2(s.c0 - s.c1, s.c0 + s.c1)
+    def mul(s, o, B): return F2(B.mul(s.c0, o.c0, s.c1, o.c1, neg=True), B.mul(s.c0, o.c1, s.c1, o.c0))
+    def sqr(s, B): return F2(B.mul(s.c0 + s.c1, s.c0 - s.c1), B.mul(s.c0, s.c1).scale(2))
+    def mul_fp(s, k, B): return F2(B.mul(s.c0, k), B.mul(s.c1, k))
+
+
+class F6:
+    def __init__(self, c0, c1, c2): self.c0, self.c1, self.c2 = c0, c1, c2
+    def __add__(s, o): return F6(s.c0 + o.c0, s.c1 + o.c1, s.c2 + o.c2)
+    def __sub__(s, o): return F6(s.c0 - o.c0, s.c1 - o.c1, s.c2 - o.c2)
+    def neg(s): return F6(s.c0.neg(), s.c1.neg(), s.c2.neg())
+    def mul_v(s): return F6(s.c2.mul_xi(), s.c0, s.c1)
+    def mul(a, b, B):
+        t0, t1, t2 = a.c0.mul(b.c0, B), a.c1.mul(b.c1, B), a.c2.mul(b.c2, B)
+        r0 = t0 + ((a.c1 + a.c2).mul(b.c1 + b.c2, B) - t1 - t2).mul_xi()
+        r1 = (a.c0 + a.c1).mul(b.c0 + b.c1, B) - t0 - t1 + t2.mul_xi()
+        r2 = (a.c0 + a.c2).mul(b.c0 + b.c2, B) - t0 - t2 + t1
+        return F6(r0, r1, r2)
+
+
+class F12:
+    def __init__(self, c0, c1): self.c0, self.c1 = c0, c1
+    def mul(a, b, B):
+        t0, t1 = a.c0.mul(b.c0, B), a.c1.mul(b.c1, B)
+        m = (a.c0 + a.c1).mul(b.c0 + b.c1, B) - t0 - t1
+        return F12(t0 + t1.mul_v(), m)
+    def sqr(a, B):
+        ab = a.c0.mul(a.c1, B)
+        s = (a.c0 + a.c1).mul(a.c0 + a.c1.mul_v(), B) - ab - ab.mul_v()
+        return F12(s, ab + ab)
+    def conj(a): return F12(a.c0, a.c1.neg())
+    def flat(a): return [a.c0.c0.c0, a.c0.c0.c1, a.c0.c1.c0, a.c0.c1.c1, a.c0.c2.c0, a.c0.c2.c1,
+                         a.c1.c0.c0, a.c1.c0.c1, a.c1.c1.c0, a.c1.c1.c1, a.c1.c2.c0, a.c1.c2.c1]
+
+
+def f12_in(B, base):
+    v = [B.input(base + i) for i in range(12)]
+    return F12(F6(F2(v[0], v[1]), F2(v[2], v[3]), F2(v[4], v[5])), F6(F2(v[6], v[7]), F2(v[8], v[9]), F2(v[10], v[11])))
+
+
+def f2_in(B, base):
+    return F2(B.input(base), B.input(base + 1))
+
+
+def out12(B, x, base):
+    for i, v in enumerate(x.flat()):
+        B.output(v, base + i)
+
+
+# Register-file layout shared with vliw.cuh -------------------------------------------------------------------
+# pairing programs: F = regs 0..11 (the Miller / exponentiation accumulator), G = 12..23, H = 24..35 (second /
+# third Fp12 operand or result), line inputs 36..47: two lines (A, Bx, Cy as Fp2: 6 Fp each), constants 48..57
+# (Frobenius coefficients xi^(k(p-1)/6), k = 1..5, as Fp2), scratch from 64.
+RF = 12
+RG = 12
+RH = 24
+RL = 36
+RC = 48
+RP = 58          # xP1, yP1, xP2, yP2 (G1 arguments of the two pairs)
+N_IN = 64
+
+
+def prog_f12_mul():        # F <- F * G
+    B = Builder("f12_mul", N_IN)
+    out12(B, f12_in(B, 0).mul(f12_in(B, RG), B), 0)
+    return B
+
+
+def prog_f12_sqr():        # F <- F^2
+    B = Builder("f12_sqr", N_IN)
+    out12(B, f12_in(B, 0).sqr(B), 0)
+    return B
+
+
+def sparse014(A, Bx, Cy):
+    z = Val()
+    return F12(F6(A, Bx, F2(z, z)), F6(F2(z, z), Cy, F2(z, z)))
+
+
+def line_in(B, j):
+    """line j (raw A, B, C at RL + 6j) evaluated at P_j = (regs RP+2j, RP+2j+1): A + (B xP) v + (C yP) vw"""
+    A, Bc, Cc = f2_in(B, RL + 6 * j), f2_in(B, RL + 6 * j + 2), f2_in(B, RL + 6 * j + 4)
+    xP, yP = B.input(RP + 2 * j), B.input(RP + 2 * j + 1)
+    return sparse014(A, Bc.mul_fp(xP, B), Cc.mul_fp(yP, B))
+
+
+def prog_sqr_lines():      # F <- F^2 ; G <- line1(P1) * line2(P2)
+    B = Builder("sqr_lines", N_IN)
+    f2 = f12_in(B, 0).sqr(B)
+    out12(B, f2, 0)
+    out12(B, sparse_mul(line_in(B, 0), line_in(B, 1), B), RG)
+    return B
+
+
+def prog_lines():          # G <- line1(P1) * line2(P2)
+    B = Builder("lines", N_IN)
+    out12(B, sparse_mul(line_in(B, 0), line_in(B, 1), B), RG)
+    return B
+
+
+def prog_line1():          # G <- line1(P1) as a full Fp12 element (the other pair is skipped)
+    B = Builder("line1", N_IN)
+    out12(B, line_in(B, 0), RG)
+    return B
+
+
+def prog_conj_g():         # G <- conj(G)
+    B = Builder("conj_g", N_IN)
+    out12(B, f12_in(B, RG).conj(), RG)
+    return B
+
+
+def sparse_mul(a, b, B):
+    """(a0 + a1 v + a4 vw)(b0 + b1 v + b4 vw) written out (zero coefficients skipped)"""
+    a0, a1, a4 = a.c0.c0, a.c0.c1, a.c1.c1
+    b0, b1, b4 = b.c0.c0, b.c0.c1, b.c1.c1
+    c0 = a0.mul(b0, B) + a4.mul(b4, B).mul_xi()
+    c1 = a0.mul(b1, B) + a1.mul(b0, B)
+    c2 = a1.mul(b1, B)
+    d0 = F2(Val(), Val())
+    d1 = a0.mul(b4, B) + a4.mul(b0, B)
+    d2 = a1.mul(b4, B) + a4.mul(b1, B)
+    return F12(F6(c0, c1, c2), F6(d0, d1, d2))
+
+
+def prog_conj():           # F <- conj(F)
+    B = Builder("conj", N_IN)
+    out12(B, f12_in(B, 0).conj(), 0)
+    return B
+
+
+def frob(B, a):
+    g = [None] + [f2_in(B, RC + 2 * (k - 1)) for k in range(1, 6)]
+    c = a
+    return F12(F6(c.c0.c0.conj(), c.c0.c1.conj().mul(g[2], B), c.c0.c2.conj().mul(g[4], B)),
+               F6(c.c1.c0.conj().mul(g[1], B), c.c1.c1.conj().mul(g[3], B), c.c1.c2.conj().mul(g[5], B)))
+
+
+def prog_frob():           # G <- frob(F)
+    B = Builder("frob", N_IN)
+    out12(B, frob(B, f12_in(B, 0)), RG)
+    return B
+
+
+def prog_frob2():          # G <- frob(frob(F))
+    B = Builder("frob2", N_IN)
+    out12(B, frob(B, frob(B, f12_in(B, 0))), RG)
+    return B
+
+
+def prog_inv_prep():
+    """Fp12 inversion, part 1: F = a0 + a1 w.  t = a0^2 - v a1^2 (Fp6); its Fp6 inverse needs the Fp2 norm
+    n2 = t0*c0 + xi(t2*c1 + t1*c2) and then the Fp norm n = n2.c0^2 + n2.c1^2.  Outputs: H[0..5] = (c0,c1,c2)
+    cofactors, H[6..7] = n2, H[8] = n (to be inverted by the caller), G = copy of F."""
+    B = Builder("inv_prep", N_IN)
+    a = f12_in(B, 0)
+    t = a.c0.mul(a.c0, B) - a.c1.mul(a.c1, B).mul_v()
+    c0 = t.c0.sqr(B) - t.c1.mul(t.c2, B).mul_xi()
+    c1 = t.c2.sqr(B).mul_xi() - t.c0.mul(t.c1, B)
+    c2 = t.c1.sqr(B) - t.c0.mul(t.c2, B)
+    n2 = t.c0.mul(c0, B) + (t.c2.mul(c1, B) + t.c1.mul(c2, B)).mul_xi()
+    n = B.mul(n2.c0, n2.c0, n2.c1, n2.c1)
+    for i, v in enumerate([c0.c0, c0.c1, c1.c0, c1.c1, c2.c0, c2.c1, n2.c0, n2.c1, n]):
+        B.output(v, RH + i)
+    out12(B, a, RG)
+    return B
+
+
+def prog_inv_finish():
+    """part 2: H[8] now holds 1/n.  n2^-1 = conj(n2)/n ; t^-1 = (c0,c1,c2) * n2^-1 ; F <- (a0 t^-1, -a1 t^-1)
+    with a = G."""
+    B = Builder("inv_finish", N_IN)
+    a = f12_in(B, RG)
+    c = [f2_in(B, RH), f2_in(B, RH + 2), f2_in(B, RH + 4)]
+    n2, ninv = f2_in(B, RH + 6), B.input(RH + 8)
+    n2i = F2(B.mul(n2.c0, ninv), -B.mul(n2.c1, ninv))
+    ti = F6(c[0].mul(n2i, B), c[1].mul(n2i, B), c[2].mul(n2i, B))
+    out12(B, F12(a.c0.mul(ti, B), a.c1.mul(ti, B).neg()), 0)
+    return B
+
+
+def prog_copy(src, dst, name):
+    B = Builder(name, N_IN)
+    for i in range(12):
+        B.output(B.input(src + i), dst + i)
+    return B
+
+
+# G1 Jacobian programs for the MSM recombination: point X,Y,Z = regs 0,1,2 ; second point 3,4,5
+def prog_g1_dbl():
+    B = Builder("g1_dbl", N_IN)
+    X, Y, Z = B.input(0), B.input(1), B.input(2)
+    A, Bq = B.mul(X, X), B.mul(Y, Y)
+    C = B.mul(Bq, Bq)
+    t = X + Bq
+    D = (B.mul(t, t) - A - C).scale(2)
+    E = A.scale(3)
+    F = B.mul(E, E)
+    X3 = F - D.scale(2)
+    Y3 = B.mul(E, D - X3) - C.scale(8)
+    Z3 = B.mul(Y, Z).scale(2)
+    B.output(X3, 0); B.output(Y3, 1); B.output(Z3, 2)
+    return B
+
+
+def prog_g1_add():
+    """generic Jacobian addition (0,1,2) += (3,4,5); the caller handles identities / equal points.
+    Also leaves H = U2-U1 in reg 6 and R = S2-S1 in reg 7 for the caller's special-case test."""
+    B = Builder("g1_add", N_IN)
+    X1, Y1, Z1, X2, Y2, Z2 = (B.input(i) for i in range(6))
+    Z1Z1, Z2Z2 = B.mul(Z1, Z1), B.mul(Z2, Z2)
+    U1, U2 = B.mul(X1, Z2Z2), B.mul(X2, Z1Z1)
+    S1, S2 = B.mul(B.mul(Y1, Z2Z2), Z2), B.mul(B.mul(Y2, Z1Z1), Z1)
+    H, Rr = U2 - U1, S2 - S1
+    H2 = B.mul(H, H)
+    H3, UH2 = B.mul(H2, H), B.mul(U1, H2)
+    X3 = B.mul(Rr, Rr) - H3 - UH2.scale(2)
+    Y3 = B.mul(Rr, UH2 - X3) - B.mul(S1, H3)
+    Z3 = B.mul(B.mul(Z1, Z2), H)
+    B.output(X3, 0); B.output(Y3, 1); B.output(Z3, 2); B.output(H, 6); B.output(Rr, 7)
+    return B
+
+
+PROGRAMS = [prog_f12_mul, prog_f12_sqr, prog_sqr_lines, prog_lines, prog_line1, prog_conj, prog_conj_g, prog_frob, prog_frob2,
+            prog_inv_prep, prog_inv_finish, prog_g1_dbl, prog_g1_add]
+
+
+# ------------------------------------------------------------------------------------------ python interpreter
+def run(prog, regs):
+    for kind, ins in prog:
+        new = {}
+        for _, dst, pay in ins:
+            if kind == "MUL":
+                (s, neg) = pay
+                v = regs[s[0]] * regs[s[1]]
+                if len(s) == 4:
+                    w = regs[s[2]] * regs[s[3]]
+                    v = v - w if neg else v + w
+            else:
+                v = 0
+                for r, ng, db in pay:
+                    t = regs[r] * (2 if db else 1)
+                    v = v - t if ng else v + t
+            new[dst] = v % P
+        regs.update(new)
+
+
+def selftest(progs):
+    rnd = random.Random(11)
+    def rnd12():
+        return tuple(tuple((rnd.randrange(P), rnd.randrange(P)) for _ in range(3)) for _ in range(2))
+    def flat(a):
+        return [x for c6 in a for c2 in c6 for x in c2]
+    def unflat(v):
+        return ((tuple(v[0:2]), tuple(v[2:4]), tuple(v[4:6])), (tuple(v[6:8]), tuple(v[8:10]), tuple(v[10:12])))
+    G6 = [R.f2_pow(R.XI, k * (P - 1) // 6) for k in range(6)]
+    def fresh():
+        regs = {i: rnd.randrange(P) for i in range(4096)}
+        for k in range(1, 6):
+            regs[RC + 2 * (k - 1)], regs[RC + 2 * (k - 1) + 1] = G6[k]
+        return regs
+    for _ in range(3):
+        f, g = rnd12(), rnd12()
+        regs = fresh()
+        for i, v in enumerate(flat(f)): regs[i] = v
+        for i, v in enumerate(flat(g)): regs[RG + i] = v
+        r2 = dict(regs); run(progs["f12_mul"], r2)
+        assert unflat([r2[i] for i in range(12)]) == R.f12_mul(f, g)
+        r2 = dict(regs); run(progs["f12_sqr"], r2)
+        assert unflat([r2[i] for i in range(12)]) == R.f12_sqr(f)
+        r2 = dict(regs); run(progs["conj"], r2)
+        assert unflat([r2[i] for i in range(12)]) == R.f12_conj(f)
+        r2 = dict(regs); run(progs["frob"], r2)
+        assert unflat([r2[RG + i] for i in range(12)]) == R.f12_frob(f)
+        r2 = dict(regs); run(progs["frob2"], r2)
+        assert unflat([r2[RG + i] for i in range(12)]) == R.f12_frob(R.f12_frob(f))
+        # lines
+        lines = [(rnd.randrange(P), rnd.randrange(P)) for _ in range(6)]
+        for i, (a, b) in enumerate(lines):
+            regs[RL + 2 * i], regs[RL + 2 * i + 1] = a, b
+        Z = R.F2_ZERO
+        pc = [rnd.randrange(P) for _ in range(4)]
+        for i in range(4): regs[RP + i] = pc[i]
+        sc = lambda v, k: (v[0] * k % P, v[1] * k % P)
+        l1 = ((lines[0], sc(lines[1], pc[0]), Z), (Z, sc(lines[2], pc[1]), Z))
+        l2 = ((lines[3], sc(lines[4], pc[2]), Z), (Z, sc(lines[5], pc[3]), Z))
+        r2 = dict(regs); run(progs["sqr_lines"], r2)
+        assert unflat([r2[i] for i in range(12)]) == R.f12_sqr(f)
+        assert unflat([r2[RG + i] for i in range(12)]) == R.f12_mul(l1, l2)
+        r2 = dict(regs); run(progs["lines"], r2)
+        assert unflat([r2[RG + i] for i in range(12)]) == R.f12_mul(l1, l2)
+        r2 = dict(regs); run(progs["line1"], r2)
+        assert unflat([r2[RG + i] for i in range(12)]) == l1
+        r2 = dict(regs); run(progs["conj_g"], r2)
+        assert unflat([r2[RG + i] for i in range(12)]) == R.f12_conj(g)
+        # inversion
+        r2 = dict(regs); run(progs["inv_prep"], r2)
+        r2[RH + 8] = pow(r2[RH + 8], P - 2, P)
+        run(progs["inv_finish"], r2)
+        assert unflat([r2[i] for i in range(12)]) == R.f12_inv(f)
+        # G1
+        p1 = R.g1_mul(R.G1_GEN, rnd.randrange(R.Q)); p2 = R.g1_mul(R.G1_GEN, rnd.randrange(R.Q))
+        z1, z2 = rnd.randrange(1, P), rnd.randrange(1, P)
+        regs[0], regs[1], regs[2] = p1[0] * z1 * z1 % P, p1[1] * z1 ** 3 % P, z1
+        regs[3], regs[4], regs[5] = p2[0] * z2 * z2 % P, p2[1] * z2 ** 3 % P, z2
+        def aff(r):
+            zi = pow(r[2], P - 2, P); return (r[0] * zi * zi % P, r[1] * zi ** 3 % P)
+        r2 = dict(regs); run(progs["g1_dbl"], r2)
+        assert aff(r2) == R.g1_add(p1, p1)
+        r2 = dict(regs); run(progs["g1_add"], r2)
+        assert aff(r2) == R.g1_add(p1, p2)
+    print("python self-test of all programs: ok")
+
+
+def emit(progs, path):
+    out = ["// GENERATED by tools/gen_vliw.py -- do not edit.  Level-scheduled Fp programs for vliw.cuh.",
+           "#pragma once", "#include <stdint.h>", "namespace kzgb200 { namespace vliw {",
+           "constexpr int kRegF = 0, kRegG = %d, kRegH = %d, kRegLines = %d, kRegConst = %d, kRegP = %d, kNumInputRegs = %d;" % (RG, RH, RL, RC, RP, N_IN),
+           "// MUL instruction: dst, s0, s1, s2, s3 (s2 = 0xffff: single product), flag bit0 = subtract the second product",
+           "// LIN instruction: dst, first term index, term count; a term = reg | neg << 14 | dbl << 15",
+           "struct Level { uint16_t kind /*0 LIN, 1 MUL*/, count; uint32_t first; };",
+           "struct Program { uint16_t first_level, n_levels, n_regs; };"]
+    mul_tab, lin_tab, term_tab, level_tab, prog_tab, names = [], [], [], [], [], []
+    stats = []
+    for name, prog in progs.items():
+        first_level = len(level_tab)
+        n_regs = N_IN
+        nmul = nlin = 0
+        for kind, ins in prog:
+            if kind == "MUL":
+                level_tab.append((1, len(ins), len(mul_tab)))
+                for _, dst, (s, neg) in ins:
+                    s = list(s) + [0xffff, 0xffff] if len(s) == 2 else list(s)
+                    mul_tab.append((dst, s[0], s[1], s[2], s[3], 1 if neg else 0))
+                    n_regs = max(n_regs, dst + 1)
+                nmul += len(ins)
+            else:
+                level_tab.append((0, len(ins), len(lin_tab)))
+                for _, dst, terms in ins:
+                    lin_tab.append((dst, len(term_tab), len(terms)))
+                    for r, ng, db in terms:
+                        term_tab.append(r | (1 << 14 if ng else 0) | (1 << 15 if db else 0))
+                    n_regs = max(n_regs, dst + 1)
+                nlin += len(ins)
+        prog_tab.append((first_level, len(level_tab) - first_level, n_regs))
+        names.append(name)
+        stats.append((name, len(level_tab) - first_level, nmul, nlin, n_regs))
+    out.append("enum ProgramId { " + ", ".join("kProg_%s = %d" % (n, i) for i, n in enumerate(names)) + ", kNumPrograms = %d };" % len(names))
+    out.append("constexpr int kMaxRegs = %d;" % max(p[2] for p in prog_tab))
+    out.append("constexpr int kNumMul = %d, kNumLin = %d, kNumTerm = %d, kNumLevel = %d;" % (len(mul_tab), len(lin_tab), len(term_tab), len(level_tab)))
+    out.append("static __device__ const uint16_t d_mul[%d][6] = {%s};" % (len(mul_tab), ",".join("{%d,%d,%d,%d,%d,%d}" % m for m in mul_tab)))
+    out.append("static __device__ const uint32_t d_lin[%d][3] = {%s};" % (len(lin_tab), ",".join("{%d,%d,%d}" % m for m in lin_tab)))
+    out.append("static __device__ const uint16_t d_term[%d] = {%s};" % (len(term_tab), ",".join(str(t) for t in term_tab)))
+    out.append("static __device__ const Level d_level[%d] = {%s};" % (len(level_tab), ",".join("{%d,%d,%d}" % l for l in level_tab)))
+    out.append("static __device__ const Program d_prog[%d] = {%s};" % (len(prog_tab), ",".join("{%d,%d,%d}" % p for p in prog_tab)))
+    # host copies for the CPU unit test of the interpreter
+    out.append("#ifndef __CUDA_ARCH__")
+    out.append("static const uint16_t h_mul[%d][6] = {%s};" % (len(mul_tab), ",".join("{%d,%d,%d,%d,%d,%d}" % m for m in mul_tab)))
+    out.append("static const uint32_t h_lin[%d][3] = {%s};" % (len(lin_tab), ",".join("{%d,%d,%d}" % m for m in lin_tab)))
+    out.append("static const uint16_t h_term[%d] = {%s};" % (len(term_tab), ",".join(str(t) for t in term_tab)))
+    out.append("static const Level h_level[%d] = {%s};" % (len(level_tab), ",".join("{%d,%d,%d}" % l for l in level_tab)))
+    out.append("static const Program h_prog[%d] = {%s};" % (len(prog_tab), ",".join("{%d,%d,%d}" % p for p in prog_tab)))
+    out.append("#endif")
+    out.append("}}  // namespace kzgb200::vliw")
+    open(path, "w").write("\n".join(out) + "\n")
+    for s in stats:
+        print("%-14s levels %2d  MUL %3d  LIN %3d  regs %3d" % s)
+
+
+if __name__ == "__main__":
+    progs = {}
+    for mk in PROGRAMS:
+        B = mk()
+        prog = B.finish()
+        check_hazards(prog, N_IN)
+        progs[B.name] = prog
+    selftest(progs)
+    emit(progs, os.path.join(ROOT, "kzg_rs_b200", "csrc", "vliw_programs.cuh"))
