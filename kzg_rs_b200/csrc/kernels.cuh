@@ -391,51 +391,88 @@ __global__ void transcript_tree_root_kernel(const uint32_t* __restrict__ digests
 // [y_i]G:   A = sum r_i pi_i ,  B = sum (r_i C_i + (r_i z_i) pi_i) - [sum r_i y_i] G ,  r_i = r^(offset+i).
 // v1: one thread per blob does its scalar multiplications (Shamir's trick for the pair), results are then
 // tree-summed by pair_sum_kernel.
-// One thread per (blob, 32-bit chunk of the scalars): chunk j of blob i yields [r_i^(j)] pi_i and
-// [r_i^(j)] C_i + [(r_i z_i)^(j)] pi_i, where s^(j) is the j-th 32-bit limb of s.  Chunk sums over the blobs are
-// formed by pair_sum_kernel; the weights 2^(32 j) are applied once per batch (finish_partial_kernel), so the
-// per-blob ladders are 32 steps deep instead of 255.
-constexpr int kChunks = 8;
-struct LincombTerm { G1 a, b; };
-__global__ void __launch_bounds__(128) lincomb_scalars_kernel(const Fr* __restrict__ z_mont, const ZY* __restrict__ zy, const Fr* __restrict__ r_mont,
-                                                              uint64_t offset, int n, Fr* __restrict__ ri_raw, Fr* __restrict__ rz_raw,
-                                                              Fr* __restrict__ ry) {
+// Pippenger bucket method, 8-bit windows (32 windows x 255 buckets), three point/scalar sets per rank:
+//   set 0: pi_i with r_i  (-> A),   set 1: C_i with r_i,   set 2: pi_i with r_i z_i   (sets 1+2 -> B').
+// No sorting network and no atomics on points: a counting sort of the digits per (set, window) gives every
+// bucket a contiguous index list, one thread then owns one bucket and walks its list.
+constexpr int kWindows = 32, kBuckets = 256, kMsmSets = 3;
+struct MsmDigits { uint8_t d[2][kWindows]; };   // per blob: bytes of r_i, bytes of r_i z_i
+__global__ void __launch_bounds__(128) msm_scalars_kernel(const Fr* __restrict__ z_mont, const ZY* __restrict__ zy, const Fr* __restrict__ r_mont,
+                                                          uint64_t offset, int n, uint8_t* __restrict__ digits /* [2][32][n] */,
+                                                          Fr* __restrict__ ry) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t e = offset + (uint64_t)i;
     uint32_t ee[2] = {(uint32_t)e, (uint32_t)(e >> 32)};
     Fr ri = r_mont->pow(ee, 64);              // r^(offset+i), Montgomery   (compute_powers, kzg_proof.rs:279-289)
-    ri_raw[i] = ri.to_raw();
-    rz_raw[i] = (ri * z_mont[i]).to_raw();    // r_i z_i   (kzg_proof.rs:425)
+    Fr ri_raw = ri.to_raw();
+    Fr rz_raw = (ri * z_mont[i]).to_raw();    // r_i z_i   (kzg_proof.rs:425)
     ry[i] = ri * zy[i].y;                     // r_i y_i in normal form
-}
-// terms layout: [chunk][blob]
-__global__ void __launch_bounds__(128) lincomb_terms_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P,
-                                                            const Fr* __restrict__ ri_raw, const Fr* __restrict__ rz_raw, int n,
-                                                            LincombTerm* __restrict__ terms) {
-    int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= n * kChunks) return;
-    int i = tid % n, j = tid / n;
-    uint32_t kr = ri_raw[i].l[j], kz = rz_raw[i].l[j];
-    G1Affine c = C[i], p = P[i];
-    G1 cp = G1::from_affine(c).add_mixed(p);  // C_i + pi_i for the joint ladder
-    G1 a = G1::identity(), b = G1::identity();
-    for (int bit = 31; bit >= 0; bit--) {
-        a = a.dbl(); b = b.dbl();
-        uint32_t br = (kr >> bit) & 1, bz = (kz >> bit) & 1;
-        if (br) a = a.add_mixed(p);
-        if (br && bz) b = b.add(cp); else if (br) b = b.add_mixed(c); else if (bz) b = b.add_mixed(p);
+    for (int w = 0; w < kWindows; w++) {
+        digits[((size_t)0 * kWindows + w) * n + i] = (uint8_t)(ri_raw.l[w >> 2] >> (8 * (w & 3)));
+        digits[((size_t)1 * kWindows + w) * n + i] = (uint8_t)(rz_raw.l[w >> 2] >> (8 * (w & 3)));
     }
-    terms[tid].a = a; terms[tid].b = b;
 }
-// terms[j][i] += terms[j][i + half] for i < half, every chunk j (grid.y = chunk); Fr sums on chunk 0
-__global__ void __launch_bounds__(128) pair_sum_kernel(LincombTerm* __restrict__ terms, Fr* __restrict__ ry, int n, int count, int half) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
-    if (i >= half || i + half >= count) return;
-    LincombTerm* t = terms + (size_t)j * n;
-    t[i].a = t[i].a.add(t[i + half].a);
-    t[i].b = t[i].b.add(t[i + half].b);
-    if (j == 0) ry[i] = ry[i] + ry[i + half];
+// counting sort of one digit row: grid = (32 windows, 2 scalar kinds); order[kind][w][*] = blob indices grouped by
+// digit, start[kind][w][b] = first position of digit b (start[..][256] = n)
+__global__ void __launch_bounds__(256) msm_sort_kernel(const uint8_t* __restrict__ digits, int n, uint32_t* __restrict__ order,
+                                                       uint32_t* __restrict__ start) {
+    __shared__ uint32_t hist[kBuckets], cursor[kBuckets];
+    int w = blockIdx.x, kind = blockIdx.y, t = threadIdx.x;
+    const uint8_t* row = digits + ((size_t)kind * kWindows + w) * n;
+    uint32_t* ord = order + ((size_t)kind * kWindows + w) * n;
+    uint32_t* st = start + ((size_t)kind * kWindows + w) * (kBuckets + 1);
+    hist[t] = 0;
+    __syncthreads();
+    for (int i = t; i < n; i += blockDim.x) atomicAdd(&hist[row[i]], 1u);
+    __syncthreads();
+    if (t == 0) {
+        uint32_t acc = 0;
+        for (int b = 0; b < kBuckets; b++) { cursor[b] = acc; st[b] = acc; acc += hist[b]; }
+        st[kBuckets] = acc;
+    }
+    __syncthreads();
+    for (int i = t; i < n; i += blockDim.x) ord[atomicAdd(&cursor[row[i]], 1u)] = (uint32_t)i;
+}
+// one thread per (set, window, bucket b >= 1): sum of the bucket's points
+__global__ void __launch_bounds__(128) msm_bucket_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P, int n,
+                                                         const uint32_t* __restrict__ order, const uint32_t* __restrict__ start,
+                                                         G1* __restrict__ buckets /* [3][32][256] */) {
+    int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= kMsmSets * kWindows * kBuckets) return;
+    int b = tid % kBuckets, w = (tid / kBuckets) % kWindows, set = tid / (kBuckets * kWindows);
+    int kind = set == 2 ? 1 : 0;
+    const G1Affine* pts = set == 1 ? C : P;
+    const uint32_t* ord = order + ((size_t)kind * kWindows + w) * n;
+    const uint32_t* st = start + ((size_t)kind * kWindows + w) * (kBuckets + 1);
+    G1 acc = G1::identity();
+    if (b != 0) {
+        uint32_t lo = st[b], hi = st[b + 1];
+        for (uint32_t k = lo; k < hi; k++) acc = acc.add_mixed(pts[ord[k]]);
+    }
+    buckets[tid] = acc;
+}
+// one warp per (set, window): W = sum_b b * bucket[b].  Lane l owns buckets 8l .. 8l+7 (running-sum trick inside
+// the segment, then the segment's offset 8l by a short double-and-add), then a shared-memory tree over the lanes.
+__global__ void __launch_bounds__(32) msm_window_kernel(const G1* __restrict__ buckets, G1* __restrict__ windows /* [3][32] */) {
+    __shared__ G1 sm[32];
+    int l = threadIdx.x, sw = blockIdx.x;          // sw = set * 32 + window
+    const G1* bk = buckets + (size_t)sw * kBuckets + 8 * l;
+    G1 run = G1::identity(), acc = G1::identity();
+    for (int j = 7; j >= 0; j--) {
+        run = run.add(bk[j]);                      // bucket 0 holds the identity
+        acc = acc.add(run);                        // after the loop: acc = sum_j (j+1) bk[j], run = sum_j bk[j]
+    }
+    // sum_j (8l + j) bk[j] = acc + (8l - 1) run
+    uint32_t k[1] = {(uint32_t)(8 * l)};
+    G1 off = scalar_mul(run, k, 8);
+    sm[l] = acc.add(off).add(run.neg());
+    __syncthreads();
+    for (int span = 16; span >= 1; span >>= 1) {
+        if (l < span) sm[l] = sm[l].add(sm[l + span]);
+        __syncthreads();
+    }
+    if (l == 0) windows[sw] = sm[0];
 }
 // per-rank partial result exchanged between ranks (the payload of the allgather)
 struct Partial {
@@ -444,27 +481,118 @@ struct Partial {
     uint32_t err;     // OR of the per-blob error flags of this rank
     uint32_t pad[7];
 };
-// chunk sums S_j -> sum_j 2^(32 j) S_j (Horner), thread 0 for A and thread 32 for B; all threads OR the error flags
-__global__ void finish_partial_kernel(const LincombTerm* __restrict__ terms, const Fr* __restrict__ ry, const uint32_t* __restrict__ status, int n,
-                                      Partial* __restrict__ out) {
+// Warp-cooperative Jacobian doubling / addition for the Horner recombination: the 248 doublings are a serial
+// chain, but each doubling has only 3 dependent multiplication levels (each addition 5), so three / four lanes
+// of a warp run the independent products of a level side by side through shared memory.
+// Lanes of a warp run in lockstep, so the lanes do not branch to different products: every lane SELECTS its two
+// operands and all of them execute the one multiplication together.
+struct CoopPoint { Fp v[20]; };   // [0..2] = X,Y,Z ; the rest scratch
+__device__ __forceinline__ Fp sel(int k, const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = k == 0 ? a.l[i] : (k == 1 ? b.l[i] : (k == 2 ? c.l[i] : d.l[i]));
+    return r;
+}
+__device__ __forceinline__ void coop_dbl(CoopPoint* s, int lane) {
+    Fp* v = s->v;
+    if (v[2].is_zero()) return;                                   // identity (uniform: every lane reads the same value)
+    int k = lane & 3;
+    Fp X = v[0], Y = v[1], Z = v[2];
+    // level 1: X*X, Y*Y, Y*Z
+    Fp r1 = sel(k, X, Y, Y, Y).mul_inl(sel(k, X, Y, Z, Z));
+    if (lane < 3) v[3 + lane] = r1;
+    __syncwarp();
+    Fp A = v[3], B = v[4], YZ = v[5];
+    Fp E = A.add_inl(A).add_inl(A), XB = X.add_inl(B);
+    // level 2: B*B, (X+B)^2, E*E
+    Fp o2 = sel(k, B, XB, E, E);
+    Fp r2 = o2.mul_inl(o2);
+    if (lane < 3) v[6 + lane] = r2;
+    __syncwarp();
+    Fp C = v[6], D = v[7].sub_inl(A).sub_inl(C); D = D.add_inl(D);
+    Fp X3 = v[8].sub_inl(D).sub_inl(D);
+    // level 3: E*(D - X3)
+    Fp c8 = C.add_inl(C); c8 = c8.add_inl(c8); c8 = c8.add_inl(c8);
+    Fp y3 = E.mul_inl(D.sub_inl(X3)).sub_inl(c8);
+    __syncwarp();                                                  // everyone has read the old state
+    if (lane == 0) { v[0] = X3; v[1] = y3; v[2] = YZ.add_inl(YZ); }
+    __syncwarp();
+}
+// v[0..2] += q (Jacobian)
+__device__ __forceinline__ void coop_add(CoopPoint* s, const G1& q, int lane) {
+    Fp* v = s->v;
+    if (q.is_identity()) return;
+    if (v[2].is_zero()) { if (lane == 0) { v[0] = q.x; v[1] = q.y; v[2] = q.z; } __syncwarp(); return; }
+    int k = lane & 3;
+    Fp X1 = v[0], Y1 = v[1], Z1 = v[2];
+    // level 1: Z1*Z1, Z2*Z2, Z1*Z2
+    Fp r = sel(k, Z1, q.z, Z1, Z1).mul_inl(sel(k, Z1, q.z, q.z, q.z));
+    if (lane < 3) v[3 + lane] = r;
+    __syncwarp();
+    Fp Z1Z1 = v[3], Z2Z2 = v[4], Z1Z2 = v[5];
+    // level 2: U1 = X1 Z2Z2, U2 = X2 Z1Z1, Y1 Z2Z2, Y2 Z1Z1
+    r = sel(k, X1, q.x, Y1, q.y).mul_inl(sel(k, Z2Z2, Z1Z1, Z2Z2, Z1Z1));
+    if (lane < 4) v[6 + lane] = r;
+    __syncwarp();
+    Fp U1 = v[6], H = v[7].sub_inl(U1);
+    // level 3: S1 = (Y1 Z2Z2) Z2, S2 = (Y2 Z1Z1) Z1, H*H, Z1Z2*H
+    r = sel(k, v[8], v[9], H, Z1Z2).mul_inl(sel(k, q.z, Z1, H, H));
+    if (lane < 4) v[10 + lane] = r;
+    __syncwarp();
+    Fp S1 = v[10], R = v[11].sub_inl(S1), H2 = v[12], Z3 = v[13];
+    if (H.is_zero()) {                                             // same x: doubling or cancellation (uniform)
+        if (R.is_zero()) { coop_dbl(s, lane); return; }
+        if (lane == 0) { v[0] = Fp::one(); v[1] = Fp::one(); v[2] = Fp::zero(); }
+        __syncwarp();
+        return;
+    }
+    // level 4: R*R, H2*H, U1*H2
+    r = sel(k, R, H2, U1, U1).mul_inl(sel(k, R, H, H2, H2));
+    if (lane < 3) v[14 + lane] = r;
+    __syncwarp();
+    Fp H3 = v[15], UH2 = v[16];
+    Fp X3 = v[14].sub_inl(H3).sub_inl(UH2).sub_inl(UH2);
+    // level 5: R*(UH2 - X3), S1*H3
+    r = sel(k, R, S1, S1, S1).mul_inl(sel(k, UH2.sub_inl(X3), H3, H3, H3));
+    if (lane < 2) v[17 + lane] = r;
+    __syncwarp();
+    if (lane == 0) { v[0] = X3; v[1] = v[17].sub_inl(v[18]); v[2] = Z3; }
+    __syncwarp();
+}
+// window sums -> A = sum_w 256^w W[0][w], B' = sum_w 256^w (W[1][w] + W[2][w]) (Horner, 8 doublings per window):
+// warp 0 does A, warp 1 does B' with the cooperative point operations above; the other warps OR the per-blob error
+// flags and tree-sum the r_i y_i.
+__global__ void __launch_bounds__(256) msm_combine_kernel(const G1* __restrict__ windows, const Fr* __restrict__ ry, const uint32_t* __restrict__ status,
+                                                          int n, Partial* __restrict__ out) {
     __shared__ uint32_t s_err;
-    if (threadIdx.x == 0) s_err = 0;
+    __shared__ Fr s_ry[256];
+    __shared__ CoopPoint cp[2];
+    int t = threadIdx.x;
+    if (t == 0) s_err = 0;
     __syncthreads();
     uint32_t e = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) e |= status[i];
+    Fr acc_ry = Fr::zero();
+    for (int i = t; i < n; i += blockDim.x) { e |= status[i]; acc_ry = acc_ry.add_inl(ry[i]); }
     if (e) atomicOr(&s_err, e);
-    if (threadIdx.x == 0 || threadIdx.x == 32) {
-        bool is_b = threadIdx.x == 32;
-        G1 acc = G1::identity();
-        for (int j = kChunks - 1; j >= 0; j--) {
-            if (j != kChunks - 1) for (int k = 0; k < 32; k++) acc = acc.dbl();
-            const LincombTerm& t = terms[(size_t)j * n];
-            acc = acc.add(is_b ? t.b : t.a);
-        }
-        if (is_b) out->b = acc; else out->a = acc;
-    }
+    s_ry[t] = acc_ry;
     __syncthreads();
-    if (threadIdx.x == 0) { out->ry = ry[0]; out->err = s_err; }
+    for (int span = 128; span >= 1; span >>= 1) {
+        if (t < span) s_ry[t] = s_ry[t].add_inl(s_ry[t + span]);
+        __syncthreads();
+    }
+    if (t < 64) {
+        int warp = t >> 5, lane = t & 31;
+        CoopPoint* s = &cp[warp];
+        if (lane == 0) { s->v[0] = Fp::one(); s->v[1] = Fp::one(); s->v[2] = Fp::zero(); }
+        __syncwarp();
+        for (int w = kWindows - 1; w >= 0; w--) {
+            if (w != kWindows - 1) for (int k = 0; k < 8; k++) coop_dbl(s, lane);
+            if (warp == 1) { coop_add(s, windows[1 * kWindows + w], lane); coop_add(s, windows[2 * kWindows + w], lane); }
+            else coop_add(s, windows[w], lane);
+        }
+        if (lane == 0) { G1 r = {s->v[0], s->v[1], s->v[2]}; if (warp == 1) out->b = r; else out->a = r; }
+    }
+    if (t == 0) { out->ry = s_ry[0]; out->err = s_err; }
 }
 
 // ------------------------------------------------------------------------------------------------ K7

@@ -27,8 +27,10 @@ struct kzgb200_ctx {
     ZY* d_zy = nullptr;
     G1Affine *d_C = nullptr, *d_P = nullptr;
     uint32_t* d_status = nullptr;
-    LincombTerm* d_terms = nullptr;
-    Fr *d_ry = nullptr, *d_r = nullptr, *d_ri = nullptr, *d_rz = nullptr;
+    Fr *d_ry = nullptr, *d_r = nullptr;
+    uint8_t* d_digits = nullptr;            // [2][32][cap]
+    uint32_t *d_order = nullptr, *d_start = nullptr;
+    G1 *d_buckets = nullptr, *d_windows = nullptr;
     Partial* d_partial = nullptr;
     uint32_t* d_result = nullptr;
     uint8_t *d_zout = nullptr, *d_yout = nullptr;
@@ -75,8 +77,8 @@ static int ensure_capacity(kzgb200_ctx* ctx, size_t n, bool need_blob_staging) {
         CK(regrow(ctx->d_c, c * 48)); CK(regrow(ctx->d_p, c * 48));
         CK(regrow(ctx->d_z_mont, c)); CK(regrow(ctx->d_zy, c));
         CK(regrow(ctx->d_C, c)); CK(regrow(ctx->d_P, c));
-        CK(regrow(ctx->d_status, c)); CK(regrow(ctx->d_terms, c * kChunks)); CK(regrow(ctx->d_ry, c));
-        CK(regrow(ctx->d_ri, c)); CK(regrow(ctx->d_rz, c));
+        CK(regrow(ctx->d_status, c)); CK(regrow(ctx->d_ry, c));
+        CK(regrow(ctx->d_digits, c * 2 * kWindows)); CK(regrow(ctx->d_order, c * 2 * kWindows));
         CK(regrow(ctx->d_zout, c * 32)); CK(regrow(ctx->d_yout, c * 32));
         ctx->cap = c;
     }
@@ -102,6 +104,9 @@ extern "C" int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_p
         CK(cudaMalloc(&ctx->d_r, sizeof(Fr)));
         CK(cudaMalloc(&ctx->d_partial, sizeof(Partial)));
         CK(cudaMalloc(&ctx->d_result, 16));
+        CK(cudaMalloc(&ctx->d_start, 2 * kWindows * (kBuckets + 1) * sizeof(uint32_t)));
+        CK(cudaMalloc(&ctx->d_buckets, kMsmSets * kWindows * kBuckets * sizeof(G1)));
+        CK(cudaMalloc(&ctx->d_windows, kMsmSets * kWindows * sizeof(G1)));
         CK(cudaMallocHost(&ctx->h_result, 16));
         uint8_t* d_g2 = nullptr;
         CK(cudaMalloc(&d_g2, 192));
@@ -124,7 +129,8 @@ extern "C" void kzgb200_destroy(kzgb200_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->tables, ctx->d_blobs, ctx->d_c, ctx->d_p, ctx->d_z_mont, ctx->d_zy, ctx->d_C, ctx->d_P, ctx->d_status,
-                    ctx->d_terms, ctx->d_ry, ctx->d_r, ctx->d_partial, ctx->d_result, ctx->d_zout, ctx->d_yout, ctx->d_many, ctx->d_wk, ctx->d_ri, ctx->d_rz};
+                    ctx->d_ry, ctx->d_r, ctx->d_partial, ctx->d_result, ctx->d_zout, ctx->d_yout, ctx->d_many, ctx->d_wk,
+                    ctx->d_digits, ctx->d_order, ctx->d_start, ctx->d_buckets, ctx->d_windows};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -172,16 +178,12 @@ static int launch_transcript(kzgb200_ctx* ctx, const uint8_t* d_all_c, const ZY*
 // K6: per-blob terms, tree sum, partial
 static int launch_lincomb(kzgb200_ctx* ctx, size_t offset, Partial* d_out) {
     int n = (int)ctx->cur_n;
-    lincomb_scalars_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_z_mont, ctx->d_zy, ctx->d_r, (uint64_t)offset, n,
-                                                                    ctx->d_ri, ctx->d_rz, ctx->d_ry);
-    lincomb_terms_kernel<<<(n * kChunks + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_C, ctx->d_P, ctx->d_ri, ctx->d_rz, n, ctx->d_terms);
+    msm_scalars_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_z_mont, ctx->d_zy, ctx->d_r, (uint64_t)offset, n, ctx->d_digits, ctx->d_ry);
+    msm_sort_kernel<<<dim3(kWindows, 2), 256, 0, ctx->stream>>>(ctx->d_digits, n, ctx->d_order, ctx->d_start);
+    msm_bucket_kernel<<<(kMsmSets * kWindows * kBuckets + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_C, ctx->d_P, n, ctx->d_order, ctx->d_start, ctx->d_buckets);
     mark(ctx, 5);
-    for (int count = n; count > 1;) {
-        int half = (count + 1) / 2;
-        pair_sum_kernel<<<dim3((half + 127) / 128, kChunks), 128, 0, ctx->stream>>>(ctx->d_terms, ctx->d_ry, n, count, half);
-        count = half;
-    }
-    finish_partial_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_terms, ctx->d_ry, ctx->d_status, n, d_out);
+    msm_window_kernel<<<kMsmSets * kWindows, 32, 0, ctx->stream>>>(ctx->d_buckets, ctx->d_windows);
+    msm_combine_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_windows, ctx->d_ry, ctx->d_status, n, d_out);
     mark(ctx, 6);
     CK(cudaGetLastError());
     return KZGB200_OK;

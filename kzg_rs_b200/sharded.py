@@ -19,9 +19,50 @@ PARTIAL_BYTES = 352
 FR_MODULUS_BE = bytes.fromhex("73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001")
 
 
+class GpuBackend:
+    """The four phases on libkzgb200.so (device pointers)."""
+
+    def __init__(self, lib, ctx):
+        self.lib, self.ctx = lib, ctx
+
+    def _check(self, rc):
+        if rc == 1:
+            return None           # Err(BadArgs)
+        if rc:
+            raise RuntimeError("kzgb200 rc=%d: %s" % (rc, self.lib.kzgb200_last_error(self.ctx).decode()))
+        return True
+
+    def batch(self, blobs, cs, ps, n, z_out, y_out):
+        ok = C.c_int(-1)
+        rc = self.lib.kzgb200_verify_blob_kzg_proof_batch_device(self.ctx, blobs.data_ptr(), cs.data_ptr(), ps.data_ptr(), n, C.byref(ok),
+                                                                 z_out.data_ptr(), y_out.data_ptr())
+        return self._check(rc) and bool(ok.value)
+
+    def evaluate(self, blobs, cs, ps, n, zy_out):
+        self._check(self.lib.kzgb200_shard_evaluate(self.ctx, blobs.data_ptr(), cs.data_ptr(), ps.data_ptr(), n, zy_out.data_ptr()))
+
+    def challenge(self, all_c, all_zy, all_p, n_total):
+        self._check(self.lib.kzgb200_shard_challenge(self.ctx, all_c.data_ptr(), all_zy.data_ptr(), all_p.data_ptr(), n_total))
+
+    def lincomb(self, offset, partial_out):
+        self._check(self.lib.kzgb200_shard_lincomb(self.ctx, offset, partial_out.data_ptr()))
+
+    def finalize(self, partials, world):
+        ok = C.c_int(-1)
+        rc = self.lib.kzgb200_shard_finalize(self.ctx, partials.data_ptr(), world, C.byref(ok))
+        return self._check(rc) and bool(ok.value)
+
+    def sync_collectives(self):
+        torch.cuda.current_stream().synchronize()
+
+
 class ShardedBatch:
-    def __init__(self, lib, ctx, n_local, rank=0, world=1, dist=None, device=None):
+    """Orchestration of one sharded batch; `backend` supplies the four phases (GpuBackend in production; the CPU
+    tests drive the same code with an oracle-backed stand-in under gloo)."""
+
+    def __init__(self, lib, ctx, n_local, rank=0, world=1, dist=None, device=None, backend=None):
         self.lib, self.ctx, self.n, self.rank, self.world, self.dist = lib, ctx, n_local, rank, world, dist
+        self.backend = backend or GpuBackend(lib, ctx)
         dev = device or torch.device("cuda", torch.cuda.current_device())
         u8 = dict(dtype=torch.uint8, device=dev)
         self.z_out = torch.empty(n_local * 32, **u8)
@@ -46,25 +87,20 @@ class ShardedBatch:
 
     def verify_device(self, d_blobs, d_cs, d_ps):
         """Inputs resident in HBM.  Returns True / False / None (= Err(BadArgs))."""
-        ok = C.c_int(-1)
+        be = self.backend
         if self.world == 1:
-            rc = self.lib.kzgb200_verify_blob_kzg_proof_batch_device(self.ctx, d_blobs.data_ptr(), d_cs.data_ptr(), d_ps.data_ptr(),
-                                                                     self.n, C.byref(ok), self.z_out.data_ptr(), self.y_out.data_ptr())
-            return self._check(rc) and bool(ok.value)
+            return be.batch(d_blobs, d_cs, d_ps, self.n, self.z_out, self.y_out)
         dist = self.dist
-        rc = self.lib.kzgb200_shard_evaluate(self.ctx, d_blobs.data_ptr(), d_cs.data_ptr(), d_ps.data_ptr(), self.n, self.zy.data_ptr())
-        self._check(rc)
+        be.evaluate(d_blobs, d_cs, d_ps, self.n, self.zy)
         dist.all_gather_into_tensor(self.all_c, d_cs)
         dist.all_gather_into_tensor(self.all_p, d_ps)
         dist.all_gather_into_tensor(self.all_zy, self.zy)
-        torch.cuda.current_stream().synchronize()
-        self._check(self.lib.kzgb200_shard_challenge(self.ctx, self.all_c.data_ptr(), self.all_zy.data_ptr(), self.all_p.data_ptr(),
-                                                     self.n * self.world))
-        self._check(self.lib.kzgb200_shard_lincomb(self.ctx, self.rank * self.n, self.partial.data_ptr()))
+        be.sync_collectives()
+        be.challenge(self.all_c, self.all_zy, self.all_p, self.n * self.world)
+        be.lincomb(self.rank * self.n, self.partial)
         dist.all_gather_into_tensor(self.partials, self.partial)
-        torch.cuda.current_stream().synchronize()
-        rc = self.lib.kzgb200_shard_finalize(self.ctx, self.partials.data_ptr(), self.world, C.byref(ok))
-        return self._check(rc) and bool(ok.value)
+        be.sync_collectives()
+        return be.finalize(self.partials, self.world)
 
     def verify_host(self, h_blobs, h_cs, h_ps):
         """Inputs in (pinned) host memory; host->device copies are part of the call."""
@@ -79,7 +115,7 @@ class ShardedBatch:
                           torch.empty(self.n * 48, dtype=torch.uint8, device=dev))
         for d, h in zip(self.stage, (h_blobs, h_cs, h_ps)):
             d.copy_(h, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        self.backend.sync_collectives()
         return self.verify_device(*self.stage)
 
     def last_zy_host(self, m):
