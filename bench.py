@@ -217,6 +217,11 @@ def main():
     sampler.start()
     ms, phases = timed(step_resident, args.steps, max(args.warmup, 3))
     ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
+    # opt-in tree transcript (same verdicts, r not bit-identical to kzg-rs): reported beside the default mode
+    lib.kzgb200_set_transcript_mode(ctx, 1)
+    ms_tree, phases_tree = timed(step_resident, args.steps, 3)
+    ms_tree_e2e, _ = timed(step_e2e, args.steps, 3)
+    lib.kzgb200_set_transcript_mode(ctx, 0)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -249,8 +254,12 @@ def main():
                "config": workload_config(args, n, world),
                "e2e": {"value": e2e, "unit": "blobs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": n * ALGO_BYTES_PER_BLOB * world,
                        "d2h_bytes_per_step": 8 * world},
-               "gpu_launches": plan.launches_per_step * args.steps * 2, "clocks": sampler.summary(),
-               "phases_ms": dict(zip(PHASES, phases)) if world == 1 else None, "roofline": roof, "negatives": neg}
+               "gpu_launches": plan.launches_per_step * args.steps * 4, "clocks": sampler.summary(),
+               "phases_ms": dict(zip(PHASES, phases)) if world == 1 else None, "roofline": roof, "negatives": neg,
+               "tree_transcript": {"value": total / (ms_tree / 1e3), "e2e": total / (ms_tree_e2e / 1e3), "unit": "blobs/s",
+                                   "ms_per_step": ms_tree, "e2e_ms_per_step": ms_tree_e2e,
+                                   "phases_ms": dict(zip(PHASES, phases_tree)) if world == 1 else None,
+                                   "note": "KZGB200_TRANSCRIPT_TREE: r hashed as a 2-level tree; verdict/z/y identical, r differs from kzg-rs"}}
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         from oracle import oracle as O
         O.build()

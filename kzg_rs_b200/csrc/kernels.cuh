@@ -234,11 +234,12 @@ __device__ __forceinline__ uint8_t transcript_byte(size_t pos, uint64_t n, const
 // pieces, expands the SHA-256 message schedule and stores W[t] + K[t], t < 64 -- everything about a block that
 // does not depend on the chaining value.
 __global__ void __launch_bounds__(128) transcript_schedule_kernel(const uint8_t* __restrict__ commitments, const ZY* __restrict__ zy,
-                                                                  const uint8_t* __restrict__ proofs, uint64_t n, uint32_t* __restrict__ wk) {
+                                                                  const uint8_t* __restrict__ proofs, uint64_t n, uint32_t* __restrict__ wk,
+                                                                  uint64_t first_blk, uint64_t blk_count) {
     size_t len = 32 + (size_t)n * 160;
     size_t nblk = (len + 9 + 63) / 64;
-    size_t blk = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (blk >= nblk) return;
+    size_t blk = first_blk + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (blk >= nblk || blk >= first_blk + blk_count) return;
     uint32_t w[16];
     for (int j = 0; j < 16; j++) {
         uint32_t v = 0;
@@ -272,14 +273,20 @@ __global__ void __launch_bounds__(128) transcript_schedule_kernel(const uint8_t*
 // the next blocks into shared memory with coalesced loads, every lane then runs the same rounds on
 // broadcast reads (SIMT makes the redundant lanes free); lane 0 publishes r.
 constexpr int kTranscriptStage = 8;   // blocks per shared-memory stage
-__global__ void __launch_bounds__(32) transcript_chain_kernel(const uint32_t* __restrict__ wk, uint64_t n, Fr* __restrict__ r_mont) {
+// Processes blocks [first_blk, first_blk + blk_count) and carries the chaining value in `state` (8 words), so the
+// chain can advance while later blobs are still being copied / hashed; the call that reaches the last block
+// publishes r.
+__global__ void __launch_bounds__(32) transcript_chain_kernel(const uint32_t* __restrict__ wk_all, uint64_t n, Fr* __restrict__ r_mont,
+                                                              uint32_t* __restrict__ state, uint64_t first_blk, uint64_t blk_count) {
     __shared__ uint4 stage[2][kTranscriptStage * 16];
     size_t len = 32 + (size_t)n * 160;
-    size_t nblk = (len + 9 + 63) / 64;
+    size_t total_blk = (len + 9 + 63) / 64;
+    size_t nblk = blk_count;
     int lane = threadIdx.x;
-    const uint4* src = reinterpret_cast<const uint4*>(wk);
+    const uint4* src = reinterpret_cast<const uint4*>(wk_all + first_blk * 64);
     uint32_t st[8];
-    sha256_init(st);
+    if (first_blk == 0) sha256_init(st);
+    else for (int j = 0; j < 8; j++) st[j] = state[j];
     size_t nstage = (nblk + kTranscriptStage - 1) / kTranscriptStage;
     auto load_stage = [&](size_t sidx, int buf) {
         size_t base = sidx * kTranscriptStage * 16, total = nblk * 16;
@@ -323,9 +330,12 @@ __global__ void __launch_bounds__(32) transcript_chain_kernel(const uint32_t* __
         __syncwarp();
     }
     if (lane == 0) {
-        Fr raw;
-        for (int j = 0; j < 8; j++) raw.l[j] = st[7 - j];
-        *r_mont = Fr::from_raw(raw);
+        for (int j = 0; j < 8; j++) state[j] = st[j];
+        if (first_blk + blk_count >= total_blk) {
+            Fr raw;
+            for (int j = 0; j < 8; j++) raw.l[j] = st[7 - j];
+            *r_mont = Fr::from_raw(raw);
+        }
     }
 }
 
@@ -336,10 +346,11 @@ __global__ void __launch_bounds__(32) transcript_chain_kernel(const uint32_t* __
 // same data), so this mode is NOT the default; see DESIGN.md "transcript modes".
 constexpr int kTreeGroup = 64;
 __global__ void __launch_bounds__(64) transcript_tree_leaf_kernel(const uint8_t* __restrict__ commitments, const ZY* __restrict__ zy,
-                                                                  const uint8_t* __restrict__ proofs, uint64_t n, uint32_t* __restrict__ digests) {
-    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                                                  const uint8_t* __restrict__ proofs, uint64_t n, uint32_t* __restrict__ digests,
+                                                                  uint64_t first_group, uint64_t group_count) {
+    uint64_t g = first_group + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t ngroups = (n + kTreeGroup - 1) / kTreeGroup;
-    if (g >= ngroups) return;
+    if (g >= ngroups || g >= first_group + group_count) return;
     uint64_t first = g * kTreeGroup, cnt = n - first < (uint64_t)kTreeGroup ? n - first : (uint64_t)kTreeGroup;
     size_t len = (size_t)cnt * 160, nblk = (len + 9 + 63) / 64;
     uint32_t st[8], w[16];

@@ -43,17 +43,21 @@ struct kzgb200_ctx {
     size_t cur_n = 0;
     // optional per-phase timing (CUDA events on the context stream)
     int transcript_mode = KZGB200_TRANSCRIPT_EXACT;
+    cudaStream_t s_aux = nullptr, s_copy = nullptr, s_work[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_begin = nullptr, ev_parse = nullptr, ev_h2d[64] = {nullptr}, ev_zy[64] = {nullptr};
+    uint32_t* d_chain_state = nullptr;
+    size_t tr_done = 0;             // transcript blocks (exact) / leaf groups (tree) already hashed
+    // optional per-phase timing (CUDA event pairs on the stream each phase runs on)
     bool profile = false;
-    cudaEvent_t ev[9] = {nullptr};
-    int ev_used = 0;
+    cudaEvent_t ev_s[8] = {nullptr}, ev_e[8] = {nullptr};
+    bool ph_started[8] = {false};
     float phase_ms[8] = {0};
     std::mutex lock;
     char err[256] = {0};
 };
 enum Phase { kPhParse = 0, kPhChallenge, kPhEval, kPhTranscript, kPhLincomb, kPhReduce, kPhFinal, kPhCount };
-static void mark(kzgb200_ctx* ctx, int idx) {
-    if (ctx->profile && ctx->ev[idx]) { cudaEventRecord(ctx->ev[idx], ctx->stream); if (idx + 1 > ctx->ev_used) ctx->ev_used = idx + 1; }
-}
+constexpr int kMaxChunks = 64, kWorkStreams = 4;
+constexpr size_t kMinChunk = 1024;   // blobs per host->device chunk (128 MiB)
 
 #define CK(expr)                                                                                   \
     do {                                                                                           \
@@ -100,6 +104,17 @@ extern "C" int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_p
     int rc = [&]() -> int {
         CK(cudaSetDevice(device));
         CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        int prio_lo = 0, prio_hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        // the hash chains are the long pole of phase 1: their CTAs go first, G1 parsing fills the rest of the machine
+        CK(cudaStreamCreateWithPriority(&ctx->s_aux, cudaStreamNonBlocking, prio_lo));
+        CK(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
+        for (auto& w : ctx->s_work) CK(cudaStreamCreateWithPriority(&w, cudaStreamNonBlocking, prio_hi));
+        CK(cudaEventCreateWithFlags(&ctx->ev_begin, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_parse, cudaEventDisableTiming));
+        for (auto& e : ctx->ev_h2d) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : ctx->ev_zy) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CK(cudaMalloc(&ctx->d_chain_state, 32));
         CK(cudaMalloc(&ctx->tables, sizeof(DeviceTables)));
         CK(cudaMalloc(&ctx->d_r, sizeof(Fr)));
         CK(cudaMalloc(&ctx->d_partial, sizeof(Partial)));
@@ -127,7 +142,14 @@ extern "C" int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_p
 extern "C" void kzgb200_destroy(kzgb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaDeviceSynchronize();
+    for (cudaStream_t st : {ctx->s_aux, ctx->s_copy, ctx->s_work[0], ctx->s_work[1], ctx->s_work[2], ctx->s_work[3]}) if (st) cudaStreamDestroy(st);
+    for (cudaEvent_t e : {ctx->ev_begin, ctx->ev_parse}) if (e) cudaEventDestroy(e);
+    for (auto e : ctx->ev_h2d) if (e) cudaEventDestroy(e);
+    for (auto e : ctx->ev_zy) if (e) cudaEventDestroy(e);
+    for (auto e : ctx->ev_s) if (e) cudaEventDestroy(e);
+    for (auto e : ctx->ev_e) if (e) cudaEventDestroy(e);
+    if (ctx->d_chain_state) cudaFree(ctx->d_chain_state);
     void* ptrs[] = {ctx->tables, ctx->d_blobs, ctx->d_c, ctx->d_p, ctx->d_z_mont, ctx->d_zy, ctx->d_C, ctx->d_P, ctx->d_status,
                     ctx->d_ry, ctx->d_r, ctx->d_partial, ctx->d_result, ctx->d_zout, ctx->d_yout, ctx->d_many, ctx->d_wk,
                     ctx->d_digits, ctx->d_order, ctx->d_start, ctx->d_buckets, ctx->d_windows};
@@ -139,52 +161,114 @@ extern "C" void kzgb200_destroy(kzgb200_ctx* ctx) {
 
 extern "C" const char* kzgb200_last_error(const kzgb200_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 
-// ---- phases (all asynchronous on ctx->stream) ---------------------------------------------------------------
-// phase 1: K4 (parse C, pi) + K2 (challenge) + K1/K3 (canonicity + evaluation)
-static int launch_phase1(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t* d_c, const uint8_t* d_p, size_t n) {
-    int ni = (int)n;
+// ---- phases ---------------------------------------------------------------------------------------------------
+// Streams: `stream` (main: transcript, MSM, pairing, result), `s_aux` (G1 parsing, runs beside the hashing),
+// `s_work[k]` (per-chunk challenge -> evaluation), `s_copy` (host->device blob chunks).  A device-resident batch is one
+// chunk (the per-blob SHA-256 chain is latency-bound: splitting it buys nothing); a host batch is cut into chunks so
+// that hashing / evaluation / the serial transcript chain of chunk c overlap the PCIe copy of chunk c+1.
+static void phase_begin(kzgb200_ctx* ctx, int ph, cudaStream_t st) { if (ctx->profile && !ctx->ph_started[ph]) { cudaEventRecord(ctx->ev_s[ph], st); ctx->ph_started[ph] = true; } }
+static void phase_end(kzgb200_ctx* ctx, int ph, cudaStream_t st) { if (ctx->profile) cudaEventRecord(ctx->ev_e[ph], st); }
+
+// transcript blocks / tree groups that only depend on entries < avail
+static int advance_transcript(kzgb200_ctx* ctx, const uint8_t* d_c, const ZY* d_zy, const uint8_t* d_p, size_t n, size_t avail) {
+    if (ctx->transcript_mode == KZGB200_TRANSCRIPT_TREE) {
+        size_t ngroups = (n + kTreeGroup - 1) / kTreeGroup;
+        size_t ready = avail >= n ? ngroups : avail / kTreeGroup;
+        if (ready > ctx->tr_done) {
+            phase_begin(ctx, kPhTranscript, ctx->stream);
+            size_t cnt = ready - ctx->tr_done;
+            transcript_tree_leaf_kernel<<<(unsigned)((cnt + 63) / 64), 64, 0, ctx->stream>>>(d_c, d_zy, d_p, (uint64_t)n, ctx->d_wk, ctx->tr_done, cnt);
+            ctx->tr_done = ready;
+        }
+        if (avail >= n) {
+            transcript_tree_root_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_wk, (uint64_t)n, ctx->d_r);
+            phase_end(ctx, kPhTranscript, ctx->stream);
+        }
+    } else {
+        size_t nblk = (32 + n * 160 + 9 + 63) / 64;
+        size_t ready = avail >= n ? nblk : (32 + avail * 160) / 64;
+        if (ready > ctx->tr_done) {
+            phase_begin(ctx, kPhTranscript, ctx->stream);
+            size_t cnt = ready - ctx->tr_done;
+            transcript_schedule_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, ctx->stream>>>(d_c, d_zy, d_p, (uint64_t)n, ctx->d_wk, ctx->tr_done, cnt);
+            transcript_chain_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_wk, (uint64_t)n, ctx->d_r, ctx->d_chain_state, ctx->tr_done, cnt);
+            ctx->tr_done = ready;
+        }
+        if (avail >= n) phase_end(ctx, kPhTranscript, ctx->stream);
+    }
+    CK(cudaGetLastError());
+    return KZGB200_OK;
+}
+static int reserve_transcript(kzgb200_ctx* ctx, size_t n) {
+    size_t words = ctx->transcript_mode == KZGB200_TRANSCRIPT_TREE ? ((n + kTreeGroup - 1) / kTreeGroup) * 8 + 64
+                                                                   : ((32 + n * 160 + 9 + 63) / 64) * 64;
+    if (words > ctx->wk_cap) { CK(regrow(ctx->d_wk, words)); ctx->wk_cap = words; }
+    ctx->tr_done = 0;
+    return KZGB200_OK;
+}
+// phase 1 for blobs [0, n): K4 on s_aux; per chunk K2 -> K1/K3 on a work stream; optionally the transcript advances
+// on the main stream as chunks complete.  h_blobs != nullptr: the blobs are copied chunk by chunk from the host.
+static int launch_phase1(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t* h_blobs, const uint8_t* d_c, const uint8_t* d_p, size_t n,
+                         bool with_transcript) {
+    for (int i = 0; i < kPhCount; i++) ctx->ph_started[i] = false;
+    size_t chunk = n;
+    if (h_blobs) { chunk = (n + kMaxChunks - 1) / kMaxChunks; if (chunk < kMinChunk) chunk = kMinChunk; }
+    size_t nchunks = (n + chunk - 1) / chunk;
     CK(cudaMemsetAsync(ctx->d_status, 0, n * sizeof(uint32_t), ctx->stream));
-    ctx->ev_used = 0;
-    mark(ctx, 0);
-    g1_parse_kernel<<<(2 * ni + 127) / 128, 128, 0, ctx->stream>>>(d_c, d_p, ni, ctx->d_C, ctx->d_P, ctx->d_status);
-    mark(ctx, 1);
-    challenge_kernel<<<(ni + 63) / 64, 64, 0, ctx->stream>>>(d_blobs, d_c, ni, ctx->d_z_mont, ctx->d_zy);
-    mark(ctx, 2);
-    eval_kernel<<<ni, kEvalThreads, 0, ctx->stream>>>(d_blobs, ni, ctx->d_z_mont, ctx->tables, ctx->d_zy, ctx->d_status);
-    mark(ctx, 3);
+    CK(cudaEventRecord(ctx->ev_begin, ctx->stream));
+    if (with_transcript) { int rc = reserve_transcript(ctx, n); if (rc) return rc; }
+    if (h_blobs) CK(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_begin, 0));
+    for (size_t c = 0; c < nchunks; c++) {
+        size_t lo = c * chunk, cnt = n - lo < chunk ? n - lo : chunk;
+        cudaStream_t sw = ctx->s_work[c % kWorkStreams];
+        if (h_blobs) {
+            CK(cudaMemcpyAsync(const_cast<uint8_t*>(d_blobs) + lo * kBytesPerBlob, h_blobs + lo * kBytesPerBlob, cnt * (size_t)kBytesPerBlob,
+                               cudaMemcpyHostToDevice, ctx->s_copy));
+            CK(cudaEventRecord(ctx->ev_h2d[c], ctx->s_copy));
+            CK(cudaStreamWaitEvent(sw, ctx->ev_h2d[c], 0));
+        }
+        CK(cudaStreamWaitEvent(sw, ctx->ev_begin, 0));
+        phase_begin(ctx, kPhChallenge, sw);
+        challenge_kernel<<<((int)cnt + 63) / 64, 64, 0, sw>>>(d_blobs + lo * kBytesPerBlob, d_c + lo * 48, (int)cnt, ctx->d_z_mont + lo, ctx->d_zy + lo);
+        phase_end(ctx, kPhChallenge, sw);
+        phase_begin(ctx, kPhEval, sw);
+        eval_kernel<<<(int)cnt, kEvalThreads, 0, sw>>>(d_blobs + lo * kBytesPerBlob, (int)cnt, ctx->d_z_mont + lo, ctx->tables, ctx->d_zy + lo,
+                                                       ctx->d_status + lo);
+        phase_end(ctx, kPhEval, sw);
+        CK(cudaEventRecord(ctx->ev_zy[c], sw));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_zy[c], 0));
+        if (c == 0) {   // G1 parsing is queued behind the first hash launch (and on a low-priority stream)
+            CK(cudaStreamWaitEvent(ctx->s_aux, ctx->ev_begin, 0));
+            phase_begin(ctx, kPhParse, ctx->s_aux);
+            g1_parse_kernel<<<(2 * (int)n + 127) / 128, 128, 0, ctx->s_aux>>>(d_c, d_p, (int)n, ctx->d_C, ctx->d_P, ctx->d_status);
+            phase_end(ctx, kPhParse, ctx->s_aux);
+            CK(cudaEventRecord(ctx->ev_parse, ctx->s_aux));
+        }
+        if (with_transcript && n >= 2) { int rc = advance_transcript(ctx, d_c, ctx->d_zy, d_p, n, lo + cnt); if (rc) return rc; }
+    }
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_parse, 0));
     CK(cudaGetLastError());
     ctx->cur_c = d_c; ctx->cur_p = d_p; ctx->cur_n = n;
     return KZGB200_OK;
 }
-// K5
+// K5 over gathered arrays (sharded path: every rank derives the same r)
 static int launch_transcript(kzgb200_ctx* ctx, const uint8_t* d_all_c, const ZY* d_all_zy, const uint8_t* d_all_p, size_t n_total) {
-    if (ctx->transcript_mode == KZGB200_TRANSCRIPT_TREE) {
-        size_t ngroups = (n_total + kTreeGroup - 1) / kTreeGroup;
-        if (ngroups * 8 > ctx->wk_cap * 64) { CK(regrow(ctx->d_wk, ngroups * 8 + 64)); ctx->wk_cap = (ngroups * 8 + 64) / 64; }
-        transcript_tree_leaf_kernel<<<(unsigned)((ngroups + 63) / 64), 64, 0, ctx->stream>>>(d_all_c, d_all_zy, d_all_p, (uint64_t)n_total, ctx->d_wk);
-        transcript_tree_root_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_wk, (uint64_t)n_total, ctx->d_r);
-        mark(ctx, 4);
-        CK(cudaGetLastError());
-        return KZGB200_OK;
-    }
-    size_t nblk = (32 + n_total * 160 + 9 + 63) / 64;
-    if (nblk > ctx->wk_cap) { CK(regrow(ctx->d_wk, nblk * 64)); ctx->wk_cap = nblk; }
-    transcript_schedule_kernel<<<(unsigned)((nblk + 127) / 128), 128, 0, ctx->stream>>>(d_all_c, d_all_zy, d_all_p, (uint64_t)n_total, ctx->d_wk);
-    transcript_chain_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_wk, (uint64_t)n_total, ctx->d_r);
-    mark(ctx, 4);
-    CK(cudaGetLastError());
-    return KZGB200_OK;
+    int rc = reserve_transcript(ctx, n_total);
+    if (rc) return rc;
+    return advance_transcript(ctx, d_all_c, d_all_zy, d_all_p, n_total, n_total);
 }
-// K6: per-blob terms, tree sum, partial
+// K6: digits, counting sort, buckets, window sums, Horner -> partial
 static int launch_lincomb(kzgb200_ctx* ctx, size_t offset, Partial* d_out) {
     int n = (int)ctx->cur_n;
+    phase_begin(ctx, kPhLincomb, ctx->stream);
     msm_scalars_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_z_mont, ctx->d_zy, ctx->d_r, (uint64_t)offset, n, ctx->d_digits, ctx->d_ry);
     msm_sort_kernel<<<dim3(kWindows, 2), 256, 0, ctx->stream>>>(ctx->d_digits, n, ctx->d_order, ctx->d_start);
     msm_bucket_kernel<<<(kMsmSets * kWindows * kBuckets + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_C, ctx->d_P, n, ctx->d_order, ctx->d_start, ctx->d_buckets);
-    mark(ctx, 5);
+    phase_end(ctx, kPhLincomb, ctx->stream);
+    phase_begin(ctx, kPhReduce, ctx->stream);
     msm_window_kernel<<<kMsmSets * kWindows, 32, 0, ctx->stream>>>(ctx->d_buckets, ctx->d_windows);
     msm_combine_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_windows, ctx->d_ry, ctx->d_status, n, d_out);
-    mark(ctx, 6);
+    phase_end(ctx, kPhReduce, ctx->stream);
     CK(cudaGetLastError());
     return KZGB200_OK;
 }
@@ -201,25 +285,28 @@ static int export_zy(kzgb200_ctx* ctx, size_t n, uint8_t* d_z, uint8_t* d_y) {
     CK(cudaGetLastError());
     return KZGB200_OK;
 }
-// whole batch on one GPU, device-resident inputs, n >= 1
-static int batch_device_locked(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t* d_c, const uint8_t* d_p, size_t n, int* ok,
-                               uint8_t* d_z_out, uint8_t* d_y_out) {
-    int rc = launch_phase1(ctx, d_blobs, d_c, d_p, n);
+// whole batch on one GPU, n >= 1; blobs either resident (h_blobs == nullptr) or streamed from the host
+static int batch_locked(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t* h_blobs, const uint8_t* d_c, const uint8_t* d_p, size_t n, int* ok,
+                        uint8_t* d_z_out, uint8_t* d_y_out) {
+    int rc = launch_phase1(ctx, d_blobs, h_blobs, d_c, d_p, n, true);
     if (rc) return rc;
     if ((rc = export_zy(ctx, n, d_z_out, d_y_out))) return rc;
+    phase_begin(ctx, kPhFinal, ctx->stream);
     if (n == 1) {   // single path (reference src/kzg_proof.rs:482-489)
         single_final_kernel<<<1, kFinalThreads, 0, ctx->stream>>>(ctx->d_C, ctx->d_P, ctx->d_zy, ctx->d_status, ctx->tables, ctx->d_result);
-        CK(cudaGetLastError());
-        return read_result(ctx, ok);
+    } else {
+        ctx->ph_started[kPhFinal] = false;
+        if ((rc = launch_lincomb(ctx, 0, ctx->d_partial))) return rc;
+        phase_begin(ctx, kPhFinal, ctx->stream);
+        batch_final_kernel<<<1, kFinalThreads, 0, ctx->stream>>>(ctx->d_partial, 1, ctx->tables, ctx->d_result);
     }
-    if ((rc = launch_transcript(ctx, d_c, ctx->d_zy, d_p, n))) return rc;
-    if ((rc = launch_lincomb(ctx, 0, ctx->d_partial))) return rc;
-    batch_final_kernel<<<1, kFinalThreads, 0, ctx->stream>>>(ctx->d_partial, 1, ctx->tables, ctx->d_result);
-    mark(ctx, 7);
+    phase_end(ctx, kPhFinal, ctx->stream);
     CK(cudaGetLastError());
     rc = read_result(ctx, ok);
-    if (ctx->profile && ctx->ev_used == 8)
-        for (int i = 0; i < 7; i++) cudaEventElapsedTime(&ctx->phase_ms[i], ctx->ev[i], ctx->ev[i + 1]);
+    if (ctx->profile) {
+        cudaDeviceSynchronize();
+        for (int i = 0; i < kPhCount; i++) { ctx->phase_ms[i] = 0; if (ctx->ph_started[i]) cudaEventElapsedTime(&ctx->phase_ms[i], ctx->ev_s[i], ctx->ev_e[i]); }
+    }
     return rc;
 }
 
@@ -230,7 +317,7 @@ extern "C" int kzgb200_verify_blob_kzg_proof_batch_device(kzgb200_ctx* ctx, cons
     CK(cudaSetDevice(ctx->device));
     int rc = ensure_capacity(ctx, n, false);
     if (rc) return rc;
-    return batch_device_locked(ctx, d_blobs, d_commitments, d_proofs, n, ok, d_z_out, d_y_out);
+    return batch_locked(ctx, d_blobs, nullptr, d_commitments, d_proofs, n, ok, d_z_out, d_y_out);
 }
 
 extern "C" int kzgb200_verify_blob_kzg_proof_batch(kzgb200_ctx* ctx, const uint8_t* blobs, size_t n_blobs, const uint8_t* commitments,
@@ -252,8 +339,7 @@ extern "C" int kzgb200_verify_blob_kzg_proof_batch(kzgb200_ctx* ctx, const uint8
     if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->d_c, commitments, n * 48, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_p, proofs, n * 48, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_blobs, blobs, n * (size_t)kBytesPerBlob, cudaMemcpyHostToDevice, ctx->stream));
-    rc = batch_device_locked(ctx, ctx->d_blobs, ctx->d_c, ctx->d_p, n, ok, z_out ? ctx->d_zout : nullptr, y_out ? ctx->d_yout : nullptr);
+    rc = batch_locked(ctx, ctx->d_blobs, blobs, ctx->d_c, ctx->d_p, n, ok, z_out ? ctx->d_zout : nullptr, y_out ? ctx->d_yout : nullptr);
     if (rc == KZGB200_OK) {
         if (z_out) CK(cudaMemcpyAsync(z_out, ctx->d_zout, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
         if (y_out) CK(cudaMemcpyAsync(y_out, ctx->d_yout, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
@@ -305,7 +391,7 @@ extern "C" int kzgb200_shard_evaluate(kzgb200_ctx* ctx, const uint8_t* d_blobs, 
     CK(cudaSetDevice(ctx->device));
     int rc = ensure_capacity(ctx, n_local, false);
     if (rc) return rc;
-    if ((rc = launch_phase1(ctx, d_blobs, d_commitments, d_proofs, n_local))) return rc;
+    if ((rc = launch_phase1(ctx, d_blobs, nullptr, d_commitments, d_proofs, n_local, false))) return rc;
     if (d_zy_out) CK(cudaMemcpyAsync(d_zy_out, ctx->d_zy, n_local * sizeof(ZY), cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return KZGB200_OK;
@@ -398,7 +484,7 @@ extern "C" int kzgb200_set_profiling(kzgb200_ctx* ctx, int on) {
     if (!ctx) return KZGB200_BAD_ARGS;
     std::lock_guard<std::mutex> g(ctx->lock);
     CK(cudaSetDevice(ctx->device));
-    if (on) for (auto& e : ctx->ev) if (!e) CK(cudaEventCreate(&e));
+    if (on) { for (auto& e : ctx->ev_s) if (!e) CK(cudaEventCreate(&e)); for (auto& e : ctx->ev_e) if (!e) CK(cudaEventCreate(&e)); }
     ctx->profile = on != 0;
     return KZGB200_OK;
 }

@@ -557,4 +557,5 @@ if __name__ == "__main__":
         check_hazards(prog, N_IN)
         progs[B.name] = prog
     selftest(progs)
-    emit(progs, os.path.join(ROOT, "kzg_rs_b200", "csrc", "vliw_programs.cuh"))
+    if "--check" not in sys.argv:
+        emit(progs, os.path.join(ROOT, "kzg_rs_b200", "csrc", "vliw_programs.cuh"))

@@ -1,5 +1,6 @@
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include "field.cuh"
 using namespace kzgb200;
 // usage: reads lines "F a b c d" hex from stdin; prints mont_mul(a,b), dual(a,b,c,d), a+b, a-b
