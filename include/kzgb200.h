@@ -85,6 +85,11 @@ int kzgb200_verify_kzg_proof_many(kzgb200_ctx* ctx, const uint8_t* commitments, 
  *          hashes, reference src/kzg_proof.rs:320-328). */
 int kzgb200_shard_evaluate(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t* d_commitments,
                            const uint8_t* d_proofs, size_t n_local, uint8_t* d_zy_out);
+/* phase 1 with the shard's inputs in HOST memory (pageable or pinned): the blobs are copied in chunks while earlier
+ * chunks are hashed / evaluated.  The device copies of the commitments / proofs (n_local x 48 each) and zy are written
+ * to the given device buffers for the exchange. */
+int kzgb200_shard_evaluate_host(kzgb200_ctx* ctx, const uint8_t* blobs, const uint8_t* commitments, const uint8_t* proofs,
+                                size_t n_local, uint8_t* d_commitments_out, uint8_t* d_proofs_out, uint8_t* d_zy_out);
 /* r = SHA-256 transcript over ALL n_total blobs in global order (reference src/kzg_proof.rs:291-348), from the
  * gathered commitments (n_total x 48), zy (n_total x 64, as produced by phase 1) and proofs (n_total x 48). */
 int kzgb200_shard_challenge(kzgb200_ctx* ctx, const uint8_t* d_all_commitments, const uint8_t* d_all_zy,

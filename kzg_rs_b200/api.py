@@ -69,6 +69,7 @@ class Library:
         d.kzgb200_verify_blob_kzg_proof_batch_device.argtypes = [p, p, p, p, sz, ip, p, p]
         d.kzgb200_verify_kzg_proof_many.argtypes = [p, p, p, p, p, sz, p]
         d.kzgb200_shard_evaluate.argtypes = [p, p, p, p, sz, p]
+        d.kzgb200_shard_evaluate_host.argtypes = [p, p, p, p, sz, p, p, p]
         d.kzgb200_shard_challenge.argtypes = [p, p, p, p, sz]
         d.kzgb200_shard_lincomb.argtypes = [p, sz, p]
         d.kzgb200_shard_finalize.argtypes = [p, p, sz, ip]

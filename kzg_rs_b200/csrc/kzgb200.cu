@@ -396,6 +396,23 @@ extern "C" int kzgb200_shard_evaluate(kzgb200_ctx* ctx, const uint8_t* d_blobs, 
     CK(cudaStreamSynchronize(ctx->stream));
     return KZGB200_OK;
 }
+// same with the shard's inputs in host memory: chunked host->device copies overlapped with hashing / evaluation
+extern "C" int kzgb200_shard_evaluate_host(kzgb200_ctx* ctx, const uint8_t* blobs, const uint8_t* commitments, const uint8_t* proofs,
+                                           size_t n_local, uint8_t* d_commitments_out, uint8_t* d_proofs_out, uint8_t* d_zy_out) {
+    if (!ctx || n_local == 0 || n_local > 0x7fffffff / 2) return KZGB200_BAD_ARGS;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_capacity(ctx, n_local, true);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->d_c, commitments, n_local * 48, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_p, proofs, n_local * 48, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = launch_phase1(ctx, ctx->d_blobs, blobs, ctx->d_c, ctx->d_p, n_local, false))) return rc;
+    if (d_commitments_out) CK(cudaMemcpyAsync(d_commitments_out, ctx->d_c, n_local * 48, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (d_proofs_out) CK(cudaMemcpyAsync(d_proofs_out, ctx->d_p, n_local * 48, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (d_zy_out) CK(cudaMemcpyAsync(d_zy_out, ctx->d_zy, n_local * sizeof(ZY), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return KZGB200_OK;
+}
 extern "C" int kzgb200_shard_challenge(kzgb200_ctx* ctx, const uint8_t* d_all_commitments, const uint8_t* d_all_zy,
                                        const uint8_t* d_all_proofs, size_t n_total) {
     if (!ctx || n_total == 0) return KZGB200_BAD_ARGS;

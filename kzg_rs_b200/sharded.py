@@ -41,6 +41,10 @@ class GpuBackend:
     def evaluate(self, blobs, cs, ps, n, zy_out):
         self._check(self.lib.kzgb200_shard_evaluate(self.ctx, blobs.data_ptr(), cs.data_ptr(), ps.data_ptr(), n, zy_out.data_ptr()))
 
+    def evaluate_host(self, h_blobs, h_cs, h_ps, n, c_out, p_out, zy_out):
+        self._check(self.lib.kzgb200_shard_evaluate_host(self.ctx, h_blobs.data_ptr(), h_cs.data_ptr(), h_ps.data_ptr(), n,
+                                                         c_out.data_ptr(), p_out.data_ptr(), zy_out.data_ptr()))
+
     def challenge(self, all_c, all_zy, all_p, n_total):
         self._check(self.lib.kzgb200_shard_challenge(self.ctx, all_c.data_ptr(), all_zy.data_ptr(), all_p.data_ptr(), n_total))
 
@@ -90,8 +94,11 @@ class ShardedBatch:
         be = self.backend
         if self.world == 1:
             return be.batch(d_blobs, d_cs, d_ps, self.n, self.z_out, self.y_out)
-        dist = self.dist
         be.evaluate(d_blobs, d_cs, d_ps, self.n, self.zy)
+        return self._exchange_and_finish(d_cs, d_ps)
+
+    def _exchange_and_finish(self, d_cs, d_ps):
+        be, dist = self.backend, self.dist
         dist.all_gather_into_tensor(self.all_c, d_cs)
         dist.all_gather_into_tensor(self.all_p, d_ps)
         dist.all_gather_into_tensor(self.all_zy, self.zy)
@@ -111,12 +118,9 @@ class ShardedBatch:
             return self._check(rc) and bool(ok.value)
         if self.stage is None:
             dev = self.z_out.device
-            self.stage = (torch.empty(self.n * BLOB, dtype=torch.uint8, device=dev), torch.empty(self.n * 48, dtype=torch.uint8, device=dev),
-                          torch.empty(self.n * 48, dtype=torch.uint8, device=dev))
-        for d, h in zip(self.stage, (h_blobs, h_cs, h_ps)):
-            d.copy_(h, non_blocking=True)
-        self.backend.sync_collectives()
-        return self.verify_device(*self.stage)
+            self.stage = (torch.empty(self.n * 48, dtype=torch.uint8, device=dev), torch.empty(self.n * 48, dtype=torch.uint8, device=dev))
+        self.backend.evaluate_host(h_blobs, h_cs, h_ps, self.n, self.stage[0], self.stage[1], self.zy)
+        return self._exchange_and_finish(*self.stage)
 
     def last_zy_host(self, m):
         """(z bytes, y bytes), 32-byte big-endian each, of the first m blobs of the last single-GPU call."""
