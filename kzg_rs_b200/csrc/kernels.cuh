@@ -80,9 +80,11 @@ __global__ void __launch_bounds__(64) challenge_kernel(const uint8_t* __restrict
     }
     sha256_compress(st, w);
     // blocks 1..2047: blob[64k-32 .. 64k+32)
+    // software pipeline: the next block's 64 bytes are in flight while this block is compressed
+    uint4 na = __ldg(bp + 2), nb = __ldg(bp + 3), nc = __ldg(bp + 4), nd = __ldg(bp + 5);
     for (int k = 1; k < 2048; k++) {
-        const uint4* p = bp + (4 * k - 2);
-        uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+        uint4 a = na, b = nb, c = nc, d = nd;
+        if (k < 2047) { const uint4* p = bp + (4 * k + 2); na = __ldg(p); nb = __ldg(p + 1); nc = __ldg(p + 2); nd = __ldg(p + 3); }
         w[0] = sha_bswap(a.x); w[1] = sha_bswap(a.y); w[2] = sha_bswap(a.z); w[3] = sha_bswap(a.w);
         w[4] = sha_bswap(b.x); w[5] = sha_bswap(b.y); w[6] = sha_bswap(b.z); w[7] = sha_bswap(b.w);
         w[8] = sha_bswap(c.x); w[9] = sha_bswap(c.y); w[10] = sha_bswap(c.z); w[11] = sha_bswap(c.w);
@@ -230,6 +232,19 @@ __device__ __forceinline__ uint8_t transcript_byte(size_t pos, uint64_t n, const
     if (o < 112) { size_t k = o - 80; return (uint8_t)(zy[q].y.l[k >> 2] >> (8 * (k & 3))); }
     return P[q * 48 + (o - 112)];
 }
+// the same transcript as big-endian 32-bit words (header and entries are word aligned: 8 + 40 n words)
+__device__ __forceinline__ uint32_t transcript_word(size_t w, uint64_t n, const uint32_t* C, const ZY* zy, const uint32_t* P) {
+    if (w < 8) {
+        const uint32_t hdr[8] = {0x52434b5a, 0x47424154, 0x43485f5f, 0x5f56315f, 0, 4096, (uint32_t)(n >> 32), (uint32_t)n};
+        return hdr[w];
+    }
+    size_t q = (w - 8) / 40;
+    uint32_t o = (uint32_t)((w - 8) % 40);
+    if (o < 12) return sha_bswap(__ldg(C + q * 12 + o));
+    if (o < 20) return sha_bswap(zy[q].z.l[o - 12]);
+    if (o < 28) return sha_bswap(zy[q].y.l[o - 20]);
+    return sha_bswap(__ldg(P + q * 12 + (o - 28)));
+}
 // K5a (parallel): one thread per 64-byte block of the transcript builds the block from the device-resident
 // pieces, expands the SHA-256 message schedule and stores W[t] + K[t], t < 64 -- everything about a block that
 // does not depend on the chaining value.
@@ -241,14 +256,12 @@ __global__ void __launch_bounds__(128) transcript_schedule_kernel(const uint8_t*
     size_t blk = first_blk + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (blk >= nblk || blk >= first_blk + blk_count) return;
     uint32_t w[16];
+    size_t nwords = len / 4;
+    const uint32_t* Cw = reinterpret_cast<const uint32_t*>(commitments);
+    const uint32_t* Pw = reinterpret_cast<const uint32_t*>(proofs);
     for (int j = 0; j < 16; j++) {
-        uint32_t v = 0;
-        for (int b = 0; b < 4; b++) {
-            size_t pos = blk * 64 + 4 * j + b;
-            uint8_t byte = pos < len ? transcript_byte(pos, n, commitments, zy, proofs) : (pos == len ? 0x80 : 0);
-            v = (v << 8) | byte;
-        }
-        w[j] = v;
+        size_t wi = blk * 16 + j;
+        w[j] = wi < nwords ? transcript_word(wi, n, Cw, zy, Pw) : (wi == nwords ? 0x80000000u : 0u);
     }
     if (blk == nblk - 1) { w[14] = (uint32_t)(((uint64_t)len * 8) >> 32); w[15] = (uint32_t)((uint64_t)len * 8); }
     uint4* dst = reinterpret_cast<uint4*>(wk + blk * 64);
@@ -355,17 +368,13 @@ __global__ void __launch_bounds__(64) transcript_tree_leaf_kernel(const uint8_t*
     size_t len = (size_t)cnt * 160, nblk = (len + 9 + 63) / 64;
     uint32_t st[8], w[16];
     sha256_init(st);
+    size_t nwords = len / 4;
+    const uint32_t* Cw = reinterpret_cast<const uint32_t*>(commitments + first * 48);
+    const uint32_t* Pw = reinterpret_cast<const uint32_t*>(proofs + first * 48);
     for (size_t blk = 0; blk < nblk; blk++) {
         for (int j = 0; j < 16; j++) {
-            uint32_t v = 0;
-            for (int b = 0; b < 4; b++) {
-                size_t pos = blk * 64 + 4 * j + b;
-                // entry bytes start at transcript offset 32 of a batch whose first entry is `first`
-                uint8_t byte = pos < len ? transcript_byte(32 + pos, 0, commitments + first * 48, zy + first, proofs + first * 48)
-                                         : (pos == len ? 0x80 : 0);
-                v = (v << 8) | byte;
-            }
-            w[j] = v;
+            size_t wi = blk * 16 + j;   // entry words start at transcript word 8 of a batch whose first entry is `first`
+            w[j] = wi < nwords ? transcript_word(8 + wi, 0, Cw, zy + first, Pw) : (wi == nwords ? 0x80000000u : 0u);
         }
         if (blk == nblk - 1) { w[14] = (uint32_t)(((uint64_t)len * 8) >> 32); w[15] = (uint32_t)((uint64_t)len * 8); }
         sha256_compress(st, w);
@@ -445,23 +454,34 @@ __global__ void __launch_bounds__(256) msm_sort_kernel(const uint8_t* __restrict
     __syncthreads();
     for (int i = t; i < n; i += blockDim.x) ord[atomicAdd(&cursor[row[i]], 1u)] = (uint32_t)i;
 }
-// one thread per (set, window, bucket b >= 1): sum of the bucket's points
+// four threads per (set, window, bucket b >= 1): each sums every fourth point of the bucket's list, then a
+// shared-memory tree joins the four partial sums (the lists are ~n/256 long; splitting them shortens the serial
+// chain of point additions that sits between "r is known" and the pairing check)
+constexpr int kBucketSplit = 4;
 __global__ void __launch_bounds__(128) msm_bucket_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P, int n,
                                                          const uint32_t* __restrict__ order, const uint32_t* __restrict__ start,
                                                          G1* __restrict__ buckets /* [3][32][256] */) {
+    __shared__ G1 sm[128];
     int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= kMsmSets * kWindows * kBuckets) return;
-    int b = tid % kBuckets, w = (tid / kBuckets) % kWindows, set = tid / (kBuckets * kWindows);
-    int kind = set == 2 ? 1 : 0;
-    const G1Affine* pts = set == 1 ? C : P;
-    const uint32_t* ord = order + ((size_t)kind * kWindows + w) * n;
-    const uint32_t* st = start + ((size_t)kind * kWindows + w) * (kBuckets + 1);
+    int bucket_id = tid / kBucketSplit, part = tid % kBucketSplit;
+    bool live = bucket_id < kMsmSets * kWindows * kBuckets;
     G1 acc = G1::identity();
-    if (b != 0) {
-        uint32_t lo = st[b], hi = st[b + 1];
-        for (uint32_t k = lo; k < hi; k++) acc = acc.add_mixed(pts[ord[k]]);
+    if (live) {
+        int b = bucket_id % kBuckets, w = (bucket_id / kBuckets) % kWindows, set = bucket_id / (kBuckets * kWindows);
+        int kind = set == 2 ? 1 : 0;
+        const G1Affine* pts = set == 1 ? C : P;
+        const uint32_t* ord = order + ((size_t)kind * kWindows + w) * n;
+        const uint32_t* st = start + ((size_t)kind * kWindows + w) * (kBuckets + 1);
+        if (b != 0) {
+            uint32_t lo = st[b], hi = st[b + 1];
+            for (uint32_t k = lo + part; k < hi; k += kBucketSplit) acc = acc.add_mixed(pts[ord[k]]);
+        }
     }
-    buckets[tid] = acc;
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    if (part < 2) sm[threadIdx.x] = sm[threadIdx.x].add(sm[threadIdx.x + 2]);
+    __syncthreads();
+    if (part == 0 && live) buckets[bucket_id] = sm[threadIdx.x].add(sm[threadIdx.x + 1]);
 }
 // one warp per (set, window): W = sum_b b * bucket[b].  Lane l owns buckets 8l .. 8l+7 (running-sum trick inside
 // the segment, then the segment's offset 8l by a short double-and-add), then a shared-memory tree over the lanes.

@@ -263,7 +263,7 @@ static int launch_lincomb(kzgb200_ctx* ctx, size_t offset, Partial* d_out) {
     phase_begin(ctx, kPhLincomb, ctx->stream);
     msm_scalars_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_z_mont, ctx->d_zy, ctx->d_r, (uint64_t)offset, n, ctx->d_digits, ctx->d_ry);
     msm_sort_kernel<<<dim3(kWindows, 2), 256, 0, ctx->stream>>>(ctx->d_digits, n, ctx->d_order, ctx->d_start);
-    msm_bucket_kernel<<<(kMsmSets * kWindows * kBuckets + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_C, ctx->d_P, n, ctx->d_order, ctx->d_start, ctx->d_buckets);
+    msm_bucket_kernel<<<(kMsmSets * kWindows * kBuckets * kBucketSplit + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_C, ctx->d_P, n, ctx->d_order, ctx->d_start, ctx->d_buckets);
     phase_end(ctx, kPhLincomb, ctx->stream);
     phase_begin(ctx, kPhReduce, ctx->stream);
     msm_window_kernel<<<kMsmSets * kWindows, 32, 0, ctx->stream>>>(ctx->d_buckets, ctx->d_windows);

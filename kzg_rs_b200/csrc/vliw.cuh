@@ -65,51 +65,45 @@ KZG_HD void exec_mul(Fp* regs, const uint16_t* ins) {
         regs[ins[0]] = Fp::mul_dual_inl(a, b, c, d);
     }
 }
-// dst = sum of (+/-)(1|2) * src over up to 24 terms: plain 13-limb signed accumulation, one reduction at the end
+// dst = sum of (+/-)(1|2) * src over up to 24 terms.  Everything is accumulated as a NON-NEGATIVE integer
+// (a negative term contributes p - v), 12 limbs plus a small carry count, and reduced once at the end:
+// quotient estimate from the top words, one multiply-subtract, at most three conditional subtractions.
 KZG_HD void exec_lin(Fp* regs, const uint32_t* ins, const uint16_t* terms) {
-    uint32_t acc[13];
+    uint32_t acc[12];
 #pragma unroll
-    for (int i = 0; i < 13; i++) acc[i] = 0;
+    for (int i = 0; i < 12; i++) acc[i] = 0;
+    uint32_t top = 0;                           // total = top * 2^384 + acc  <  48 p  <  2^387
+    Fp p = Fp::modulus();
     const uint16_t* t = terms + ins[1];
     for (uint32_t k = 0; k < ins[2]; k++) {
         uint16_t e = t[k];
-        const Fp& v = regs[e & 0x3fff];
-        uint32_t sh = (e >> 15) & 1u;          // doubled term: shift left by one
-        uint32_t w[13];
-#pragma unroll
-        for (int i = 0; i < 12; i++) w[i] = sh ? ((v.l[i] << 1) | (i ? (v.l[i - 1] >> 31) : 0u)) : v.l[i];
-        w[12] = sh ? (v.l[11] >> 31) : 0u;
-        if (e & 0x4000) {
-            uint64_t bw = 0;
-#pragma unroll
-            for (int i = 0; i < 13; i++) { uint64_t d = (uint64_t)acc[i] - w[i] - bw; acc[i] = (uint32_t)d; bw = (d >> 32) & 1; }
-        } else {
-            uint64_t c = 0;
-#pragma unroll
-            for (int i = 0; i < 13; i++) { c += (uint64_t)acc[i] + w[i]; acc[i] = (uint32_t)c; c >>= 32; }
-        }
+        Fp v = regs[e & 0x3fff];
+        if (e & 0x4000) sub_n<12>(v.l, p.l, v.l);            // p - v  (v <= p, no borrow)
+        top += add_n<12>(acc, acc, v.l);
+        if (e & 0x8000) top += add_n<12>(acc, acc, v.l);     // doubled term
     }
-    // acc in (-48p, 48p) as a two's-complement 416-bit value: add 64p, then subtract 64p, 32p, .., p where possible
-    uint32_t pk[13];
-    Fp p = Fp::modulus();
+    // q <= total / p, within 3 of it: top 64 bits of total over (top word of p) + 1
+    uint64_t t64 = ((uint64_t)top << 32) | acc[11];
+    uint32_t q = (uint32_t)(t64 / ((uint64_t)p.l[11] + 1));
+    // total -= q * p   (q < 2^9)
+    uint64_t carry = 0, bw = 0;
 #pragma unroll
-    for (int i = 0; i < 13; i++) pk[i] = ((i < 12 ? p.l[i] : 0u) << 6) | (i ? (p.l[i - 1] >> 26) : 0u);
-    {
-        uint64_t c = 0;
-#pragma unroll
-        for (int i = 0; i < 13; i++) { c += (uint64_t)acc[i] + pk[i]; acc[i] = (uint32_t)c; c >>= 32; }
+    for (int i = 0; i < 12; i++) {
+        carry += (uint64_t)p.l[i] * q;
+        uint64_t d = (uint64_t)acc[i] - (uint32_t)carry - bw;
+        acc[i] = (uint32_t)d; bw = (d >> 32) & 1; carry >>= 32;
     }
-    for (int s = 6; s >= 0; s--) {
-        uint32_t tmp[13];
-        uint64_t bw = 0;
+    top -= (uint32_t)carry + (uint32_t)bw;
+    // now 0 <= total < 4p
 #pragma unroll
-        for (int i = 0; i < 13; i++) { uint64_t d = (uint64_t)acc[i] - pk[i] - bw; tmp[i] = (uint32_t)d; bw = (d >> 32) & 1; }
-        if (!bw) {
+    for (int r = 0; r < 3; r++) {
+        uint32_t tmp[12];
+        uint32_t borrow = sub_n<12>(tmp, acc, p.l);
+        if (top || !borrow) {
 #pragma unroll
-            for (int i = 0; i < 13; i++) acc[i] = tmp[i];
+            for (int i = 0; i < 12; i++) acc[i] = tmp[i];
+            top -= borrow;
         }
-#pragma unroll
-        for (int i = 0; i < 13; i++) pk[i] = (pk[i] >> 1) | (i < 12 ? (pk[i + 1] << 31) : 0u);
     }
     Fp r;
 #pragma unroll
