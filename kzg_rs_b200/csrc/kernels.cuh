@@ -5,6 +5,7 @@
 #include "sha256.cuh"
 #include "verify.cuh"
 #include "vliw.cuh"
+#include "glv.cuh"
 
 namespace kzgb200 {
 
@@ -411,14 +412,14 @@ __global__ void transcript_tree_root_kernel(const uint32_t* __restrict__ digests
 // [y_i]G:   A = sum r_i pi_i ,  B = sum (r_i C_i + (r_i z_i) pi_i) - [sum r_i y_i] G ,  r_i = r^(offset+i).
 // v1: one thread per blob does its scalar multiplications (Shamir's trick for the pair), results are then
 // tree-summed by pair_sum_kernel.
-// Pippenger bucket method, 8-bit windows (32 windows x 255 buckets), three point/scalar sets per rank:
+// Pippenger bucket method with the GLV split: every scalar k = k1 + k2 x^2 (glv.cuh), so a point P contributes
+// [k1]P + [k2](-phi(P)) with two 128-bit halves -> 16 windows of 8 bits x 255 buckets.  Three point/scalar sets per rank:
 //   set 0: pi_i with r_i  (-> A),   set 1: C_i with r_i,   set 2: pi_i with r_i z_i   (sets 1+2 -> B').
-// No sorting network and no atomics on points: a counting sort of the digits per (set, window) gives every
-// bucket a contiguous index list, one thread then owns one bucket and walks its list.
-constexpr int kWindows = 32, kBuckets = 256, kMsmSets = 3;
-struct MsmDigits { uint8_t d[2][kWindows]; };   // per blob: bytes of r_i, bytes of r_i z_i
+// No sorting network and no atomics on points: a counting sort of the digits per (scalar kind, half, window) gives
+// every bucket two contiguous index lists (low halves -> P_i, high halves -> -phi(P_i)); threads own buckets.
+constexpr int kWindows = 16, kBuckets = 256, kMsmSets = 3, kDigitRows = 4 * kWindows;   // rows: (kind r|rz) x (half lo|hi) x window
 __global__ void __launch_bounds__(128) msm_scalars_kernel(const Fr* __restrict__ z_mont, const ZY* __restrict__ zy, const Fr* __restrict__ r_mont,
-                                                          uint64_t offset, int n, uint8_t* __restrict__ digits /* [2][32][n] */,
+                                                          uint64_t offset, int n, uint8_t* __restrict__ digits /* [4*16][n] */,
                                                           Fr* __restrict__ ry) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -428,20 +429,23 @@ __global__ void __launch_bounds__(128) msm_scalars_kernel(const Fr* __restrict__
     Fr ri_raw = ri.to_raw();
     Fr rz_raw = (ri * z_mont[i]).to_raw();    // r_i z_i   (kzg_proof.rs:425)
     ry[i] = ri * zy[i].y;                     // r_i y_i in normal form
-    for (int w = 0; w < kWindows; w++) {
-        digits[((size_t)0 * kWindows + w) * n + i] = (uint8_t)(ri_raw.l[w >> 2] >> (8 * (w & 3)));
-        digits[((size_t)1 * kWindows + w) * n + i] = (uint8_t)(rz_raw.l[w >> 2] >> (8 * (w & 3)));
-    }
+    uint32_t h[2][2][4];
+    glv_split(ri_raw.l, h[0][0], h[0][1]);
+    glv_split(rz_raw.l, h[1][0], h[1][1]);
+    for (int kind = 0; kind < 2; kind++)
+        for (int half = 0; half < 2; half++)
+            for (int w = 0; w < kWindows; w++)
+                digits[((size_t)(kind * 2 + half) * kWindows + w) * n + i] = (uint8_t)(h[kind][half][w >> 2] >> (8 * (w & 3)));
 }
-// counting sort of one digit row: grid = (32 windows, 2 scalar kinds); order[kind][w][*] = blob indices grouped by
-// digit, start[kind][w][b] = first position of digit b (start[..][256] = n)
+// counting sort of one digit row: grid = kDigitRows; order[row][*] = blob indices grouped by digit,
+// start[row][b] = first position of digit b (start[row][256] = n)
 __global__ void __launch_bounds__(256) msm_sort_kernel(const uint8_t* __restrict__ digits, int n, uint32_t* __restrict__ order,
                                                        uint32_t* __restrict__ start) {
     __shared__ uint32_t hist[kBuckets], cursor[kBuckets];
-    int w = blockIdx.x, kind = blockIdx.y, t = threadIdx.x;
-    const uint8_t* row = digits + ((size_t)kind * kWindows + w) * n;
-    uint32_t* ord = order + ((size_t)kind * kWindows + w) * n;
-    uint32_t* st = start + ((size_t)kind * kWindows + w) * (kBuckets + 1);
+    int row_id = blockIdx.x, t = threadIdx.x;
+    const uint8_t* row = digits + (size_t)row_id * n;
+    uint32_t* ord = order + (size_t)row_id * n;
+    uint32_t* st = start + (size_t)row_id * (kBuckets + 1);
     hist[t] = 0;
     __syncthreads();
     for (int i = t; i < n; i += blockDim.x) atomicAdd(&hist[row[i]], 1u);
@@ -454,13 +458,13 @@ __global__ void __launch_bounds__(256) msm_sort_kernel(const uint8_t* __restrict
     __syncthreads();
     for (int i = t; i < n; i += blockDim.x) ord[atomicAdd(&cursor[row[i]], 1u)] = (uint32_t)i;
 }
-// four threads per (set, window, bucket b >= 1): each sums every fourth point of the bucket's list, then a
-// shared-memory tree joins the four partial sums (the lists are ~n/256 long; splitting them shortens the serial
-// chain of point additions that sits between "r is known" and the pairing check)
+// four threads per (set, window, bucket b >= 1): threads 0,1 walk the low-half list (points P_i), threads 2,3 the
+// high-half list (points -phi(P_i)), each taking every second entry; a shared-memory tree joins the four partial sums
+// (splitting the lists shortens the serial chain of point additions between "r is known" and the pairing check)
 constexpr int kBucketSplit = 4;
 __global__ void __launch_bounds__(128) msm_bucket_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P, int n,
                                                          const uint32_t* __restrict__ order, const uint32_t* __restrict__ start,
-                                                         G1* __restrict__ buckets /* [3][32][256] */) {
+                                                         G1* __restrict__ buckets /* [3][16][256] */) {
     __shared__ G1 sm[128];
     int tid = blockIdx.x * blockDim.x + threadIdx.x;
     int bucket_id = tid / kBucketSplit, part = tid % kBucketSplit;
@@ -468,13 +472,17 @@ __global__ void __launch_bounds__(128) msm_bucket_kernel(const G1Affine* __restr
     G1 acc = G1::identity();
     if (live) {
         int b = bucket_id % kBuckets, w = (bucket_id / kBuckets) % kWindows, set = bucket_id / (kBuckets * kWindows);
-        int kind = set == 2 ? 1 : 0;
+        int kind = set == 2 ? 1 : 0, half = part >> 1;
         const G1Affine* pts = set == 1 ? C : P;
-        const uint32_t* ord = order + ((size_t)kind * kWindows + w) * n;
-        const uint32_t* st = start + ((size_t)kind * kWindows + w) * (kBuckets + 1);
+        int row_id = (kind * 2 + half) * kWindows + w;
+        const uint32_t* ord = order + (size_t)row_id * n;
+        const uint32_t* st = start + (size_t)row_id * (kBuckets + 1);
         if (b != 0) {
             uint32_t lo = st[b], hi = st[b + 1];
-            for (uint32_t k = lo + part; k < hi; k += kBucketSplit) acc = acc.add_mixed(pts[ord[k]]);
+            for (uint32_t k = lo + (part & 1); k < hi; k += 2) {
+                G1Affine q = pts[ord[k]];
+                acc = acc.add_mixed(half ? glv_endo_neg(q) : q);
+            }
         }
     }
     sm[threadIdx.x] = acc;
@@ -485,9 +493,9 @@ __global__ void __launch_bounds__(128) msm_bucket_kernel(const G1Affine* __restr
 }
 // one warp per (set, window): W = sum_b b * bucket[b].  Lane l owns buckets 8l .. 8l+7 (running-sum trick inside
 // the segment, then the segment's offset 8l by a short double-and-add), then a shared-memory tree over the lanes.
-__global__ void __launch_bounds__(32) msm_window_kernel(const G1* __restrict__ buckets, G1* __restrict__ windows /* [3][32] */) {
+__global__ void __launch_bounds__(32) msm_window_kernel(const G1* __restrict__ buckets, G1* __restrict__ windows /* [3][16] */) {
     __shared__ G1 sm[32];
-    int l = threadIdx.x, sw = blockIdx.x;          // sw = set * 32 + window
+    int l = threadIdx.x, sw = blockIdx.x;          // sw = set * kWindows + window
     const G1* bk = buckets + (size_t)sw * kBuckets + 8 * l;
     G1 run = G1::identity(), acc = G1::identity();
     for (int j = 7; j >= 0; j--) {
@@ -512,9 +520,6 @@ struct Partial {
     uint32_t err;     // OR of the per-blob error flags of this rank
     uint32_t pad[7];
 };
-// Warp-cooperative Jacobian doubling / addition for the Horner recombination: the 248 doublings are a serial
-// chain, but each doubling has only 3 dependent multiplication levels (each addition 5), so three / four lanes
-// of a warp run the independent products of a level side by side through shared memory.
 // Lanes of a warp run in lockstep, so the lanes do not branch to different products: every lane SELECTS its two
 // operands and all of them execute the one multiplication together.
 struct CoopPoint { Fp v[20]; };   // [0..2] = X,Y,Z ; the rest scratch

@@ -28,7 +28,7 @@ struct kzgb200_ctx {
     G1Affine *d_C = nullptr, *d_P = nullptr;
     uint32_t* d_status = nullptr;
     Fr *d_ry = nullptr, *d_r = nullptr;
-    uint8_t* d_digits = nullptr;            // [2][32][cap]
+    uint8_t* d_digits = nullptr;            // [4*16][cap]
     uint32_t *d_order = nullptr, *d_start = nullptr;
     G1 *d_buckets = nullptr, *d_windows = nullptr;
     Partial* d_partial = nullptr;
@@ -82,7 +82,7 @@ static int ensure_capacity(kzgb200_ctx* ctx, size_t n, bool need_blob_staging) {
         CK(regrow(ctx->d_z_mont, c)); CK(regrow(ctx->d_zy, c));
         CK(regrow(ctx->d_C, c)); CK(regrow(ctx->d_P, c));
         CK(regrow(ctx->d_status, c)); CK(regrow(ctx->d_ry, c));
-        CK(regrow(ctx->d_digits, c * 2 * kWindows)); CK(regrow(ctx->d_order, c * 2 * kWindows));
+        CK(regrow(ctx->d_digits, c * kDigitRows)); CK(regrow(ctx->d_order, c * kDigitRows));
         CK(regrow(ctx->d_zout, c * 32)); CK(regrow(ctx->d_yout, c * 32));
         ctx->cap = c;
     }
@@ -119,7 +119,7 @@ extern "C" int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_p
         CK(cudaMalloc(&ctx->d_r, sizeof(Fr)));
         CK(cudaMalloc(&ctx->d_partial, sizeof(Partial)));
         CK(cudaMalloc(&ctx->d_result, 16));
-        CK(cudaMalloc(&ctx->d_start, 2 * kWindows * (kBuckets + 1) * sizeof(uint32_t)));
+        CK(cudaMalloc(&ctx->d_start, kDigitRows * (kBuckets + 1) * sizeof(uint32_t)));
         CK(cudaMalloc(&ctx->d_buckets, kMsmSets * kWindows * kBuckets * sizeof(G1)));
         CK(cudaMalloc(&ctx->d_windows, kMsmSets * kWindows * sizeof(G1)));
         CK(cudaMallocHost(&ctx->h_result, 16));
@@ -262,7 +262,7 @@ static int launch_lincomb(kzgb200_ctx* ctx, size_t offset, Partial* d_out) {
     int n = (int)ctx->cur_n;
     phase_begin(ctx, kPhLincomb, ctx->stream);
     msm_scalars_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_z_mont, ctx->d_zy, ctx->d_r, (uint64_t)offset, n, ctx->d_digits, ctx->d_ry);
-    msm_sort_kernel<<<dim3(kWindows, 2), 256, 0, ctx->stream>>>(ctx->d_digits, n, ctx->d_order, ctx->d_start);
+    msm_sort_kernel<<<kDigitRows, 256, 0, ctx->stream>>>(ctx->d_digits, n, ctx->d_order, ctx->d_start);
     msm_bucket_kernel<<<(kMsmSets * kWindows * kBuckets * kBucketSplit + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_C, ctx->d_P, n, ctx->d_order, ctx->d_start, ctx->d_buckets);
     phase_end(ctx, kPhLincomb, ctx->stream);
     phase_begin(ctx, kPhReduce, ctx->stream);
