@@ -122,6 +122,16 @@ int kzgb200_last_partial(kzgb200_ctx* ctx, uint8_t* out352);
  * [tau^j]G1, j < degree, are given compressed in tau_powers48 (host, degree x 48 bytes). */
 int kzgb200_harness_generate(kzgb200_ctx* ctx, uint64_t seed, size_t n, int degree, const uint8_t* tau_powers48,
                              uint8_t* d_blobs, uint8_t* d_commitments, uint8_t* d_proofs);
+/* ---- commit / prove (EIP-4844 blob_to_kzg_commitment / compute_blob_kzg_proof) -------------------
+ * kzg-rs has no commit/prove path (its g1_points are loaded but never read); these are the companion operations used
+ * to make test data for arbitrary blobs, pinned by the commitment / proof bytes of the reference's valid vectors.
+ * kzgb200_load_g1_lagrange: the setup's 4096 Lagrange G1 points, compressed, FILE order (host, 4096 x 48 bytes);
+ * builds a 4.8 GB fixed-base window table on the device (once per context).  The batch calls take DEVICE pointers. */
+int kzgb200_load_g1_lagrange(kzgb200_ctx* ctx, const uint8_t* g1_lagrange, size_t n_points);
+int kzgb200_blob_to_kzg_commitment_batch(kzgb200_ctx* ctx, const uint8_t* d_blobs, size_t n, uint8_t* d_commitments_out);
+int kzgb200_compute_blob_kzg_proof_batch(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t* d_commitments, size_t n,
+                                         uint8_t* d_proofs_out);
+
 /* per-phase device timing of single-GPU batch calls (CUDA events on the context stream).  out7 = milliseconds of
  * {parse G1, challenge, evaluate, transcript r, lincomb terms, reduce, final pairing} of the last call. */
 int kzgb200_set_profiling(kzgb200_ctx* ctx, int on);

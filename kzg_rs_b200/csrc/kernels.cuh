@@ -813,3 +813,138 @@ __global__ void __launch_bounds__(64) harness_commit_kernel(uint64_t seed, int n
 }
 
 }  // namespace kzgb200
+
+// ================================================================================================ commit / prove
+// blob_to_kzg_commitment / compute_blob_kzg_proof as GPU operations (EIP-4844 semantics; kzg-rs
+// itself has no commit/prove path -- these produce test data for arbitrary blobs and are pinned by the commitment /
+// proof bytes of the reference's valid vectors).  Fixed-base MSM over the 4096 bit-reversed Lagrange points with a
+// precomputed window table table[j][w][d-1] = [d * 256^w] L_j (Jacobian), so a blob costs 4096 x 32 table additions
+// spread over a CTA.
+namespace kzgb200 {
+
+constexpr int kLagWindows = 32, kLagEntries = 255;
+__global__ void lag_parse_kernel(const uint8_t* __restrict__ bytes /* 4096 x 48, file order */, G1Affine* __restrict__ out /* bit-reversed */,
+                                 uint32_t* __restrict__ bad) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kFieldElementsPerBlob) return;
+    uint32_t src = 0;
+    for (int b = 0; b < 12; b++) src |= (((uint32_t)i >> b) & 1u) << (11 - b);
+    uint8_t buf[48];
+    for (int k = 0; k < 48; k++) buf[k] = bytes[(size_t)src * 48 + k];
+    if (!g1_from_compressed(out[i], buf, false)) atomicOr(bad, 1u);   // unchecked, as build.rs:68
+}
+__global__ void __launch_bounds__(128) lag_table_kernel(const G1Affine* __restrict__ L, G1* __restrict__ table) {
+    int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= kFieldElementsPerBlob * kLagWindows) return;
+    int j = tid / kLagWindows, w = tid % kLagWindows;
+    G1 base = G1::from_affine(L[j]);
+    for (int k = 0; k < 8 * w; k++) base = base.dbl();
+    G1* row = table + (size_t)tid * kLagEntries;
+    G1 acc = base;
+    row[0] = acc;
+    for (int d = 2; d <= kLagEntries; d++) { acc = acc.add(base); row[d - 1] = acc; }
+}
+// scalars of the commitment MSM = the blob's field elements (canonical limbs); flags non-canonical elements
+__global__ void __launch_bounds__(128) blob_scalars_kernel(const uint8_t* __restrict__ blobs, int n, Fr* __restrict__ scalars, uint32_t* __restrict__ status) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * kFieldElementsPerBlob) return;
+    Fr f = load_fe_be(reinterpret_cast<const uint4*>(blobs) + 2 * i);
+    if (f.geq_modulus()) atomicOr(&status[i / kFieldElementsPerBlob], kErrBlob);
+    scalars[i] = f;
+}
+// quotient q_i = (f_i - y) / (w_i - z) in evaluation form (one CTA of 128 threads per blob, Montgomery batch inversion
+// across the CTA); if z = w_m the m-th entry is sum_{i != m} (f_i - y) w_i / (z (z - w_i))
+__global__ void __launch_bounds__(kEvalThreads) quotient_kernel(const uint8_t* __restrict__ blobs, int n, const Fr* __restrict__ z_mont,
+                                                                const ZY* __restrict__ zy, const DeviceTables* __restrict__ T,
+                                                                Fr* __restrict__ scalars) {
+    __shared__ Fr s_tot[kEvalThreads], s_pre[kEvalThreads], s_inv;
+    __shared__ int s_special;
+    int blob = blockIdx.x, t = threadIdx.x;
+    if (blob >= n) return;
+    if (t == 0) s_special = -1;
+    __syncthreads();
+    Fr z = z_mont[blob], y_m = Fr::from_raw(zy[blob].y), one = Fr::one();
+    const uint4* base = reinterpret_cast<const uint4*>(blobs + (size_t)blob * kBytesPerBlob) + (size_t)t * kLeavesPerThread * 2;
+    Fr den[kLeavesPerThread], pre[kLeavesPerThread];
+    Fr acc = one;
+    for (int j = 0; j < kLeavesPerThread; j++) {
+        int i = t * kLeavesPerThread + j;
+        Fr w = T->twiddle[i >> 1];
+        if (i & 1) w = w.neg();
+        Fr d = w - z;
+        if (d.is_zero()) { s_special = i; d = one; }
+        den[j] = d; pre[j] = acc; acc = acc.mul_inl(d);
+    }
+    s_tot[t] = acc;
+    __syncthreads();
+    if (t == 0) {
+        Fr run = one;
+        for (int k = 0; k < kEvalThreads; k++) { s_pre[k] = run; run = run * s_tot[k]; }
+        s_inv = fr_inv(run);
+        // s_pre[k] becomes the inverse of (product of the totals of threads 0..k)
+        Fr inv = s_inv;
+        for (int k = kEvalThreads - 1; k >= 0; k--) { Fr tk = s_tot[k]; s_tot[k] = inv; inv = inv * tk; }
+    }
+    __syncthreads();
+    // inverse of this thread's full product = s_tot[t] * (product of earlier threads' totals) = s_tot[t] * s_pre[t]
+    Fr inv_run = s_tot[t] * s_pre[t];
+    Fr* out = scalars + (size_t)blob * kFieldElementsPerBlob + (size_t)t * kLeavesPerThread;
+    for (int j = kLeavesPerThread - 1; j >= 0; j--) {
+        Fr inv_d = inv_run.mul_inl(pre[j]);          // 1 / den[j]
+        inv_run = inv_run.mul_inl(den[j]);
+        Fr f = Fr::from_raw(load_fe_be(base + 2 * j));
+        out[j] = ((f - y_m).mul_inl(inv_d)).to_raw();
+    }
+    __syncthreads();
+    if (s_special >= 0 && t == 0) {   // z in the domain (probability 2^-243 for hashed z): direct formula
+        int m = s_special;
+        Fr zi = fr_inv(z), sum = Fr::zero();
+        Fr* row = scalars + (size_t)blob * kFieldElementsPerBlob;
+        for (int i = 0; i < kFieldElementsPerBlob; i++) {
+            if (i == m) continue;
+            Fr w = T->twiddle[i >> 1];
+            if (i & 1) w = w.neg();
+            sum = sum - Fr::from_raw(row[i]) * w * zi;    // (f_i-y)/(w_i-z) = -(f_i-y)/(z-w_i)
+        }
+        row[m] = sum.to_raw();
+    }
+}
+__global__ void status_or_kernel(const uint32_t* __restrict__ status, int n, uint32_t* __restrict__ out) {
+    __shared__ uint32_t s;
+    if (threadIdx.x == 0) s = 0;
+    __syncthreads();
+    uint32_t e = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) e |= status[i];
+    if (e) atomicOr(&s, e);
+    __syncthreads();
+    if (threadIdx.x == 0) out[0] = s;
+}
+// one CTA (256 threads) per blob: sum_j [s_j] L_j through the window table, tree-summed in shared memory, compressed
+__global__ void __launch_bounds__(256) lag_msm_kernel(const Fr* __restrict__ scalars, int n, const G1* __restrict__ table, uint8_t* __restrict__ out48) {
+    __shared__ G1 sm[256];
+    int blob = blockIdx.x, t = threadIdx.x;
+    if (blob >= n) return;
+    const Fr* row = scalars + (size_t)blob * kFieldElementsPerBlob;
+    G1 acc = G1::identity();
+    for (int j = t; j < kFieldElementsPerBlob; j += 256) {
+        Fr s = row[j];
+        const G1* tj = table + (size_t)j * kLagWindows * kLagEntries;
+        for (int w = 0; w < kLagWindows; w++) {
+            uint32_t d = (s.l[w >> 2] >> (8 * (w & 3))) & 0xffu;
+            if (d) acc = acc.add(tj[(size_t)w * kLagEntries + d - 1]);
+        }
+    }
+    sm[t] = acc;
+    __syncthreads();
+    for (int span = 128; span >= 1; span >>= 1) {
+        if (t < span) sm[t] = sm[t].add(sm[t + span]);
+        __syncthreads();
+    }
+    if (t == 0) {
+        uint8_t enc[48];
+        g1_to_compressed(enc, g1_to_affine(sm[0]));
+        for (int k = 0; k < 48; k++) out48[(size_t)blob * 48 + k] = enc[k];
+    }
+}
+
+}  // namespace kzgb200

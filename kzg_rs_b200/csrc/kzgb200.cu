@@ -35,6 +35,8 @@ struct kzgb200_ctx {
     uint32_t* d_result = nullptr;
     uint8_t *d_zout = nullptr, *d_yout = nullptr;
     uint8_t *d_many = nullptr;
+    G1* d_lag_table = nullptr;      // [4096][32][255] window table of the Lagrange G1 points (commit / prove only)
+    Fr* d_scalars = nullptr;
     uint32_t* d_wk = nullptr;       // transcript W+K words, 64 per SHA block
     size_t wk_cap = 0;
     uint32_t* h_result = nullptr;   // pinned
@@ -152,7 +154,7 @@ extern "C" void kzgb200_destroy(kzgb200_ctx* ctx) {
     if (ctx->d_chain_state) cudaFree(ctx->d_chain_state);
     void* ptrs[] = {ctx->tables, ctx->d_blobs, ctx->d_c, ctx->d_p, ctx->d_z_mont, ctx->d_zy, ctx->d_C, ctx->d_P, ctx->d_status,
                     ctx->d_ry, ctx->d_r, ctx->d_partial, ctx->d_result, ctx->d_zout, ctx->d_yout, ctx->d_many, ctx->d_wk,
-                    ctx->d_digits, ctx->d_order, ctx->d_start, ctx->d_buckets, ctx->d_windows};
+                    ctx->d_digits, ctx->d_order, ctx->d_start, ctx->d_buckets, ctx->d_windows, ctx->d_lag_table, ctx->d_scalars};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -509,6 +511,67 @@ extern "C" int kzgb200_get_phase_ms(kzgb200_ctx* ctx, float* out7) {
     if (!ctx || !out7) return KZGB200_BAD_ARGS;
     for (int i = 0; i < 7; i++) out7[i] = ctx->phase_ms[i];
     return KZGB200_OK;
+}
+// ---- commit / prove ------------------------------------------------------------------------------
+extern "C" int kzgb200_load_g1_lagrange(kzgb200_ctx* ctx, const uint8_t* g1_lagrange, size_t n_points) {
+    if (!ctx || !g1_lagrange || n_points != (size_t)kFieldElementsPerBlob) return KZGB200_INVALID_SETUP;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->d_lag_table) return KZGB200_OK;
+    uint8_t* d_bytes = nullptr; G1Affine* d_L = nullptr; uint32_t* d_bad = nullptr; uint32_t bad = 0;
+    CK(cudaMalloc(&d_bytes, n_points * 48)); CK(cudaMalloc(&d_L, n_points * sizeof(G1Affine))); CK(cudaMalloc(&d_bad, 4));
+    CK(cudaMalloc(&ctx->d_lag_table, (size_t)kFieldElementsPerBlob * kLagWindows * kLagEntries * sizeof(G1)));
+    CK(cudaMemsetAsync(d_bad, 0, 4, ctx->stream));
+    CK(cudaMemcpyAsync(d_bytes, g1_lagrange, n_points * 48, cudaMemcpyHostToDevice, ctx->stream));
+    lag_parse_kernel<<<(kFieldElementsPerBlob + 127) / 128, 128, 0, ctx->stream>>>(d_bytes, d_L, d_bad);
+    lag_table_kernel<<<(kFieldElementsPerBlob * kLagWindows + 127) / 128, 128, 0, ctx->stream>>>(d_L, ctx->d_lag_table);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_bytes); cudaFree(d_L); cudaFree(d_bad);
+    if (bad) { cudaFree(ctx->d_lag_table); ctx->d_lag_table = nullptr; return KZGB200_INVALID_SETUP; }
+    return KZGB200_OK;
+}
+// shared driver: want_proof == 0 -> commitments of the blobs; 1 -> proofs at the Fiat-Shamir challenge of (blob, commitment)
+static int commit_or_prove(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t* d_commitments, size_t n, uint8_t* d_out, int want_proof) {
+    if (!ctx->d_lag_table) return KZGB200_INVALID_SETUP;
+    const size_t kChunk = 1024;
+    int rc = ensure_capacity(ctx, n < kChunk ? n : kChunk, false);
+    if (rc) return rc;
+    if (!ctx->d_scalars) CK(cudaMalloc(&ctx->d_scalars, kChunk * (size_t)kFieldElementsPerBlob * sizeof(Fr)));
+    uint32_t any_bad = 0;
+    for (size_t lo = 0; lo < n; lo += kChunk) {
+        int cnt = (int)(n - lo < kChunk ? n - lo : kChunk);
+        const uint8_t* blobs = d_blobs + lo * kBytesPerBlob;
+        CK(cudaMemsetAsync(ctx->d_status, 0, cnt * sizeof(uint32_t), ctx->stream));
+        if (!want_proof) {
+            blob_scalars_kernel<<<(unsigned)(((size_t)cnt * kFieldElementsPerBlob + 127) / 128), 128, 0, ctx->stream>>>(blobs, cnt, ctx->d_scalars, ctx->d_status);
+        } else {
+            challenge_kernel<<<(cnt + 63) / 64, 64, 0, ctx->stream>>>(blobs, d_commitments + lo * 48, cnt, ctx->d_z_mont, ctx->d_zy);
+            eval_kernel<<<cnt, kEvalThreads, 0, ctx->stream>>>(blobs, cnt, ctx->d_z_mont, ctx->tables, ctx->d_zy, ctx->d_status);
+            quotient_kernel<<<cnt, kEvalThreads, 0, ctx->stream>>>(blobs, cnt, ctx->d_z_mont, ctx->d_zy, ctx->tables, ctx->d_scalars);
+        }
+        lag_msm_kernel<<<cnt, 256, 0, ctx->stream>>>(ctx->d_scalars, cnt, ctx->d_lag_table, d_out + lo * 48);
+        status_or_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_status, cnt, ctx->d_result);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(ctx->h_result, ctx->d_result, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        any_bad |= ctx->h_result[0];
+    }
+    return any_bad ? KZGB200_BAD_ARGS : KZGB200_OK;
+}
+extern "C" int kzgb200_blob_to_kzg_commitment_batch(kzgb200_ctx* ctx, const uint8_t* d_blobs, size_t n, uint8_t* d_commitments_out) {
+    if (!ctx || !d_blobs || !d_commitments_out || n == 0) return KZGB200_BAD_ARGS;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    CK(cudaSetDevice(ctx->device));
+    return commit_or_prove(ctx, d_blobs, nullptr, n, d_commitments_out, 0);
+}
+extern "C" int kzgb200_compute_blob_kzg_proof_batch(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t* d_commitments, size_t n,
+                                                    uint8_t* d_proofs_out) {
+    if (!ctx || !d_blobs || !d_commitments || !d_proofs_out || n == 0) return KZGB200_BAD_ARGS;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    CK(cudaSetDevice(ctx->device));
+    return commit_or_prove(ctx, d_blobs, d_commitments, n, d_proofs_out, 1);
 }
 // the stream every call of this context is issued on (cudaStream_t), for event timing by the caller
 extern "C" void* kzgb200_stream(kzgb200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }

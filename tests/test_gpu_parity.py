@@ -190,3 +190,37 @@ def test_synthetic_batch_64_against_oracle(K, settings, oracle):
     with pytest.raises(K.KzgError) as e:
         K.KzgProof.verify_blob_kzg_proof_batch_raw(hb, n, hc, n - 1, hp, n, settings)
     assert e.value.kind == "InvalidBytesLength"
+
+
+def test_gpu_commit_and_prove_reproduce_reference_vector_bytes(K, settings, vectors, oracle):
+    """blob_to_kzg_commitment / compute_blob_kzg_proof on the GPU regenerate the commitment and proof
+    bytes of every valid verify_blob_kzg_proof vector, and agree with the oracle on random blobs."""
+    import random
+    import torch
+    lib, ctx = K.Library.get().dll, settings.context(0)
+    assert lib.kzgb200_load_g1_lagrange(ctx, settings.g1_lagrange_bytes, 4096) == 0
+    cases = [c for c in vectors["verify_blob_kzg_proof"] if c["output"] is True]
+    rnd = random.Random(99)
+    q = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+    extra = [b"".join(rnd.randrange(q).to_bytes(32, "big") for _ in range(4096)) for _ in range(2)]
+    blobs = [vectors.blobs[c["blob"]] for c in cases] + extra
+    n = len(blobs)
+    d_b = torch.frombuffer(bytearray(b"".join(blobs)), dtype=torch.uint8).cuda()
+    d_c = torch.empty(n * 48, dtype=torch.uint8, device="cuda")
+    d_p = torch.empty(n * 48, dtype=torch.uint8, device="cuda")
+    assert lib.kzgb200_blob_to_kzg_commitment_batch(ctx, d_b.data_ptr(), n, d_c.data_ptr()) == 0
+    assert lib.kzgb200_compute_blob_kzg_proof_batch(ctx, d_b.data_ptr(), d_c.data_ptr(), n, d_p.data_ptr()) == 0
+    hc, hp = d_c.cpu().numpy().tobytes(), d_p.cpu().numpy().tobytes()
+    for i, c in enumerate(cases):
+        assert hc[48 * i:48 * i + 48] == unhex(c["commitment"]), c["name"]
+        assert hp[48 * i:48 * i + 48] == unhex(c["proof"]), c["name"]
+    for k, blob in enumerate(extra):
+        i = len(cases) + k
+        assert hc[48 * i:48 * i + 48] == oracle.blob_to_kzg_commitment(blob)
+        assert hp[48 * i:48 * i + 48] == oracle.compute_blob_kzg_proof(blob, hc[48 * i:48 * i + 48])
+    # and the verifier accepts what the prover produced (random blobs, batch path)
+    assert K.KzgProof.verify_blob_kzg_proof_batch_raw(b"".join(blobs), n, hc, n, hp, n, settings) is True
+    # a non-canonical element is rejected by the commit path as well
+    bad = bytearray(blobs[0]); bad[0:32] = q.to_bytes(32, "big")
+    d_bad = torch.frombuffer(bad, dtype=torch.uint8).cuda()
+    assert lib.kzgb200_blob_to_kzg_commitment_batch(ctx, d_bad.data_ptr(), 1, d_c.data_ptr()) == 1
