@@ -42,6 +42,9 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=2048, help="blobs in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lowdegree-blobs", action="store_true",
+                    help="blobs = evaluations of random degree<8 polynomials (cheap generator) instead of uniformly random "
+                         "blobs committed / proved by the GPU commit/prove path")
     return ap.parse_args()
 
 
@@ -111,7 +114,8 @@ def workload_config(args, n, world):
     return {"workload": "verify_blob_kzg_proof_batch on %d synthetic blobs per GPU (%d total, %.2f GiB of blob bytes per GPU), "
                         "BASELINE.json configs[3]" % (n, n * world, n * BLOB / 2**30),
             "blobs_per_gpu": n, "total_blobs": n * world, "parallelism": "blob-sharded x%d" % world,
-            "generator": "harness: random degree<8 polynomials in evaluation form, commitments/proofs over the mainnet setup, seed 0x4B5A47",
+            "generator": ("uniformly random field elements, commitments/proofs by the GPU commit/prove path over the mainnet setup" if not args.lowdegree_blobs
+                          else "harness: random degree<8 polynomials in evaluation form, commitments/proofs over the mainnet setup, seed 0x4B5A47"),
             "cache": "inputs (>= 2 GiB per step) are larger than the 126 MB L2"}
 
 
@@ -122,6 +126,15 @@ def make_workload_device(lib, ctx, args, n, rank):
     blobs = torch.empty(n * BLOB, dtype=torch.uint8, device="cuda")
     cs = torch.empty(n * 48, dtype=torch.uint8, device="cuda")
     ps = torch.empty(n * 48, dtype=torch.uint8, device="cuda")
+    if not getattr(args, "lowdegree_blobs", False):
+        S = K.KzgSettings.load_trusted_setup_file()
+        assert lib.kzgb200_load_g1_lagrange(ctx, S.g1_lagrange_bytes, 4096) == 0
+        g = torch.Generator(device="cuda").manual_seed(0x4B5A47 + rank)
+        blobs = torch.randint(0, 256, (n * BLOB,), dtype=torch.uint8, device="cuda", generator=g)
+        blobs.view(n * 4096, 32)[:, 0] &= 0x3f          # every element < 2^254 < q
+        assert lib.kzgb200_blob_to_kzg_commitment_batch(ctx, blobs.data_ptr(), n, cs.data_ptr()) == 0
+        assert lib.kzgb200_compute_blob_kzg_proof_batch(ctx, blobs.data_ptr(), cs.data_ptr(), n, ps.data_ptr()) == 0
+        return blobs, cs, ps
     rc = lib.kzgb200_harness_generate(ctx, 0x4B5A47 + rank, n, 8, tau, blobs.data_ptr(), cs.data_ptr(), ps.data_ptr())
     assert rc == 0, "harness failed rc=%d" % rc
     return blobs, cs, ps

@@ -215,6 +215,11 @@ static int launch_phase1(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t
     for (int i = 0; i < kPhCount; i++) ctx->ph_started[i] = false;
     size_t chunk = n;
     if (h_blobs) { chunk = (n + kMaxChunks - 1) / kMaxChunks; if (chunk < kMinChunk) chunk = kMinChunk; }
+    else if (with_transcript && ctx->transcript_mode == KZGB200_TRANSCRIPT_EXACT && n >= 4 * kMinChunk) {
+        // resident batch, serial transcript: a few chunks on separate streams let the chain start as soon as the
+        // first chunk's z, y exist instead of after the evaluation of the whole batch
+        chunk = (n + 7) / 8; if (chunk < kMinChunk) chunk = kMinChunk;
+    }
     size_t nchunks = (n + chunk - 1) / chunk;
     CK(cudaMemsetAsync(ctx->d_status, 0, n * sizeof(uint32_t), ctx->stream));
     CK(cudaEventRecord(ctx->ev_begin, ctx->stream));
