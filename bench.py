@@ -284,7 +284,8 @@ def main():
                "config": cfg,
                "e2e": {"value": e2e, "unit": "blobs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": n * ALGO_BYTES_PER_BLOB * world,
                        "d2h_bytes_per_step": 8 * world},
-               "gpu_launches": plan.launches_per_step * args.steps * 4, "clocks": sampler.summary(),
+               "gpu_launches": args.steps * sum(plan.count_launches(n, resident=r, tree=t) for r in (True, False) for t in (True, False)),
+               "clocks": sampler.summary(),
                "phases_ms": dict(zip(PHASES, phases)) if world == 1 else None, "roofline": roof, "int_pipe": int_pipe, "negatives": neg,
                "exact_transcript": {"value": total / (ex_ms / 1e3), "e2e": total / (ex_e2e / 1e3), "unit": "blobs/s",
                                     "ms_per_step": ex_ms, "e2e_ms_per_step": ex_e2e,

@@ -114,6 +114,102 @@ __global__ void __launch_bounds__(64) challenge_kernel(const uint8_t* __restrict
     zy[i].z = zm.to_raw();
 }
 
+// K2, warp-specialised version.  A single warp can issue one ALU-pipe instruction every other clock, and one SHA-256
+// block costs ~1400 of them in a chain that is serial per blob, so "one thread per blob" leaves the machine at ~55 % of
+// the ALU pipe with n/32 warps.  Here a CTA owns 128 blobs with 4 CONSUMER warps (the 64 rounds: the only truly serial
+// part, ~2/3 of the work) and 4 PRODUCER warps (byte swap + message schedule + K, which do not depend on the chaining
+// value) -- one of each per SM sub-partition -- handing W[t]+K[t] over through a double-buffered shared-memory tile with
+// one named barrier per block and pair.  Additions are issued as IMAD (multiplier = a kernel argument equal to 1, so
+// ptxas cannot turn them back into IADD3): they run on the FMA pipe beside the SHF/LOP3 stream of the other warp.
+constexpr int kWsBlobs = 128, kWsThreads = 256;
+constexpr int kWsSmemBytes = 2 * 64 * kWsBlobs * 4;
+__device__ __forceinline__ uint32_t fadd(uint32_t x, uint32_t y, uint32_t one) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(one), "r"(y));
+    return r;
+}
+__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__global__ void __launch_bounds__(kWsThreads, 1) challenge_ws_kernel(const uint8_t* __restrict__ blobs, const uint8_t* __restrict__ commitments,
+                                                                     int n, Fr* __restrict__ z_mont, ZY* __restrict__ zy, uint32_t one) {
+    extern __shared__ uint32_t wk[];                 // [2][64][kWsBlobs]
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int role = warp >> 2, pair = warp & 3;           // role 0 = consumer, 1 = producer; the pair shares an SMSP (warp % 4)
+    int local = pair * 32 + lane;
+    int blob = blockIdx.x * kWsBlobs + local;
+    bool valid = blob < n;
+    int bsafe = valid ? blob : n - 1;                // out-of-range lanes shadow the last blob (barrier counts stay whole)
+    int bar_id = 1 + pair;
+    if (role == 1) {
+        const uint4* bp = reinterpret_cast<const uint4*>(blobs + (size_t)bsafe * kBytesPerBlob);
+        const uint32_t* cp = reinterpret_cast<const uint32_t*>(commitments + (size_t)bsafe * 48);
+        uint4 na = __ldg(bp + 2), nb = __ldg(bp + 3), nc = __ldg(bp + 4), nd = __ldg(bp + 5);   // block 1
+        for (int k = 0; k < 2050; k++) {
+            uint32_t w[16];
+            if (k == 0) {
+                w[0] = 0x4653424c; w[1] = 0x4f425645; w[2] = 0x52494659; w[3] = 0x5f56315f; w[4] = 0; w[5] = 0; w[6] = 0; w[7] = 4096;
+                uint4 a = __ldg(bp), b = __ldg(bp + 1);
+                w[8] = sha_bswap(a.x); w[9] = sha_bswap(a.y); w[10] = sha_bswap(a.z); w[11] = sha_bswap(a.w);
+                w[12] = sha_bswap(b.x); w[13] = sha_bswap(b.y); w[14] = sha_bswap(b.z); w[15] = sha_bswap(b.w);
+            } else if (k < 2048) {
+                uint4 a = na, b = nb, c = nc, d = nd;
+                if (k < 2047) { const uint4* p = bp + (4 * k + 2); na = __ldg(p); nb = __ldg(p + 1); nc = __ldg(p + 2); nd = __ldg(p + 3); }
+                w[0] = sha_bswap(a.x); w[1] = sha_bswap(a.y); w[2] = sha_bswap(a.z); w[3] = sha_bswap(a.w);
+                w[4] = sha_bswap(b.x); w[5] = sha_bswap(b.y); w[6] = sha_bswap(b.z); w[7] = sha_bswap(b.w);
+                w[8] = sha_bswap(c.x); w[9] = sha_bswap(c.y); w[10] = sha_bswap(c.z); w[11] = sha_bswap(c.w);
+                w[12] = sha_bswap(d.x); w[13] = sha_bswap(d.y); w[14] = sha_bswap(d.z); w[15] = sha_bswap(d.w);
+            } else if (k == 2048) {
+                uint4 a = __ldg(bp + 8190), b = __ldg(bp + 8191);
+                w[0] = sha_bswap(a.x); w[1] = sha_bswap(a.y); w[2] = sha_bswap(a.z); w[3] = sha_bswap(a.w);
+                w[4] = sha_bswap(b.x); w[5] = sha_bswap(b.y); w[6] = sha_bswap(b.z); w[7] = sha_bswap(b.w);
+                for (int j = 0; j < 8; j++) w[8 + j] = sha_bswap(__ldg(cp + j));
+            } else {
+                for (int j = 0; j < 4; j++) w[j] = sha_bswap(__ldg(cp + 8 + j));
+                w[4] = 0x80000000u;
+                for (int j = 5; j < 15; j++) w[j] = 0;
+                w[15] = 131152u * 8u;
+            }
+            uint32_t* dst = wk + (size_t)(k & 1) * 64 * kWsBlobs + local;
+#pragma unroll
+            for (int t = 0; t < 64; t++) {
+                if (t >= 16) {
+                    uint32_t w15 = w[(t + 1) & 15], w2 = w[(t + 14) & 15];
+                    uint32_t s0 = sha_rotr(w15, 7) ^ sha_rotr(w15, 18) ^ (w15 >> 3);
+                    uint32_t s1 = sha_rotr(w2, 17) ^ sha_rotr(w2, 19) ^ (w2 >> 10);
+                    w[t & 15] = fadd(fadd(w[t & 15], s0, one), fadd(w[(t + 9) & 15], s1, one), one);
+                }
+                dst[t * kWsBlobs] = fadd(w[t & 15], sha_k(t), one);
+            }
+            pair_barrier(bar_id);
+        }
+    } else {
+        uint32_t st[8];
+        sha256_init(st);
+        for (int k = 0; k < 2050; k++) {
+            pair_barrier(bar_id);
+            const uint32_t* src = wk + (size_t)(k & 1) * 64 * kWsBlobs + local;
+            uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll
+            for (int t = 0; t < 64; t++) {
+                uint32_t kw = src[t * kWsBlobs];
+                uint32_t y = fadd(h, kw, one), x = fadd(y, d, one);
+                uint32_t s1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25), ch = (e & f) ^ (~e & g);
+                uint32_t s0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22), mj = (a & b) ^ (a & c) ^ (b & c);
+                uint32_t sc = fadd(s1, ch, one);
+                uint32_t e2 = fadd(x, sc, one), t1 = fadd(y, sc, one), a2 = fadd(t1, fadd(s0, mj, one), one);
+                h = g; g = f; f = e; e = e2; d = c; c = b; b = a; a = a2;
+            }
+            st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+        }
+        if (valid) {
+            Fr raw;
+            for (int j = 0; j < 8; j++) raw.l[j] = st[7 - j];
+            Fr zm = Fr::from_raw(raw);
+            z_mont[blob] = zm;
+            zy[blob].z = zm.to_raw();
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ K1+K3
 // Barycentric evaluation y = p(z) (reference src/kzg_proof.rs:94-133 with batch_inversion :155-201), fused
 // with the canonicity check of Blob::as_polynomial (src/dtypes.rs:48-57).
@@ -195,10 +291,14 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const uint8_t* __res
 }
 
 // ------------------------------------------------------------------------------------------------ K4
-// G1 decompression + subgroup check for commitments and proofs (reference src/kzg_proof.rs:17-25).
+// G1 decompression + subgroup check for commitments and proofs (reference src/kzg_proof.rs:17-25), as two kernels:
+// the decompression (Fp square root) produces the affine points the MSM needs; the subgroup check (two 64-bit scalar
+// multiplications, ~2/3 of the work) only feeds the error flags.  Both run on a low-priority stream beside the hashing.
+// (Measured: deferring the subgroup checks into the latency-bound tail -- transcript, MSM, pairing -- costs more than it
+// saves: the bucket and pairing kernels slow down by more than the checks take.)
 // One thread per point; points [0,n) are commitments, [n,2n) proofs.
-__global__ void __launch_bounds__(128) g1_parse_kernel(const uint8_t* __restrict__ commitments, const uint8_t* __restrict__ proofs, int n,
-                                                       G1Affine* __restrict__ C, G1Affine* __restrict__ P, uint32_t* __restrict__ status) {
+__global__ void __launch_bounds__(128) g1_decompress_kernel(const uint8_t* __restrict__ commitments, const uint8_t* __restrict__ proofs, int n,
+                                                            G1Affine* __restrict__ C, G1Affine* __restrict__ P, uint32_t* __restrict__ status) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 2 * n) return;
     bool is_proof = i >= n;
@@ -210,9 +310,18 @@ __global__ void __launch_bounds__(128) g1_parse_kernel(const uint8_t* __restrict
         b[4 * k] = (uint8_t)v; b[4 * k + 1] = (uint8_t)(v >> 8); b[4 * k + 2] = (uint8_t)(v >> 16); b[4 * k + 3] = (uint8_t)(v >> 24);
     }
     G1Affine pt;
-    bool ok = g1_from_compressed(pt, b, true);
+    bool ok = g1_from_compressed(pt, b, false);
     (is_proof ? P : C)[j] = pt;
     if (!ok) atomicOr(&status[j], is_proof ? kErrProof : kErrCommitment);
+}
+__global__ void __launch_bounds__(128) g1_subgroup_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P, int n,
+                                                          uint32_t* __restrict__ status) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n; i += gridDim.x * blockDim.x) {
+        bool is_proof = i >= n;
+        int j = is_proof ? i - n : i;
+        G1Affine pt = (is_proof ? P : C)[j];
+        if (!g1_in_subgroup(pt)) atomicOr(&status[j], is_proof ? kErrProof : kErrCommitment);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ K5
@@ -659,6 +768,7 @@ __global__ void __launch_bounds__(kFinalThreads) batch_final_kernel(const Partia
     __shared__ uint32_t s_err;
     __shared__ vliw::SharedTables stab;
     int t = threadIdx.x;
+    if (t == 0) result[2] = 0;
     vliw::Tables tab = vliw::load_tables(&stab, t, kFinalThreads);
     if (t == 0) {
         Fr s = Fr::zero(); uint32_t err = 0;
@@ -692,6 +802,7 @@ __global__ void __launch_bounds__(kFinalThreads) single_final_kernel(const G1Aff
     __shared__ G1Affine pts[2];
     __shared__ vliw::SharedTables stab;
     int t = threadIdx.x;
+    if (t == 0) result[2] = 0;
     vliw::Tables tab = vliw::load_tables(&stab, t, kFinalThreads);
     if (status[0]) { if (t == 0) { result[0] = kBadArgs; result[1] = status[0]; } return; }
     G1 yg = coop_fixed_base_mul(zy[0].y, T, sm);

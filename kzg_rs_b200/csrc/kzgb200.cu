@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <new>
 #include "../../include/kzgb200.h"
@@ -45,8 +46,12 @@ struct kzgb200_ctx {
     size_t cur_n = 0;
     // optional per-phase timing (CUDA events on the context stream)
     int transcript_mode = KZGB200_TRANSCRIPT_EXACT;
+    int num_sms = 148;
+    int sha_variant = 0;            // 0 = one thread per blob (default), 1 = warp-specialised producer/consumer kernel
+    int parse_after_sha = 0;        // 1: G1 parsing starts after the first chunk's hash (beside the evaluation) instead of beside it
+    cudaEvent_t ev_sha0 = nullptr;
     cudaStream_t s_aux = nullptr, s_copy = nullptr, s_work[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev_begin = nullptr, ev_parse = nullptr, ev_h2d[64] = {nullptr}, ev_zy[64] = {nullptr};
+    cudaEvent_t ev_begin = nullptr, ev_parse = nullptr, ev_decomp = nullptr, ev_h2d[64] = {nullptr}, ev_zy[64] = {nullptr};
     uint32_t* d_chain_state = nullptr;
     size_t tr_done = 0;             // transcript blocks (exact) / leaf groups (tree) already hashed
     // optional per-phase timing (CUDA event pairs on the stream each phase runs on)
@@ -105,7 +110,8 @@ extern "C" int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_p
     auto fail = [&](int rc) { fprintf(stderr, "kzgb200_create: %s\n", ctx->err); kzgb200_destroy(ctx); return rc; };
     int rc = [&]() -> int {
         CK(cudaSetDevice(device));
-        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        CK(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device));
+        { int lo = 0, hi = 0; CK(cudaDeviceGetStreamPriorityRange(&lo, &hi)); CK(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, hi)); }
         int prio_lo = 0, prio_hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         // the hash chains are the long pole of phase 1: their CTAs go first, G1 parsing fills the rest of the machine
@@ -114,9 +120,14 @@ extern "C" int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_p
         for (auto& w : ctx->s_work) CK(cudaStreamCreateWithPriority(&w, cudaStreamNonBlocking, prio_hi));
         CK(cudaEventCreateWithFlags(&ctx->ev_begin, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ctx->ev_parse, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_decomp, cudaEventDisableTiming));
         for (auto& e : ctx->ev_h2d) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& e : ctx->ev_zy) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CK(cudaMalloc(&ctx->d_chain_state, 32));
+        CK(cudaFuncSetAttribute(challenge_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes));
+        if (const char* v = getenv("KZGB200_SHA_VARIANT")) ctx->sha_variant = atoi(v);
+        if (const char* v = getenv("KZGB200_PARSE_AFTER_SHA")) ctx->parse_after_sha = atoi(v);
+        CK(cudaEventCreateWithFlags(&ctx->ev_sha0, cudaEventDisableTiming));
         CK(cudaMalloc(&ctx->tables, sizeof(DeviceTables)));
         CK(cudaMalloc(&ctx->d_r, sizeof(Fr)));
         CK(cudaMalloc(&ctx->d_partial, sizeof(Partial)));
@@ -146,7 +157,7 @@ extern "C" void kzgb200_destroy(kzgb200_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (cudaStream_t st : {ctx->s_aux, ctx->s_copy, ctx->s_work[0], ctx->s_work[1], ctx->s_work[2], ctx->s_work[3]}) if (st) cudaStreamDestroy(st);
-    for (cudaEvent_t e : {ctx->ev_begin, ctx->ev_parse}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {ctx->ev_begin, ctx->ev_parse, ctx->ev_decomp, ctx->ev_sha0}) if (e) cudaEventDestroy(e);
     for (auto e : ctx->ev_h2d) if (e) cudaEventDestroy(e);
     for (auto e : ctx->ev_zy) if (e) cudaEventDestroy(e);
     for (auto e : ctx->ev_s) if (e) cudaEventDestroy(e);
@@ -221,6 +232,7 @@ static int launch_phase1(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t
         chunk = (n + 7) / 8; if (chunk < kMinChunk) chunk = kMinChunk;
     }
     size_t nchunks = (n + chunk - 1) / chunk;
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_parse, 0));    // a previous call's deferred subgroup checks still write status
     CK(cudaMemsetAsync(ctx->d_status, 0, n * sizeof(uint32_t), ctx->stream));
     CK(cudaEventRecord(ctx->ev_begin, ctx->stream));
     if (with_transcript) { int rc = reserve_transcript(ctx, n); if (rc) return rc; }
@@ -236,8 +248,13 @@ static int launch_phase1(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t
         }
         CK(cudaStreamWaitEvent(sw, ctx->ev_begin, 0));
         phase_begin(ctx, kPhChallenge, sw);
-        challenge_kernel<<<((int)cnt + 63) / 64, 64, 0, sw>>>(d_blobs + lo * kBytesPerBlob, d_c + lo * 48, (int)cnt, ctx->d_z_mont + lo, ctx->d_zy + lo);
+        if (ctx->sha_variant == 1)
+            challenge_ws_kernel<<<((int)cnt + kWsBlobs - 1) / kWsBlobs, kWsThreads, kWsSmemBytes, sw>>>(d_blobs + lo * kBytesPerBlob, d_c + lo * 48, (int)cnt,
+                                                                                                   ctx->d_z_mont + lo, ctx->d_zy + lo, 1u);
+        else
+            challenge_kernel<<<((int)cnt + 63) / 64, 64, 0, sw>>>(d_blobs + lo * kBytesPerBlob, d_c + lo * 48, (int)cnt, ctx->d_z_mont + lo, ctx->d_zy + lo);
         phase_end(ctx, kPhChallenge, sw);
+        if (c == 0) CK(cudaEventRecord(ctx->ev_sha0, sw));
         phase_begin(ctx, kPhEval, sw);
         eval_kernel<<<(int)cnt, kEvalThreads, 0, sw>>>(d_blobs + lo * kBytesPerBlob, (int)cnt, ctx->d_z_mont + lo, ctx->tables, ctx->d_zy + lo,
                                                        ctx->d_status + lo);
@@ -246,15 +263,18 @@ static int launch_phase1(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_zy[c], 0));
         if (c == 0) {   // G1 parsing is queued behind the first hash launch (and on a low-priority stream)
             CK(cudaStreamWaitEvent(ctx->s_aux, ctx->ev_begin, 0));
+            if (ctx->parse_after_sha) CK(cudaStreamWaitEvent(ctx->s_aux, ctx->ev_sha0, 0));
             phase_begin(ctx, kPhParse, ctx->s_aux);
-            g1_parse_kernel<<<(2 * (int)n + 127) / 128, 128, 0, ctx->s_aux>>>(d_c, d_p, (int)n, ctx->d_C, ctx->d_P, ctx->d_status);
+            g1_decompress_kernel<<<(2 * (int)n + 127) / 128, 128, 0, ctx->s_aux>>>(d_c, d_p, (int)n, ctx->d_C, ctx->d_P, ctx->d_status);
+            CK(cudaEventRecord(ctx->ev_decomp, ctx->s_aux));
+            g1_subgroup_kernel<<<(2 * (int)n + 127) / 128, 128, 0, ctx->s_aux>>>(ctx->d_C, ctx->d_P, (int)n, ctx->d_status);
             phase_end(ctx, kPhParse, ctx->s_aux);
             CK(cudaEventRecord(ctx->ev_parse, ctx->s_aux));
         }
         if (with_transcript && n >= 2) { int rc = advance_transcript(ctx, d_c, ctx->d_zy, d_p, n, lo + cnt); if (rc) return rc; }
     }
-    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_parse, 0));
-    CK(cudaGetLastError());
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_decomp, 0));   // the points exist; the subgroup verdicts (ev_parse) are awaited
+    CK(cudaGetLastError());                                     // only where the error flags are consumed
     ctx->cur_c = d_c; ctx->cur_p = d_p; ctx->cur_n = n;
     return KZGB200_OK;
 }
@@ -265,7 +285,7 @@ static int launch_transcript(kzgb200_ctx* ctx, const uint8_t* d_all_c, const ZY*
     return advance_transcript(ctx, d_all_c, d_all_zy, d_all_p, n_total, n_total);
 }
 // K6: digits, counting sort, buckets, window sums, Horner -> partial
-static int launch_lincomb(kzgb200_ctx* ctx, size_t offset, Partial* d_out) {
+static int launch_lincomb(kzgb200_ctx* ctx, size_t offset, Partial* d_out, bool wait_subgroup) {
     int n = (int)ctx->cur_n;
     phase_begin(ctx, kPhLincomb, ctx->stream);
     msm_scalars_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_z_mont, ctx->d_zy, ctx->d_r, (uint64_t)offset, n, ctx->d_digits, ctx->d_ry);
@@ -274,15 +294,16 @@ static int launch_lincomb(kzgb200_ctx* ctx, size_t offset, Partial* d_out) {
     phase_end(ctx, kPhLincomb, ctx->stream);
     phase_begin(ctx, kPhReduce, ctx->stream);
     msm_window_kernel<<<kMsmSets * kWindows, 32, 0, ctx->stream>>>(ctx->d_buckets, ctx->d_windows);
+    if (wait_subgroup) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_parse, 0));    // combine ORs the per-blob error flags
     msm_combine_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_windows, ctx->d_ry, ctx->d_status, n, d_out);
     phase_end(ctx, kPhReduce, ctx->stream);
     CK(cudaGetLastError());
     return KZGB200_OK;
 }
 static int read_result(kzgb200_ctx* ctx, int* ok) {
-    CK(cudaMemcpyAsync(ctx->h_result, ctx->d_result, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_result, ctx->d_result, 12, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (ctx->h_result[0] == kBadArgs) return KZGB200_BAD_ARGS;
+    if (ctx->h_result[0] == kBadArgs || ctx->h_result[2]) return KZGB200_BAD_ARGS;
     *ok = ctx->h_result[0] == kTrue ? 1 : 0;
     return KZGB200_OK;
 }
@@ -300,14 +321,18 @@ static int batch_locked(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t*
     if ((rc = export_zy(ctx, n, d_z_out, d_y_out))) return rc;
     phase_begin(ctx, kPhFinal, ctx->stream);
     if (n == 1) {   // single path (reference src/kzg_proof.rs:482-489)
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_parse, 0));
         single_final_kernel<<<1, kFinalThreads, 0, ctx->stream>>>(ctx->d_C, ctx->d_P, ctx->d_zy, ctx->d_status, ctx->tables, ctx->d_result);
     } else {
         ctx->ph_started[kPhFinal] = false;
-        if ((rc = launch_lincomb(ctx, 0, ctx->d_partial))) return rc;
+        if ((rc = launch_lincomb(ctx, 0, ctx->d_partial, true))) return rc;
         phase_begin(ctx, kPhFinal, ctx->stream);
         batch_final_kernel<<<1, kFinalThreads, 0, ctx->stream>>>(ctx->d_partial, 1, ctx->tables, ctx->d_result);
     }
     phase_end(ctx, kPhFinal, ctx->stream);
+    // the deferred subgroup checks may still be running beside the pairing: their flags are merged last
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_parse, 0));
+    status_or_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_status, (int)n, ctx->d_result + 2);
     CK(cudaGetLastError());
     rc = read_result(ctx, ok);
     if (ctx->profile) {
@@ -434,7 +459,7 @@ extern "C" int kzgb200_shard_lincomb(kzgb200_ctx* ctx, size_t global_offset, uin
     if (!ctx || !d_partial_out || ctx->cur_n == 0) return KZGB200_BAD_ARGS;
     std::lock_guard<std::mutex> g(ctx->lock);
     CK(cudaSetDevice(ctx->device));
-    int rc = launch_lincomb(ctx, global_offset, reinterpret_cast<Partial*>(d_partial_out));
+    int rc = launch_lincomb(ctx, global_offset, reinterpret_cast<Partial*>(d_partial_out), true);
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     return KZGB200_OK;

@@ -79,8 +79,19 @@ class ShardedBatch:
             self.partial = torch.empty(PARTIAL_BYTES, **u8)
             self.partials = torch.empty(world * PARTIAL_BYTES, **u8)
             self.stage = None
-        # kernels launched per batch: parse, challenge, eval, export, 2 transcript, lincomb, pair sums, finish, final
-        self.launches_per_step = 9 + max(1, math.ceil(math.log2(max(n_local, 2))))
+        self.launches_per_step = self.count_launches(n_local, resident=True, tree=True)
+
+    @staticmethod
+    def count_launches(n, resident, tree):
+        """Kernels of libkzgb200.so launched by one batch on one rank (mirrors launch_phase1 / advance_transcript /
+        launch_lincomb in csrc/kzgb200.cu): G1 decompress + subgroup, per chunk challenge + evaluation, export of z/y,
+        transcript (tree: leaf per chunk + root; exact: schedule + chain per chunk), 5 MSM kernels, pairing, flag merge."""
+        if resident:
+            chunks = 1 if (tree or n < 4096) else math.ceil(n / max(1024, math.ceil(n / 8)))
+        else:
+            chunks = math.ceil(n / max(1024, math.ceil(n / 64)))
+        transcript = (chunks + 1) if tree else 2 * chunks
+        return 2 + 2 * chunks + 1 + transcript + 5 + 2
 
     def _check(self, rc):
         if rc == 1:
