@@ -468,6 +468,41 @@ __global__ void __launch_bounds__(32) transcript_chain_kernel(const uint32_t* __
 // per blob.  r then differs from kzg-rs's r (the verdict does not: both are Fiat-Shamir challenges over the
 // same data), so this mode is NOT the default; see DESIGN.md "transcript modes".
 constexpr int kTreeGroup = 64;
+// entry words of the transcript (40 big-endian words per blob), written once in parallel so that the leaf hashes read
+// their blocks with plain vector loads
+__global__ void __launch_bounds__(256) transcript_words_kernel(const uint8_t* __restrict__ commitments, const ZY* __restrict__ zy,
+                                                               const uint8_t* __restrict__ proofs, uint64_t first_entry, uint64_t entry_count,
+                                                               uint32_t* __restrict__ words /* [n][40] */) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= entry_count * 40) return;
+    size_t w = first_entry * 40 + i;
+    words[w] = transcript_word(8 + w, 0, reinterpret_cast<const uint32_t*>(commitments), zy, reinterpret_cast<const uint32_t*>(proofs));
+}
+__global__ void __launch_bounds__(64) transcript_tree_leaf_words_kernel(const uint32_t* __restrict__ words, uint64_t n, uint32_t* __restrict__ digests,
+                                                                        uint64_t first_group, uint64_t group_count) {
+    uint64_t g = first_group + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t ngroups = (n + kTreeGroup - 1) / kTreeGroup;
+    if (g >= ngroups || g >= first_group + group_count) return;
+    uint64_t first = g * kTreeGroup, cnt = n - first < (uint64_t)kTreeGroup ? n - first : (uint64_t)kTreeGroup;
+    size_t nwords = (size_t)cnt * 40, nblk = (nwords * 4 + 9 + 63) / 64;
+    const uint4* src = reinterpret_cast<const uint4*>(words + first * 40);     // 160-byte entries: 16-byte aligned
+    uint32_t st[8], w[16];
+    sha256_init(st);
+    for (size_t blk = 0; blk < nblk; blk++) {
+        if ((blk + 1) * 16 <= nwords) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) { uint4 v = __ldg(src + blk * 4 + j); w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w; }
+        } else {
+            for (int j = 0; j < 16; j++) {
+                size_t wi = blk * 16 + j;
+                w[j] = wi < nwords ? words[first * 40 + wi] : (wi == nwords ? 0x80000000u : 0u);
+            }
+        }
+        if (blk == nblk - 1) { w[14] = (uint32_t)(((uint64_t)nwords * 32) >> 32); w[15] = (uint32_t)((uint64_t)nwords * 32); }
+        sha256_compress(st, w);
+    }
+    for (int j = 0; j < 8; j++) digests[g * 8 + j] = st[j];
+}
 __global__ void __launch_bounds__(64) transcript_tree_leaf_kernel(const uint8_t* __restrict__ commitments, const ZY* __restrict__ zy,
                                                                   const uint8_t* __restrict__ proofs, uint64_t n, uint32_t* __restrict__ digests,
                                                                   uint64_t first_group, uint64_t group_count) {

@@ -190,7 +190,11 @@ static int advance_transcript(kzgb200_ctx* ctx, const uint8_t* d_c, const ZY* d_
         if (ready > ctx->tr_done) {
             phase_begin(ctx, kPhTranscript, ctx->stream);
             size_t cnt = ready - ctx->tr_done;
-            transcript_tree_leaf_kernel<<<(unsigned)((cnt + 63) / 64), 64, 0, ctx->stream>>>(d_c, d_zy, d_p, (uint64_t)n, ctx->d_wk, ctx->tr_done, cnt);
+            // entries of the newly complete groups -> word image -> leaf digests
+            size_t e0 = ctx->tr_done * kTreeGroup, e1 = ready * kTreeGroup < n ? ready * kTreeGroup : n;
+            uint32_t* words = ctx->d_wk + ((n + kTreeGroup - 1) / kTreeGroup) * 8 + 64;
+            transcript_words_kernel<<<(unsigned)(((e1 - e0) * 40 + 255) / 256), 256, 0, ctx->stream>>>(d_c, d_zy, d_p, e0, e1 - e0, words);
+            transcript_tree_leaf_words_kernel<<<(unsigned)((cnt + 63) / 64), 64, 0, ctx->stream>>>(words, (uint64_t)n, ctx->d_wk, ctx->tr_done, cnt);
             ctx->tr_done = ready;
         }
         if (avail >= n) {
@@ -213,7 +217,7 @@ static int advance_transcript(kzgb200_ctx* ctx, const uint8_t* d_c, const ZY* d_
     return KZGB200_OK;
 }
 static int reserve_transcript(kzgb200_ctx* ctx, size_t n) {
-    size_t words = ctx->transcript_mode == KZGB200_TRANSCRIPT_TREE ? ((n + kTreeGroup - 1) / kTreeGroup) * 8 + 64
+    size_t words = ctx->transcript_mode == KZGB200_TRANSCRIPT_TREE ? ((n + kTreeGroup - 1) / kTreeGroup) * 8 + 64 + n * 40 + 64
                                                                    : ((32 + n * 160 + 9 + 63) / 64) * 64;
     if (words > ctx->wk_cap) { CK(regrow(ctx->d_wk, words)); ctx->wk_cap = words; }
     ctx->tr_done = 0;
