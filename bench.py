@@ -80,6 +80,27 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's host threads (and hence its first-touch pinned allocations) to the CPUs local to its GPU, so that
+    the end-to-end leg's host->device copies do not cross the socket interconnect.  Best effort."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        cpus = open("/sys/bus/pci/devices/%s/local_cpulist" % bus).read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        if ids:
+            os.sched_setaffinity(0, ids)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 def run_reference(args, rank, world):
     """The reference's CPU path (oracle port), all host threads, bounded sample per step."""
     if rank != 0:
@@ -175,6 +196,7 @@ def main():
     from kzg_rs_b200 import sharded
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -276,6 +298,7 @@ def main():
                         "evaluate_barycentric": {"achieved_ops_per_s": fr_ops / (phases[2] / 1e3), "peak_ops_per_s": 31.0 * 148 * clk,
                                                  "frac": fr_ops / (phases[2] / 1e3) / (31.0 * 148 * clk), "pipe": "FMA-heavy (IMAD.WIDE.U32.X)"}}
         cfg = workload_config(args, n, world)
+        cfg["host_affinity"] = numa_cpus
         cfg["transcript"] = "tree (opt-in KZGB200_TRANSCRIPT_TREE: same verdict / z / y as kzg-rs, r hashed as a 2-level tree)"
         ex_ms, ex_ph, ex_e2e = res["exact"]
         out = {"metric": "blobs verified/sec (verify_blob_kzg_proof_batch)", "value": value, "unit": "blobs/s", "n_gpus": world,
