@@ -153,6 +153,7 @@ def make_workload_device(lib, ctx, args, n, rank):
         g = torch.Generator(device="cuda").manual_seed(0x4B5A47 + rank)
         blobs = torch.randint(0, 256, (n * BLOB,), dtype=torch.uint8, device="cuda", generator=g)
         blobs.view(n * 4096, 32)[:, 0] &= 0x3f          # every element < 2^254 < q
+        torch.cuda.synchronize()                         # the library works on its own stream
         assert lib.kzgb200_blob_to_kzg_commitment_batch(ctx, blobs.data_ptr(), n, cs.data_ptr()) == 0
         assert lib.kzgb200_compute_blob_kzg_proof_batch(ctx, blobs.data_ptr(), cs.data_ptr(), n, ps.data_ptr()) == 0
         return blobs, cs, ps

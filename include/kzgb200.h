@@ -5,7 +5,9 @@
  * Conventions
  *   - plain pointers and sizes only; the library never frees or retains caller memory past return;
  *   - "host" entry points take host memory (pageable or pinned) and do their own staging;
- *     "_device" entry points take device pointers on the context's GPU (inputs already resident in HBM);
+ *     "_device" entry points take device pointers on the context's GPU (inputs already resident in HBM).  The library
+ *     works on its own CUDA streams: device inputs must be complete before the call (synchronise the stream that
+ *     produced them); every entry point returns only after its outputs are complete;
  *   - return codes map 1:1 onto kzg-rs's KzgError (reference src/enums.rs:6-18):
  *         KZGB200_OK                 Ok(verdict), verdict in *ok (1 = true, 0 = false)
  *         KZGB200_BAD_ARGS           Err(KzgError::BadArgs)            -- unparsable scalar / G1 point

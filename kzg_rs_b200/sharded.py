@@ -103,6 +103,7 @@ class ShardedBatch:
     def verify_device(self, d_blobs, d_cs, d_ps):
         """Inputs resident in HBM.  Returns True / False / None (= Err(BadArgs))."""
         be = self.backend
+        be.sync_collectives()     # the library runs on its own stream: the caller's pending writes to the inputs must be done
         if self.world == 1:
             return be.batch(d_blobs, d_cs, d_ps, self.n, self.z_out, self.y_out)
         be.evaluate(d_blobs, d_cs, d_ps, self.n, self.zy)
