@@ -329,19 +329,6 @@ __global__ void __launch_bounds__(128) g1_subgroup_kernel(const G1Affine* __rest
 //   "RCKZGBATCH___V1_" | u64be 4096 | u64be n | for each i: C_i[48] | z_i LE[32] | y_i LE[32] | pi_i[48]
 // reduced mod q.  The hash is one serial chain over all blobs of the batch (every rank's), so it is a
 // single-thread kernel; the message bytes are produced on the fly from the device-resident pieces.
-__device__ __forceinline__ uint8_t transcript_byte(size_t pos, uint64_t n, const uint8_t* C, const ZY* zy, const uint8_t* P) {
-    if (pos < 32) {
-        const char* dom = "RCKZGBATCH___V1_";
-        if (pos < 16) return (uint8_t)dom[pos];
-        if (pos < 24) return (uint8_t)(4096ull >> (8 * (23 - pos)));
-        return (uint8_t)(n >> (8 * (31 - pos)));
-    }
-    size_t q = (pos - 32) / 160, o = (pos - 32) % 160;
-    if (o < 48) return C[q * 48 + o];
-    if (o < 80) { size_t k = o - 48; return (uint8_t)(zy[q].z.l[k >> 2] >> (8 * (k & 3))); }
-    if (o < 112) { size_t k = o - 80; return (uint8_t)(zy[q].y.l[k >> 2] >> (8 * (k & 3))); }
-    return P[q * 48 + (o - 112)];
-}
 // the same transcript as big-endian 32-bit words (header and entries are word aligned: 8 + 40 n words)
 __device__ __forceinline__ uint32_t transcript_word(size_t w, uint64_t n, const uint32_t* C, const ZY* zy, const uint32_t* P) {
     if (w < 8) {
@@ -499,29 +486,6 @@ __global__ void __launch_bounds__(64) transcript_tree_leaf_words_kernel(const ui
             }
         }
         if (blk == nblk - 1) { w[14] = (uint32_t)(((uint64_t)nwords * 32) >> 32); w[15] = (uint32_t)((uint64_t)nwords * 32); }
-        sha256_compress(st, w);
-    }
-    for (int j = 0; j < 8; j++) digests[g * 8 + j] = st[j];
-}
-__global__ void __launch_bounds__(64) transcript_tree_leaf_kernel(const uint8_t* __restrict__ commitments, const ZY* __restrict__ zy,
-                                                                  const uint8_t* __restrict__ proofs, uint64_t n, uint32_t* __restrict__ digests,
-                                                                  uint64_t first_group, uint64_t group_count) {
-    uint64_t g = first_group + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t ngroups = (n + kTreeGroup - 1) / kTreeGroup;
-    if (g >= ngroups || g >= first_group + group_count) return;
-    uint64_t first = g * kTreeGroup, cnt = n - first < (uint64_t)kTreeGroup ? n - first : (uint64_t)kTreeGroup;
-    size_t len = (size_t)cnt * 160, nblk = (len + 9 + 63) / 64;
-    uint32_t st[8], w[16];
-    sha256_init(st);
-    size_t nwords = len / 4;
-    const uint32_t* Cw = reinterpret_cast<const uint32_t*>(commitments + first * 48);
-    const uint32_t* Pw = reinterpret_cast<const uint32_t*>(proofs + first * 48);
-    for (size_t blk = 0; blk < nblk; blk++) {
-        for (int j = 0; j < 16; j++) {
-            size_t wi = blk * 16 + j;   // entry words start at transcript word 8 of a batch whose first entry is `first`
-            w[j] = wi < nwords ? transcript_word(8 + wi, 0, Cw, zy + first, Pw) : (wi == nwords ? 0x80000000u : 0u);
-        }
-        if (blk == nblk - 1) { w[14] = (uint32_t)(((uint64_t)len * 8) >> 32); w[15] = (uint32_t)((uint64_t)len * 8); }
         sha256_compress(st, w);
     }
     for (int j = 0; j < 8; j++) digests[g * 8 + j] = st[j];
@@ -841,8 +805,21 @@ __global__ void __launch_bounds__(kFinalThreads) single_final_kernel(const G1Aff
     vliw::Tables tab = vliw::load_tables(&stab, t, kFinalThreads);
     if (status[0]) { if (t == 0) { result[0] = kBadArgs; result[1] = status[0]; } return; }
     G1 yg = coop_fixed_base_mul(zy[0].y, T, sm);
+    __shared__ CoopPoint ladder;
+    if (t < 32) {   // [z]pi: the 255-step double-and-add chain on the warp-cooperative point operations
+        if (t == 0) { ladder.v[0] = Fp::one(); ladder.v[1] = Fp::one(); ladder.v[2] = Fp::zero(); }
+        __syncwarp();
+        G1 pj = G1::from_affine(P[0]);
+        Fr z = zy[0].z;
+        for (int bit = 254; bit >= 0; bit--) {
+            coop_dbl(&ladder, t);
+            if ((z.l[bit >> 5] >> (bit & 31)) & 1) coop_add(&ladder, pj, t);
+        }
+    }
+    __syncthreads();
     if (t == 0) {
-        G1 acc = yg.neg().add_mixed(C[0]).add(scalar_mul_affine(P[0], zy[0].z.l, 255));
+        G1 zpi = {ladder.v[0], ladder.v[1], ladder.v[2]};
+        G1 acc = yg.neg().add_mixed(C[0]).add(zpi);
         Fp zi = vliw::fp_inv_bingcd(acc.z), zi2 = zi.sqr();
         pts[0] = acc.is_identity() ? G1Affine{Fp::zero(), Fp::zero(), 1} : G1Affine{acc.x * zi2, acc.y * zi2 * zi, 0};
         G1Affine np = P[0];

@@ -48,11 +48,11 @@ struct kzgb200_ctx {
     int transcript_mode = KZGB200_TRANSCRIPT_EXACT;
     int num_sms = 148;
     int sha_variant = 0;            // 0 = one thread per blob (default), 1 = warp-specialised producer/consumer kernel
-    int parse_after_sha = 0;        // 1: G1 parsing starts after the first chunk's hash (beside the evaluation) instead of beside it
     cudaEvent_t ev_sha0 = nullptr;
     cudaStream_t s_aux = nullptr, s_copy = nullptr, s_work[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_begin = nullptr, ev_parse = nullptr, ev_decomp = nullptr, ev_h2d[64] = {nullptr}, ev_zy[64] = {nullptr};
     uint32_t* d_chain_state = nullptr;
+    uint8_t* d_scratch = nullptr;   // 256 bytes for small exports
     size_t tr_done = 0;             // transcript blocks (exact) / leaf groups (tree) already hashed
     // optional per-phase timing (CUDA event pairs on the stream each phase runs on)
     bool profile = false;
@@ -124,9 +124,9 @@ extern "C" int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_p
         for (auto& e : ctx->ev_h2d) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& e : ctx->ev_zy) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CK(cudaMalloc(&ctx->d_chain_state, 32));
+        CK(cudaMalloc(&ctx->d_scratch, 256));
         CK(cudaFuncSetAttribute(challenge_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes));
         if (const char* v = getenv("KZGB200_SHA_VARIANT")) ctx->sha_variant = atoi(v);
-        if (const char* v = getenv("KZGB200_PARSE_AFTER_SHA")) ctx->parse_after_sha = atoi(v);
         CK(cudaEventCreateWithFlags(&ctx->ev_sha0, cudaEventDisableTiming));
         CK(cudaMalloc(&ctx->tables, sizeof(DeviceTables)));
         CK(cudaMalloc(&ctx->d_r, sizeof(Fr)));
@@ -163,6 +163,7 @@ extern "C" void kzgb200_destroy(kzgb200_ctx* ctx) {
     for (auto e : ctx->ev_s) if (e) cudaEventDestroy(e);
     for (auto e : ctx->ev_e) if (e) cudaEventDestroy(e);
     if (ctx->d_chain_state) cudaFree(ctx->d_chain_state);
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     void* ptrs[] = {ctx->tables, ctx->d_blobs, ctx->d_c, ctx->d_p, ctx->d_z_mont, ctx->d_zy, ctx->d_C, ctx->d_P, ctx->d_status,
                     ctx->d_ry, ctx->d_r, ctx->d_partial, ctx->d_result, ctx->d_zout, ctx->d_yout, ctx->d_many, ctx->d_wk,
                     ctx->d_digits, ctx->d_order, ctx->d_start, ctx->d_buckets, ctx->d_windows, ctx->d_lag_table, ctx->d_scalars};
@@ -267,7 +268,6 @@ static int launch_phase1(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_zy[c], 0));
         if (c == 0) {   // G1 parsing is queued behind the first hash launch (and on a low-priority stream)
             CK(cudaStreamWaitEvent(ctx->s_aux, ctx->ev_begin, 0));
-            if (ctx->parse_after_sha) CK(cudaStreamWaitEvent(ctx->s_aux, ctx->ev_sha0, 0));
             phase_begin(ctx, kPhParse, ctx->s_aux);
             g1_decompress_kernel<<<(2 * (int)n + 127) / 128, 128, 0, ctx->s_aux>>>(d_c, d_p, (int)n, ctx->d_C, ctx->d_P, ctx->d_status);
             CK(cudaEventRecord(ctx->ev_decomp, ctx->s_aux));
@@ -512,15 +512,14 @@ extern "C" int kzgb200_last_r(kzgb200_ctx* ctx, uint8_t* r_out32) {
     if (!ctx || !r_out32) return KZGB200_BAD_ARGS;
     std::lock_guard<std::mutex> g(ctx->lock);
     CK(cudaSetDevice(ctx->device));
-    ZY* tmp = nullptr;
-    CK(cudaMalloc(&tmp, sizeof(ZY)));
+    // scratch: the first ZY slot of the (idle) z/y export buffers
+    ZY* tmp = reinterpret_cast<ZY*>(ctx->d_scratch);
+    uint8_t* d_out = ctx->d_scratch + sizeof(ZY);
     r_to_raw_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_r, tmp);
-    uint8_t* d_out = nullptr;
-    CK(cudaMalloc(&d_out, 32));
     export_scalars_kernel<<<1, 1, 0, ctx->stream>>>(tmp, 1, d_out, nullptr);
+    CK(cudaGetLastError());
     CK(cudaMemcpyAsync(r_out32, d_out, 32, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(tmp); cudaFree(d_out);
     return KZGB200_OK;
 }
 // raw per-rank partial of the last single-GPU batch (Partial struct: Jacobian A, B in Montgomery limbs, sum r_i y_i, flags)
