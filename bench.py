@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--blobs", type=int, default=16384, help="blobs per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=2048, help="blobs in the CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=8192, help="blobs in the CPU-baseline sample (~19 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lowdegree-blobs", action="store_true",
                     help="blobs = evaluations of random degree<8 polynomials (cheap generator) instead of uniformly random "

@@ -280,3 +280,69 @@ def test_chunked_paths_keep_r_and_sums_bit_exact(K, settings, oracle, n):
         assert K.KzgProof.verify_blob_kzg_proof_batch_raw(hb, n, hc, n, bytes(bad), n, settings) is False
     finally:
         api.set_transcript_mode(settings, api.TRANSCRIPT_EXACT)
+
+
+def test_cpp_mirror_runs_reference_vectors(K, settings, vectors, tmp_path):
+    """The C++ mirror of the reference interface (include/kzg_rs.hpp) on the GPU: every well-formed verify_kzg_proof
+    vector and every verify_blob_kzg_proof vector through kzg_rs::KzgProof, tri-state results as in kzg_proof.rs:604-680."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "run_vectors.cpp"
+    src.write_text(r'''
+#include "kzg_rs.hpp"
+#include <cstdio>
+#include <vector>
+using namespace kzg_rs;
+static int tri(const Result<bool>& r) { return r.is_err() ? 2 : (r.unwrap() ? 1 : 0); }
+int main(int argc, char** argv) {
+    auto s = KzgSettings::load_trusted_setup_file(argv[1]);
+    if (s.is_err()) return 3;
+    const KzgSettings& ks = s.unwrap();
+    std::vector<uint8_t> rec(160);
+    uint32_t n = 0;
+    if (fread(&n, 4, 1, stdin) != 1) return 4;
+    for (uint32_t i = 0; i < n; i++) {
+        if (fread(rec.data(), 1, 160, stdin) != 160) return 4;
+        auto c = Bytes48::from_slice(rec.data(), 48).unwrap(); auto z = Bytes32::from_slice(rec.data() + 48, 32).unwrap();
+        auto y = Bytes32::from_slice(rec.data() + 80, 32).unwrap(); auto p = Bytes48::from_slice(rec.data() + 112, 48).unwrap();
+        putchar('0' + tri(KzgProof::verify_kzg_proof(c, z, y, p, ks)));
+    }
+    putchar('\n');
+    if (fread(&n, 4, 1, stdin) != 1) return 4;
+    std::vector<uint8_t> blob(BYTES_PER_BLOB + 96);
+    for (uint32_t i = 0; i < n; i++) {
+        if (fread(blob.data(), 1, blob.size(), stdin) != blob.size()) return 4;
+        auto b = Blob::from_slice(blob.data(), BYTES_PER_BLOB).unwrap();
+        auto c = Bytes48::from_slice(blob.data() + BYTES_PER_BLOB, 48).unwrap(); auto p = Bytes48::from_slice(blob.data() + BYTES_PER_BLOB + 48, 48).unwrap();
+        putchar('0' + tri(KzgProof::verify_blob_kzg_proof(b, c, p, ks)));
+        std::vector<Blob> bs{b}; std::vector<Bytes48> cs{c}, ps{p};
+        putchar('0' + tri(KzgProof::verify_blob_kzg_proof_batch(bs, cs, ps, ks)));    // kzg_proof.rs:706-737 shape
+    }
+    putchar('\n');
+    std::vector<Blob> b2; std::vector<Bytes48> c2(1), p2;
+    putchar('0' + tri(KzgProof::verify_blob_kzg_proof_batch(b2, c2, p2, ks)));          // empty -> Ok(true)
+    b2.resize(2); c2.resize(1); p2.resize(2);
+    auto r = KzgProof::verify_blob_kzg_proof_batch(b2, c2, p2, ks);                      // length mismatch
+    putchar(r.is_err() && r.unwrap_err().kind == KzgError::InvalidBytesLength ? 'L' : '?');
+    putchar('\n');
+    return 0;
+}
+''')
+    exe = tmp_path / "run_vectors"
+    lib_dir = os.path.join(root, "kzg_rs_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                           "-L", lib_dir, "-lkzgb200", "-Wl,-rpath," + lib_dir])
+    import struct
+    k_cases = [c for c in vectors["verify_kzg_proof"] if [len(unhex(c[k])) for k in ("commitment", "z", "y", "proof")] == [48, 32, 32, 48]]
+    b_cases = [c for c in vectors["verify_blob_kzg_proof"]
+               if len(vectors.blobs[c["blob"]]) == 131072 and len(unhex(c["commitment"])) == 48 and len(unhex(c["proof"])) == 48]
+    payload = struct.pack("<I", len(k_cases)) + b"".join(unhex(c["commitment"]) + unhex(c["z"]) + unhex(c["y"]) + unhex(c["proof"]) for c in k_cases)
+    payload += struct.pack("<I", len(b_cases)) + b"".join(vectors.blobs[c["blob"]] + unhex(c["commitment"]) + unhex(c["proof"]) for c in b_cases)
+    out = subprocess.run([str(exe), os.path.join(lib_dir, "data", "mainnet_setup.bin")], input=payload, capture_output=True)
+    assert out.returncode == 0, out.stderr.decode()
+    l1, l2, l3 = out.stdout.decode().split("\n")[:3]
+    code = {True: "1", False: "0", None: "2"}
+    assert l1 == "".join(code[c["output"]] for c in k_cases)
+    assert l2 == "".join(code[c["output"]] * 2 for c in b_cases)
+    assert l3 == "1L"
