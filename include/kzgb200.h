@@ -138,6 +138,8 @@ int kzgb200_compute_blob_kzg_proof_batch(kzgb200_ctx* ctx, const uint8_t* d_blob
  * {parse G1, challenge, evaluate, transcript r, lincomb terms, reduce, final pairing} of the last call. */
 int kzgb200_set_profiling(kzgb200_ctx* ctx, int on);
 int kzgb200_get_phase_ms(kzgb200_ctx* ctx, float* out7);
+/* profiling aid: SM clock stamps of the sections of the last single-GPU final pairing kernel */
+int kzgb200_debug_final_ticks(kzgb200_ctx* ctx, long long* out14);
 /* the cudaStream_t all work of this context is issued on (for CUDA-event timing by the caller) */
 void* kzgb200_stream(kzgb200_ctx* ctx);
 

@@ -741,6 +741,12 @@ __global__ void __launch_bounds__(256) msm_combine_kernel(const G1* __restrict__
 
 // ------------------------------------------------------------------------------------------------ K7
 constexpr int kFinalThreads = 64;
+// dynamic shared memory of the final kernels: engine register file, program tables, G1 tree scratch (> 48 KB: opt-in)
+struct FinalSmem {
+    Fp regs[vliw::kTotalRegs];
+    G1 sm[kFinalThreads];
+    vliw::SharedTables stab;
+};
 // [s]G from the fixed-base table: thread t < 64 takes the t-th 4-bit digit of s, then a shared-memory tree sum.
 // All kFinalThreads threads call it; the result is returned to every thread.
 __device__ __noinline__ G1 coop_fixed_base_mul(const Fr& s_raw, const DeviceTables* T, G1* sm /* kFinalThreads */) {
@@ -759,16 +765,18 @@ __device__ __noinline__ G1 coop_fixed_base_mul(const Fr& s_raw, const DeviceTabl
 // one CTA of kFinalThreads threads: the G1 prelude on a few threads, the pairing on the cooperative engine.
 // result: 0 = false, 1 = true, 2 = BadArgs (some rank flagged an unparsable input)
 __global__ void __launch_bounds__(kFinalThreads) batch_final_kernel(const Partial* __restrict__ parts, int nparts, const DeviceTables* __restrict__ T,
-                                                                    uint32_t* __restrict__ result) {
-    __shared__ Fp regs[vliw::kTotalRegs];
-    __shared__ G1 sm[kFinalThreads];
+                                                                    uint32_t* __restrict__ result, long long* __restrict__ ticks) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    FinalSmem& S = *reinterpret_cast<FinalSmem*>(dyn_smem);
+    Fp* regs = S.regs;
+    G1* sm = S.sm;
     __shared__ G1Affine pts[2];
     __shared__ Fr s_sum;
     __shared__ uint32_t s_err;
-    __shared__ vliw::SharedTables stab;
     int t = threadIdx.x;
     if (t == 0) result[2] = 0;
-    vliw::Tables tab = vliw::load_tables(&stab, t, kFinalThreads);
+    if (ticks && t == 0) { ticks[0] = clock64(); for (int i = 8; i < 14; i++) ticks[i] = 0; }
+    vliw::Tables tab = vliw::load_tables(&S.stab, t, kFinalThreads);
     if (t == 0) {
         Fr s = Fr::zero(); uint32_t err = 0;
         for (int k = 0; k < nparts; k++) { s = s.add_inl(parts[k].ry); err |= parts[k].err; }
@@ -787,8 +795,9 @@ __global__ void __launch_bounds__(kFinalThreads) batch_final_kernel(const Partia
         pts[t] = a;
     }
     __syncthreads();
-    vliw::Lanes L{t, kFinalThreads, tab};
+    vliw::Lanes L{t, kFinalThreads, tab, ticks};
     bool ok = vliw::coop_pairing_product_is_one(regs, pts[1], T->pairing.g2_gen, pts[0], T->pairing.tau_g2, L);
+    L.tick(5);
     if (t == 0) { result[0] = ok ? kTrue : kFalse; result[1] = 0; }
 }
 // Single-blob path (reference src/kzg_proof.rs:446-470 -> verify_kzg_proof_impl :203-223) after z, y and the
@@ -796,13 +805,14 @@ __global__ void __launch_bounds__(kFinalThreads) batch_final_kernel(const Partia
 __global__ void __launch_bounds__(kFinalThreads) single_final_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P, const ZY* __restrict__ zy,
                                                                      const uint32_t* __restrict__ status, const DeviceTables* __restrict__ T,
                                                                      uint32_t* __restrict__ result) {
-    __shared__ Fp regs[vliw::kTotalRegs];
-    __shared__ G1 sm[kFinalThreads];
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    FinalSmem& S = *reinterpret_cast<FinalSmem*>(dyn_smem);
+    Fp* regs = S.regs;
+    G1* sm = S.sm;
     __shared__ G1Affine pts[2];
-    __shared__ vliw::SharedTables stab;
     int t = threadIdx.x;
     if (t == 0) result[2] = 0;
-    vliw::Tables tab = vliw::load_tables(&stab, t, kFinalThreads);
+    vliw::Tables tab = vliw::load_tables(&S.stab, t, kFinalThreads);
     if (status[0]) { if (t == 0) { result[0] = kBadArgs; result[1] = status[0]; } return; }
     G1 yg = coop_fixed_base_mul(zy[0].y, T, sm);
     __shared__ CoopPoint ladder;

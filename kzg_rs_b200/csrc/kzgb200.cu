@@ -124,7 +124,9 @@ extern "C" int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_p
         for (auto& e : ctx->ev_h2d) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& e : ctx->ev_zy) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CK(cudaMalloc(&ctx->d_chain_state, 32));
-        CK(cudaMalloc(&ctx->d_scratch, 256));
+        CK(cudaMalloc(&ctx->d_scratch, 512));
+        CK(cudaFuncSetAttribute(batch_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinalSmem)));
+        CK(cudaFuncSetAttribute(single_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinalSmem)));
         CK(cudaFuncSetAttribute(challenge_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes));
         if (const char* v = getenv("KZGB200_SHA_VARIANT")) ctx->sha_variant = atoi(v);
         CK(cudaEventCreateWithFlags(&ctx->ev_sha0, cudaEventDisableTiming));
@@ -326,12 +328,12 @@ static int batch_locked(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t*
     phase_begin(ctx, kPhFinal, ctx->stream);
     if (n == 1) {   // single path (reference src/kzg_proof.rs:482-489)
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_parse, 0));
-        single_final_kernel<<<1, kFinalThreads, 0, ctx->stream>>>(ctx->d_C, ctx->d_P, ctx->d_zy, ctx->d_status, ctx->tables, ctx->d_result);
+        single_final_kernel<<<1, kFinalThreads, sizeof(FinalSmem), ctx->stream>>>(ctx->d_C, ctx->d_P, ctx->d_zy, ctx->d_status, ctx->tables, ctx->d_result);
     } else {
         ctx->ph_started[kPhFinal] = false;
         if ((rc = launch_lincomb(ctx, 0, ctx->d_partial, true))) return rc;
         phase_begin(ctx, kPhFinal, ctx->stream);
-        batch_final_kernel<<<1, kFinalThreads, 0, ctx->stream>>>(ctx->d_partial, 1, ctx->tables, ctx->d_result);
+        batch_final_kernel<<<1, kFinalThreads, sizeof(FinalSmem), ctx->stream>>>(ctx->d_partial, 1, ctx->tables, ctx->d_result, reinterpret_cast<long long*>(ctx->d_scratch + 128));
     }
     phase_end(ctx, kPhFinal, ctx->stream);
     // the deferred subgroup checks may still be running beside the pairing: their flags are merged last
@@ -472,7 +474,7 @@ extern "C" int kzgb200_shard_finalize(kzgb200_ctx* ctx, const uint8_t* d_partial
     if (!ctx || !d_partials || !ok || n_ranks == 0) return KZGB200_BAD_ARGS;
     std::lock_guard<std::mutex> g(ctx->lock);
     CK(cudaSetDevice(ctx->device));
-    batch_final_kernel<<<1, kFinalThreads, 0, ctx->stream>>>(reinterpret_cast<const Partial*>(d_partials), (int)n_ranks, ctx->tables, ctx->d_result);
+    batch_final_kernel<<<1, kFinalThreads, sizeof(FinalSmem), ctx->stream>>>(reinterpret_cast<const Partial*>(d_partials), (int)n_ranks, ctx->tables, ctx->d_result, nullptr);
     CK(cudaGetLastError());
     return read_result(ctx, ok);
 }
@@ -605,6 +607,14 @@ extern "C" int kzgb200_compute_blob_kzg_proof_batch(kzgb200_ctx* ctx, const uint
     std::lock_guard<std::mutex> g(ctx->lock);
     CK(cudaSetDevice(ctx->device));
     return commit_or_prove(ctx, d_blobs, d_commitments, n, d_proofs_out, 1);
+}
+// clock64() stamps of the last single-GPU batch_final_kernel: start, prelude end, Miller loop end, easy part end, hard part end, done
+extern "C" int kzgb200_debug_final_ticks(kzgb200_ctx* ctx, long long* out14) {
+    if (!ctx || !out14) return KZGB200_BAD_ARGS;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(out14, ctx->d_scratch + 128, 112, cudaMemcpyDeviceToHost));
+    return KZGB200_OK;
 }
 // the stream every call of this context is issued on (cudaStream_t), for event timing by the caller
 extern "C" void* kzgb200_stream(kzgb200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }

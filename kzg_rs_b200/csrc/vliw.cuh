@@ -22,6 +22,12 @@ struct Tables {
 struct Lanes {
     int tid, n;   // this thread's lane and the number of cooperating threads (host: 0, 1)
     Tables tab;
+    long long* ticks = nullptr;   // optional: per-section clock64() stamps (profiling aid)
+    KZG_HD void tick(int i) const {
+#ifdef __CUDA_ARCH__
+        if (ticks && tid == 0) ticks[i] = clock64();
+#endif
+    }
     KZG_HD void sync() const {
 #ifdef __CUDA_ARCH__
         __syncthreads();
@@ -65,27 +71,46 @@ KZG_HD void exec_mul(Fp* regs, const uint16_t* ins) {
         regs[ins[0]] = Fp::mul_dual_inl(a, b, c, d);
     }
 }
-// dst = sum of (+/-)(1|2) * src over up to 24 terms.  Everything is accumulated as a NON-NEGATIVE integer
-// (a negative term contributes p - v), 12 limbs plus a small carry count, and reduced once at the end:
-// quotient estimate from the top words, one multiply-subtract, at most three conditional subtractions.
+// dst = sum of (+/-)(1|2) * src over up to 24 terms.  The lanes of a warp execute different LIN instructions, so the
+// per-term code is branch-free: the term is shifted left by its "double" bit (funnel shifts), XOR-ed with its sign mask and
+// added with the sign as carry-in to ONE signed 14-limb accumulator (two's complement subtraction through the adder).
+// The signed total S in (-48p, 48p) is then made positive (D = S + 64p) and reduced once: quotient estimate from the top
+// words, one multiply-subtract, the candidates D - p, D - 2p, D - 3p side by side.
 KZG_HD void exec_lin(Fp* regs, const uint32_t* ins, const uint16_t* terms) {
     uint32_t acc[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) acc[i] = 0;
-    uint32_t top = 0;                           // total = top * 2^384 + acc  <  48 p  <  2^387
-    Fp p = Fp::modulus();
+    uint32_t hi = 0;                            // signed overflow word(s): total = (int32)hi * 2^384 + acc
     const uint16_t* t = terms + ins[1];
     for (uint32_t k = 0; k < ins[2]; k++) {
         uint16_t e = t[k];
-        Fp v = regs[e & 0x3fff];
-        if (e & 0x4000) sub_n<12>(v.l, p.l, v.l);            // p - v  (v <= p, no borrow)
-        top += add_n<12>(acc, acc, v.l);
-        if (e & 0x8000) top += add_n<12>(acc, acc, v.l);     // doubled term
+        const Fp& v = regs[e & 0x3fff];
+        uint32_t sh = (e >> 15) & 1u, m = (e & 0x4000) ? 0xffffffffu : 0u;
+        uint32_t wv[12], prev = 0;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            uint32_t cur = v.l[i];
+#ifdef __CUDA_ARCH__
+            wv[i] = __funnelshift_l(prev, cur, sh);      // one SHF: (cur << sh) | (prev >> (32 - sh)), sh in {0, 1}
+#else
+            wv[i] = (cur << sh) | ((prev >> 31) & sh);
+#endif
+            prev = cur;
+        }
+        uint32_t c = add_signed_12(acc, wv, m);
+        hi += (uint32_t)c + (((prev >> 31) & sh) ^ m);
     }
-    // q <= total / p, within 3 of it: top 64 bits of total over (top word of p) + 1
+    Fp p = Fp::modulus();
+    // D = S + 64p  in (16p, 112p)
+    uint32_t p64[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) p64[i] = (p.l[i] << 6) | (i ? (p.l[i - 1] >> 26) : 0u);
+    uint32_t top = hi + (p.l[11] >> 26) + add_n<12>(acc, acc, p64);
+    // quotient estimate q <= D / p (at most 3 short) from the top 64 bits of D and the top word of p, in float
+    // (D < 112 p, so q < 128: the 2^-23 relative error of the float product is far below one unit; minus one for safety)
     uint64_t t64 = ((uint64_t)top << 32) | acc[11];
-    uint32_t q = (uint32_t)(t64 / ((uint64_t)p.l[11] + 1));
-    // total -= q * p   (q < 2^9)
+    float qf = (float)t64 * (1.0f / ((float)p.l[11] + 2.0f));
+    uint32_t q = qf >= 1.0f ? (uint32_t)qf - 1u : 0u;
     uint64_t carry = 0, bw = 0;
 #pragma unroll
     for (int i = 0; i < 12; i++) {
@@ -94,17 +119,15 @@ KZG_HD void exec_lin(Fp* regs, const uint32_t* ins, const uint16_t* terms) {
         acc[i] = (uint32_t)d; bw = (d >> 32) & 1; carry >>= 32;
     }
     top -= (uint32_t)carry + (uint32_t)bw;
-    // now 0 <= total < 4p
+    // now 0 <= D < 4p: the three candidates D - p, D - 2p, D - 3p are formed side by side (independent borrow chains)
+    uint32_t p2[12], p3[12], r1[12], r2[12], r3[12];
+    add_n<12>(p2, p.l, p.l);
+    add_n<12>(p3, p2, p.l);
+    uint32_t b1 = sub_n<12>(r1, acc, p.l), b2 = sub_n<12>(r2, acc, p2), b3 = sub_n<12>(r3, acc, p3);
+    // top is 0 or 1 here (D < 4p < 2^384 * 0.41, so top == 0 in fact); candidate k is valid iff D >= k p
+    bool ok1 = top || !b1, ok2 = top || !b2, ok3 = top || !b3;
 #pragma unroll
-    for (int r = 0; r < 3; r++) {
-        uint32_t tmp[12];
-        uint32_t borrow = sub_n<12>(tmp, acc, p.l);
-        if (top || !borrow) {
-#pragma unroll
-            for (int i = 0; i < 12; i++) acc[i] = tmp[i];
-            top -= borrow;
-        }
-    }
+    for (int i = 0; i < 12; i++) acc[i] = ok3 ? r3[i] : (ok2 ? r2[i] : (ok1 ? r1[i] : acc[i]));
     Fp r;
 #pragma unroll
     for (int i = 0; i < 12; i++) r.l[i] = acc[i];
@@ -115,9 +138,22 @@ KZG_HD void run(int prog, Fp* regs, const Lanes& L) {
     const Program p = L.tab.prog[prog];
     for (int lv = p.first_level; lv < p.first_level + p.n_levels; lv++) {
         const Level lev = L.tab.level[lv];
+#ifdef __CUDA_ARCH__
+        long long c0 = L.ticks ? clock64() : 0;
+#endif
         if (lev.kind == 1) { for (int k = L.tid; k < lev.count; k += L.n) exec_mul(regs, L.tab.mul[lev.first + k]); }
         else { for (int k = L.tid; k < lev.count; k += L.n) exec_lin(regs, L.tab.lin[lev.first + k], L.tab.term); }
+#ifdef __CUDA_ARCH__
+        long long c1 = L.ticks ? clock64() : 0;
+#endif
         L.sync();
+#ifdef __CUDA_ARCH__
+        if (L.ticks && L.tid == 0) {   // profiling aid: body / barrier-wait cycles of lane 0 per level kind
+            long long c2 = clock64();
+            int b = lev.kind == 1 ? 10 : 8;
+            L.ticks[b] += c1 - c0; L.ticks[b + 1] += c2 - c1; L.ticks[b == 10 ? 13 : 12] += 1;
+        }
+#endif
     }
 }
 // regs[dst .. dst+count) = regs[src ..)
@@ -177,12 +213,26 @@ KZG_HD void load_lines(Fp* regs, const LineCoeffs* c1, const LineCoeffs* c2, int
     L.sync();
 }
 // F <- F^|x| conjugated (x < 0), base = save slot `base` (F is overwritten; G is used as the multiplier slot)
+// k squarings of F, F in the cyclotomic subgroup (everything after the easy part of the final exponentiation):
+// Granger-Scott squarings (18 single products per squaring instead of 24 dual ones).  Measured: fusing consecutive
+// squarings into one program (output level + next operand level) makes the sums longer and the chain SLOWER --
+// a level costs time proportional to its longest sum.
+KZG_HD void sqr_times(Fp* regs, int k, const Lanes& L) {
+    for (; k > 0; k--) run(kProg_cyc_sqr1, regs, L);
+}
 KZG_HD void exp_by_x_slot(Fp* regs, int base, const Lanes& L) {
     copy_regs(regs, kRegF, base, 12, L);
+    int pending = 0;
     for (int bit = 62; bit >= 0; bit--) {
-        run(kProg_f12_sqr, regs, L);
-        if ((KZG_BLS_X_ABS >> bit) & 1) { copy_regs(regs, kRegG, base, 12, L); run(kProg_f12_mul, regs, L); }
+        pending++;
+        if ((KZG_BLS_X_ABS >> bit) & 1) {
+            sqr_times(regs, pending, L);
+            pending = 0;
+            copy_regs(regs, kRegG, base, 12, L);
+            run(kProg_f12_mul, regs, L);
+        }
     }
+    sqr_times(regs, pending, L);
     run(kProg_conj, regs, L);
 }
 // e(P1, Q1) e(P2, Q2) == 1 with the lines of Q1, Q2 precomputed (c1, c2).  All cooperating threads call it with
@@ -205,6 +255,7 @@ KZG_HD bool coop_pairing_product_is_one(Fp* regs, const G1Affine& P1, const Line
         regs[kRegF] = Fp::one();
     }
     L.sync();
+    L.tick(1);
     // Miller loop
     int k = 0;
     for (int bit = 62; bit >= 0; bit--) {
@@ -218,6 +269,7 @@ KZG_HD bool coop_pairing_product_is_one(Fp* regs, const G1Affine& P1, const Line
         }
     }
     run(kProg_conj, regs, L);
+    L.tick(2);
     // final exponentiation, f^(3(p^12-1)/r):  easy part
     const int S0 = kSave0, S1 = kSave0 + 12, S2 = kSave0 + 24, S3 = kSave0 + 36, S4 = kSave0 + 48;
     copy_regs(regs, S0, kRegF, 12, L);                       // S0 = f0
@@ -232,6 +284,7 @@ KZG_HD bool coop_pairing_product_is_one(Fp* regs, const G1Affine& P1, const Line
     run(kProg_frob2, regs, L);                               // G = F^(p^2)
     run(kProg_f12_mul, regs, L);                             // F = f = f0^((p^6-1)(p^2+1))
     copy_regs(regs, S0, kRegF, 12, L);                       // S0 = f
+    L.tick(3);
     // hard part: (x-1)^2 (x+p)(x^2+p^2-1) + 3
     exp_by_x_slot(regs, S0, L);                              // F = f^x
     copy_regs(regs, kRegG, S0, 12, L); run(kProg_conj_g, regs, L); run(kProg_f12_mul, regs, L);     // f^(x-1)
@@ -255,6 +308,7 @@ KZG_HD bool coop_pairing_product_is_one(Fp* regs, const G1Affine& P1, const Line
     copy_regs(regs, kRegF, S0, 12, L); run(kProg_f12_sqr, regs, L);
     copy_regs(regs, kRegG, S0, 12, L); run(kProg_f12_mul, regs, L);                                  // f^3
     copy_regs(regs, kRegG, S4, 12, L); run(kProg_f12_mul, regs, L);                                  // c f^3
+    L.tick(4);
     // == 1 ?
     bool ok = regs[kRegF] == Fp::one();
     for (int i = 1; i < 12; i++) ok = ok && regs[kRegF + i].is_zero();

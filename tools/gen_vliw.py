@@ -254,6 +254,77 @@ def prog_f12_sqr():        # F <- F^2
     return B
 
 
+def prog_f12_sqr_k(k):     # F <- F^(2^k): k squarings in one program; the lazy additions fuse each output level with the next
+    def mk():              # squaring's operand level, so a squaring costs 2 levels instead of 3
+        B = Builder("f12_sqr%d" % k, N_IN)
+        x = f12_in(B, 0)
+        for _ in range(k):
+            x = x.sqr(B)
+        out12(B, x, 0)
+        return B
+    return mk
+
+
+def prog_miller_step():    # F <- F^2 * line1(P1) * line2(P2)   (one doubling step of the Miller loop, both pairs live)
+    B = Builder("miller_step", N_IN)
+    f2 = f12_in(B, 0).sqr(B)
+    L = sparse_mul(line_in(B, 0), line_in(B, 1), B)
+    out12(B, f2.mul(L, B), 0)
+    return B
+
+
+def prog_miller_add():     # F <- F * line1(P1) * line2(P2)     (an addition step)
+    B = Builder("miller_add", N_IN)
+    L = sparse_mul(line_in(B, 0), line_in(B, 1), B)
+    out12(B, f12_in(B, 0).mul(L, B), 0)
+    return B
+
+
+def fp4_square(a, b, B):
+    """(a + b s)^2 in Fp4 = Fp2[s]/(s^2 - xi): (a^2 + xi b^2, 2ab)"""
+    t0, t1 = a.sqr(B), b.sqr(B)
+    return t0 + t1.mul_xi(), (a + b).sqr(B) - t0 - t1
+
+
+def cyclotomic_sqr(f, fr, B):
+    """Granger-Scott squaring for f in the cyclotomic subgroup (f^(p^4-p^2+1) = 1).  With Fp12 = Fp4[w]/(w^3 - s), s = w^3,
+    f = A + B w + C w^2, A = z0 + z1 s, B = z2 + z3 s, C = z4 + z5 s:
+        f^2 = (3A^2 - 2 conj A) + (3 s C^2 + 2 conj B) w + (3B^2 - 2 conj C) w^2.
+    f = the input as lazy linear combinations (feeds the multiplication operands), fr = the same values as plain
+    registers (used for the +-2z terms, so that coefficients do not compound over a chain of squarings)."""
+    z0, z4, z3 = f.c0.c0, f.c0.c1, f.c0.c2
+    z2, z1, z5 = f.c1.c0, f.c1.c1, f.c1.c2
+    r0, r4, r3 = fr.c0.c0, fr.c0.c1, fr.c0.c2
+    r2, r1, r5 = fr.c1.c0, fr.c1.c1, fr.c1.c2
+    a0, a1 = fp4_square(z0, z1, B)
+    b0, b1 = fp4_square(z2, z3, B)
+    c0, c1 = fp4_square(z4, z5, B)
+    three = lambda x: x + x + x
+    n0 = three(a0) - r0.dbl(); n1 = three(a1) + r1.dbl()
+    n4 = three(b0) - r4.dbl(); n5 = three(b1) + r5.dbl()
+    n2 = three(c1.mul_xi()) + r2.dbl(); n3 = three(c0) - r3.dbl()
+    return F12(F6(n0, n4, n3), F6(n2, n1, n5))
+
+
+def materialize12(B, x):
+    m = lambda v: Val({B.materialize(v): 1})
+    m2 = lambda a: F2(m(a.c0), m(a.c1))
+    return F12(F6(m2(x.c0.c0), m2(x.c0.c1), m2(x.c0.c2)), F6(m2(x.c1.c0), m2(x.c1.c1), m2(x.c1.c2)))
+
+
+def prog_cyc_sqr_k(k):     # F <- F^(2^k) for F in the cyclotomic subgroup (hard part of the final exponentiation)
+    def mk():
+        B = Builder("cyc_sqr%d" % k, N_IN)
+        x = xr = f12_in(B, 0)
+        for i in range(k):
+            x = cyclotomic_sqr(x, xr, B)
+            if i + 1 < k:
+                xr = materialize12(B, x)     # same level as the next squaring's operand sums
+        out12(B, x, 0)
+        return B
+    return mk
+
+
 def sparse014(A, Bx, Cy):
     z = Val()
     return F12(F6(A, Bx, F2(z, z)), F6(F2(z, z), Cy, F2(z, z)))
@@ -403,7 +474,7 @@ def prog_g1_add():
     return B
 
 
-PROGRAMS = [prog_f12_mul, prog_f12_sqr, prog_sqr_lines, prog_lines, prog_line1, prog_conj, prog_conj_g, prog_frob, prog_frob2,
+PROGRAMS = [prog_cyc_sqr_k(1), prog_f12_mul, prog_f12_sqr, prog_sqr_lines, prog_lines, prog_line1, prog_conj, prog_conj_g, prog_frob, prog_frob2,
             prog_inv_prep, prog_inv_finish, prog_g1_dbl, prog_g1_add]
 
 
@@ -452,6 +523,16 @@ def selftest(progs):
         assert unflat([r2[i] for i in range(12)]) == R.f12_sqr(f)
         r2 = dict(regs); run(progs["conj"], r2)
         assert unflat([r2[i] for i in range(12)]) == R.f12_conj(f)
+        # cyclotomic squarings: on an element of the cyclotomic subgroup g = f^((p^6-1)(p^2+1))
+        g1_ = R.f12_mul(R.f12_conj(f), R.f12_inv(f))
+        gc = R.f12_mul(R.f12_frob(R.f12_frob(g1_)), g1_)
+        rc = dict(regs)
+        for i, v in enumerate(flat(gc)): rc[i] = v
+        for k in (1,):
+            r2 = dict(rc); run(progs["cyc_sqr%d" % k], r2)
+            want = gc
+            for _ in range(k): want = R.f12_sqr(want)
+            assert unflat([r2[i] for i in range(12)]) == want
         r2 = dict(regs); run(progs["frob"], r2)
         assert unflat([r2[RG + i] for i in range(12)]) == R.f12_frob(f)
         r2 = dict(regs); run(progs["frob2"], r2)
@@ -471,6 +552,7 @@ def selftest(progs):
         assert unflat([r2[RG + i] for i in range(12)]) == R.f12_mul(l1, l2)
         r2 = dict(regs); run(progs["lines"], r2)
         assert unflat([r2[RG + i] for i in range(12)]) == R.f12_mul(l1, l2)
+
         r2 = dict(regs); run(progs["line1"], r2)
         assert unflat([r2[RG + i] for i in range(12)]) == l1
         r2 = dict(regs); run(progs["conj_g"], r2)

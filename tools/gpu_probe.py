@@ -45,3 +45,14 @@ for n in [int(x) for x in (sys.argv[1:] or ["64", "1024", "4096"])]:
     ps2 = ps.clone(); ps2[:48] = ps[48:96]; ps2[48:96] = ps[:48]
     rc = lib.kzgb200_verify_blob_kzg_proof_batch_device(ctx, blobs.data_ptr(), cs.data_ptr(), ps2.data_ptr(), n, C.byref(ok), None, None)
     print("  swapped proofs: rc", rc, "ok", ok.value)
+    try:
+        lib.kzgb200_debug_final_ticks.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+        tk = (C.c_longlong * 14)()
+        lib.kzgb200_verify_blob_kzg_proof_batch_device(ctx, blobs.data_ptr(), cs.data_ptr(), ps.data_ptr(), n, C.byref(ok), None, None)
+        lib.kzgb200_debug_final_ticks(ctx, tk)
+        names2 = ["prelude(G1 sums, [s]G, affine)", "miller loop", "final exp easy", "final exp hard", "compare"]
+        print("  final kernel sections (us @1.965GHz):", {k: round((tk[i + 1] - tk[i]) / 1965.0, 1) for i, k in enumerate(names2)})
+        print("  engine levels (lane 0): LIN body %.0f us, LIN barrier wait %.0f us over %d levels; MUL body %.0f us, MUL wait %.0f us over %d levels"
+              % (tk[8] / 1965.0, tk[9] / 1965.0, tk[12], tk[10] / 1965.0, tk[11] / 1965.0, tk[13]))
+    except Exception as e:
+        print("ticks unavailable", e)
