@@ -143,6 +143,28 @@ int kzgb200_debug_final_ticks(kzgb200_ctx* ctx, long long* out14);
 /* the cudaStream_t all work of this context is issued on (for CUDA-event timing by the caller) */
 void* kzgb200_stream(kzgb200_ctx* ctx);
 
+/* ---- streaming front-end: several batches in flight on one GPU --------------------------------
+ * A batch is a blob-streaming head (challenges, evaluations, G1 parsing: all SMs busy) followed by a latency-bound tail
+ * (transcript hash, MSM reduction, ONE pairing: a handful of CTAs).  A pipeline owns `depth` (1..8; 2 is enough)
+ * independent contexts with one host worker thread each, so that the tail of one batch runs under the head -- and,
+ * for host buffers, under the PCIe copy -- of the next.  Each ticket is exactly one kzgb200_verify_blob_kzg_proof_batch
+ * (host pointers) or ..._batch_device (device pointers) call: same verdicts, same return codes, same z / y.
+ * submit returns once the batch is queued (it blocks while `depth` batches are already in flight); the buffers must
+ * stay valid and unmodified until the ticket has been waited for.  wait returns that batch's return code and verdict;
+ * a ticket can be waited for once (KZGB200_BAD_ARGS otherwise).  Tickets complete in any order; wait in any order.
+ * kzgb200_pipeline_context(p, slot) exposes the contexts for the tuning calls (e.g. kzgb200_set_transcript_mode). */
+typedef struct kzgb200_pipeline kzgb200_pipeline;
+int kzgb200_pipeline_create(kzgb200_pipeline** out, int device, const uint8_t* g2_points, size_t g2_points_len, int depth);
+void kzgb200_pipeline_destroy(kzgb200_pipeline* p);   /* finishes what was submitted, then frees */
+int kzgb200_pipeline_depth(const kzgb200_pipeline* p);
+kzgb200_ctx* kzgb200_pipeline_context(kzgb200_pipeline* p, int slot);
+int kzgb200_pipeline_submit(kzgb200_pipeline* p, const uint8_t* blobs, size_t n_blobs, const uint8_t* commitments,
+                            size_t n_commitments, const uint8_t* proofs, size_t n_proofs, uint8_t* z_out, uint8_t* y_out,
+                            uint64_t* ticket);
+int kzgb200_pipeline_submit_device(kzgb200_pipeline* p, const uint8_t* d_blobs, const uint8_t* d_commitments,
+                                   const uint8_t* d_proofs, size_t n, uint8_t* d_z_out, uint8_t* d_y_out, uint64_t* ticket);
+int kzgb200_pipeline_wait(kzgb200_pipeline* p, uint64_t ticket, int* ok);
+
 /* pinned host memory helpers for callers that want full-rate host->device copies */
 void* kzgb200_alloc_pinned(size_t bytes);
 void kzgb200_free_pinned(void* p);

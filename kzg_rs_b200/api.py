@@ -84,6 +84,15 @@ class Library:
         d.kzgb200_load_g1_lagrange.argtypes = [p, C.c_char_p, sz]
         d.kzgb200_blob_to_kzg_commitment_batch.argtypes = [p, p, sz, p]
         d.kzgb200_compute_blob_kzg_proof_batch.argtypes = [p, p, p, sz, p]
+        u64 = C.c_uint64
+        d.kzgb200_pipeline_create.argtypes = [C.POINTER(p), C.c_int, C.c_char_p, sz, C.c_int]
+        d.kzgb200_pipeline_destroy.argtypes = [p]
+        d.kzgb200_pipeline_depth.argtypes = [p]
+        d.kzgb200_pipeline_context.argtypes = [p, C.c_int]
+        d.kzgb200_pipeline_context.restype = p
+        d.kzgb200_pipeline_submit.argtypes = [p, p, sz, p, sz, p, sz, p, p, C.POINTER(u64)]
+        d.kzgb200_pipeline_submit_device.argtypes = [p, p, p, p, sz, p, p, C.POINTER(u64)]
+        d.kzgb200_pipeline_wait.argtypes = [p, u64, ip]
         d.kzgb200_alloc_pinned.argtypes = [sz]
         d.kzgb200_alloc_pinned.restype = p
         d.kzgb200_free_pinned.argtypes = [p]
@@ -274,6 +283,73 @@ class KzgProof:
 TRANSCRIPT_EXACT, TRANSCRIPT_TREE = 0, 1
 
 
+class BatchPipeline:
+    """Streaming front-end: `depth` batches in flight on one GPU, each one exactly a
+    KzgProof::verify_blob_kzg_proof_batch call (reference src/kzg_proof.rs:472-525).  The latency-bound tail of one
+    batch (transcript, MSM reduction, pairing) runs under the blob-streaming head / the PCIe copy of the next.
+
+        pipe = BatchPipeline(settings, depth=2)
+        t = pipe.submit(blobs, n, commitments, n, proofs, n)      # host buffers (bytes / pinned tensors / pointers)
+        ...                                                       # submit more; blocks when `depth` are in flight
+        ok = pipe.wait(t)                                         # True / False, raises KzgError like the blocking call
+    """
+
+    def __init__(self, kzg_settings, depth=2, device=0, transcript_mode=None):
+        self.lib = Library.get().dll
+        self.h = C.c_void_p()
+        rc = self.lib.kzgb200_pipeline_create(C.byref(self.h), device, kzg_settings.g2_monomial_bytes[:192], 192, depth)
+        if rc:
+            _raise(rc)
+        self.depth = depth
+        self._keep = {}
+        if transcript_mode is not None:
+            for i in range(depth):
+                self.lib.kzgb200_set_transcript_mode(self.context(i), transcript_mode)
+
+    def context(self, slot):
+        return C.c_void_p(self.lib.kzgb200_pipeline_context(self.h, slot))
+
+    def submit(self, blobs, n_blobs, commitments, n_commitments, proofs, n_proofs, z_out=None, y_out=None):
+        """Host buffers; they must stay alive and unmodified until wait() (bytes objects are held by the pipeline)."""
+        t = C.c_uint64()
+        rc = self.lib.kzgb200_pipeline_submit(self.h, _ptr(blobs), n_blobs, _ptr(commitments), n_commitments, _ptr(proofs), n_proofs,
+                                              _ptr(z_out), _ptr(y_out), C.byref(t))
+        if rc:
+            _raise(rc)
+        self._keep[t.value] = (blobs, commitments, proofs, z_out, y_out)
+        return t.value
+
+    def submit_device(self, d_blobs, d_commitments, d_proofs, n, d_z_out=None, d_y_out=None):
+        """Device pointers (ints or objects with data_ptr()) on the pipeline's GPU; pending writes must be complete."""
+        t = C.c_uint64()
+        rc = self.lib.kzgb200_pipeline_submit_device(self.h, _ptr(d_blobs), _ptr(d_commitments), _ptr(d_proofs), n,
+                                                     _ptr(d_z_out), _ptr(d_y_out), C.byref(t))
+        if rc:
+            _raise(rc)
+        self._keep[t.value] = (d_blobs, d_commitments, d_proofs, d_z_out, d_y_out)
+        return t.value
+
+    def wait(self, ticket):
+        ok = C.c_int(0)
+        rc = self.lib.kzgb200_pipeline_wait(self.h, ticket, C.byref(ok))
+        self._keep.pop(ticket, None)
+        if rc:
+            _raise(rc)
+        return bool(ok.value)
+
+    def close(self):
+        if self.h:
+            self.lib.kzgb200_pipeline_destroy(self.h)
+            self.h = C.c_void_p()
+            self._keep = {}
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
 def set_transcript_mode(kzg_settings, mode, device=0):
     """EXACT (default, r bit-identical to kzg-rs) or TREE (parallel hash, same verdicts)."""
     rc = Library.get().dll.kzgb200_set_transcript_mode(kzg_settings.context(device), mode)
@@ -309,6 +385,8 @@ def _ptr(x):
         return None
     if isinstance(x, int):
         return C.c_void_p(x)
+    if hasattr(x, "data_ptr"):          # torch tensor (pinned host or device memory)
+        return C.c_void_p(x.data_ptr())
     if isinstance(x, (bytes, bytearray)):
         return C.cast(C.c_char_p(bytes(x)), C.c_void_p) if isinstance(x, bytes) else C.cast((C.c_char * len(x)).from_buffer(x), C.c_void_p)
     return C.cast(x, C.c_void_p)

@@ -38,6 +38,22 @@ def test_no_cpu_fallback_without_gpu(dll):
     assert dll.kzgb200_create(C.byref(ctx), 0, bytes(10), 10) == 5        # KZGB200_INVALID_SETUP
 
 
+def test_pipeline_argument_checks(dll):
+    """Streaming front-end: argument validation needs no device; creation fails loudly without one."""
+    h, ok, t = C.c_void_p(), C.c_int(), C.c_uint64()
+    dll.kzgb200_pipeline_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_char_p, C.c_size_t, C.c_int]
+    dll.kzgb200_pipeline_wait.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_int)]
+    dll.kzgb200_pipeline_depth.argtypes = [C.c_void_p]
+    assert dll.kzgb200_pipeline_create(C.byref(h), 0, bytes(192), 192, 0) == 1          # depth out of range
+    assert dll.kzgb200_pipeline_create(C.byref(h), 0, bytes(192), 192, 9) == 1
+    assert dll.kzgb200_pipeline_wait(None, 1, C.byref(ok)) == 1
+    assert dll.kzgb200_pipeline_depth(None) == 0
+    import torch
+    if not torch.cuda.is_available():
+        assert dll.kzgb200_pipeline_create(C.byref(h), 0, bytes(192), 192, 2) == 2      # no device -> InternalError, no fallback
+        assert not h.value
+
+
 def test_python_mirror_types_and_errors():
     import kzg_rs_b200 as K
     assert len(K.Bytes32.from_slice(bytes(32))) == 32 and len(K.Bytes48.from_slice(bytes(48))) == 48   # dtypes.rs:61-71

@@ -192,6 +192,53 @@ def test_synthetic_batch_64_against_oracle(K, settings, oracle):
     assert e.value.kind == "InvalidBytesLength"
 
 
+def test_pipeline_matches_blocking_calls(K, settings, oracle):
+    """Streaming front-end: batches in flight on two contexts give the verdicts, errors and z / y of the
+    blocking entry, whatever the completion order; host and device submissions mixed."""
+    import ctypes as C
+    import os
+    import torch
+    lib, ctx = K.Library.get().dll, settings.context(0)
+    tau = open(os.path.join(os.path.dirname(K.__file__), "data", "tau_powers_g1.bin"), "rb").read()
+    sizes, data = (64, 700, 1, 2), []
+    for k, n in enumerate(sizes):
+        b = torch.empty(n * 131072, dtype=torch.uint8, device="cuda")
+        c = torch.empty(n * 48, dtype=torch.uint8, device="cuda")
+        p = torch.empty(n * 48, dtype=torch.uint8, device="cuda")
+        assert lib.kzgb200_harness_generate(ctx, 0x1000 + k, n, 8, tau, b.data_ptr(), c.data_ptr(), p.data_ptr()) == 0
+        data.append((b, c, p))
+    torch.cuda.synchronize()
+    host = [tuple(t.cpu().numpy().tobytes() for t in d) for d in data]
+    q = bytes.fromhex("73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001")
+    hb, hc, hp = host[0]
+    bad_proof = bytearray(hp); bad_proof[17 * 48:18 * 48] = hp[18 * 48:19 * 48]
+    bad_blob = bytearray(hb); bad_blob[5 * 131072 + 9 * 32:5 * 131072 + 10 * 32] = q
+    z0, y0 = bytearray(64 * 32), bytearray(64 * 32)
+    want_ok, want_z, want_y = K.KzgProof.verify_blob_kzg_proof_batch_raw(hb, 64, hc, 64, hp, 64, settings, want_zy=True)
+    assert want_ok is True
+    with K.BatchPipeline(settings, depth=2) as pipe:
+        jobs = []      # (ticket or exception kind, expectation)
+        for rep in range(2):
+            jobs.append((pipe.submit(hb, 64, hc, 64, hp, 64, z_out=z0, y_out=y0), True))
+            jobs.append((pipe.submit_device(*data[1], 700), True))
+            jobs.append((pipe.submit(hb, 64, hc, 64, bytes(bad_proof), 64), False))
+            jobs.append((pipe.submit(bytes(bad_blob), 64, hc, 64, hp, 64), "BadArgs"))
+            jobs.append((pipe.submit(host[2][0], 1, host[2][1], 1, host[2][2], 1), True))
+            jobs.append((pipe.submit(hb, 64, hc, 63, hp, 64), "InvalidBytesLength"))
+            jobs.append((pipe.submit(b"", 0, b"", 0, b"", 0), True))
+            jobs.append((pipe.submit_device(*data[3], 2), True))
+        for ticket, want in reversed(jobs):          # wait in the opposite order
+            if isinstance(want, str):
+                with pytest.raises(K.KzgError) as e:
+                    pipe.wait(ticket)
+                assert e.value.kind == want
+            else:
+                assert pipe.wait(ticket) is want
+        assert bytes(z0) == b"".join(want_z) and bytes(y0) == b"".join(want_y)
+        with pytest.raises(K.KzgError):
+            pipe.wait(jobs[0][0])                    # a ticket can be waited for once
+
+
 def test_gpu_commit_and_prove_reproduce_reference_vector_bytes(K, settings, vectors, oracle):
     """blob_to_kzg_commitment / compute_blob_kzg_proof on the GPU regenerate the commitment and proof
     bytes of every valid verify_blob_kzg_proof vector, and agree with the oracle on random blobs."""
