@@ -42,7 +42,8 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=8192, help="blobs in the CPU-baseline sample (~19 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-pipeline", action="store_true", help="skip the two-in-flight streaming front-end measurement")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the streaming front-end measurement")
+    ap.add_argument("--inflight", type=int, default=2, help="batches in flight in the streaming front-end measurement")
     ap.add_argument("--lowdegree-blobs", action="store_true",
                     help="blobs = evaluations of random degree<8 polynomials (cheap generator) instead of uniformly random "
                          "blobs committed / proved by the GPU commit/prove path")
@@ -268,14 +269,14 @@ def main():
     # headline (which stays one blocking call at a time).
     pipelined = None
     if world == 1 and not args.no_pipeline:
-        with K.BatchPipeline(S, depth=2, device=local_rank, transcript_mode=1) as pipe:
+        with K.BatchPipeline(S, depth=args.inflight, device=local_rank, transcript_mode=1) as pipe:
             def run(submit, steps):
                 tickets = [submit() for _ in range(steps)]        # submit blocks while two batches are in flight
                 for t in tickets:
                     assert pipe.wait(t) is True, "valid batch rejected (pipeline)"
 
             def timed_pipe(submit):
-                run(submit, 2 * max(args.warmup, 3))                # warm-up on both contexts
+                run(submit, args.inflight * max(args.warmup, 3))    # warm-up on every context
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -287,10 +288,10 @@ def main():
 
             ms_p = timed_pipe(lambda: pipe.submit_device(d_blobs, d_cs, d_ps, n))
             ms_pe = timed_pipe(lambda: pipe.submit(h_blobs, n, h_cs, n, h_ps, n))
-        pipelined = {"in_flight": 2, "value": n / (ms_p / 1e3), "ms_per_step": ms_p, "e2e": n / (ms_pe / 1e3), "e2e_ms_per_step": ms_pe,
+        pipelined = {"in_flight": args.inflight, "value": n / (ms_p / 1e3), "ms_per_step": ms_p, "e2e": n / (ms_pe / 1e3), "e2e_ms_per_step": ms_pe,
                      "unit": "blobs/s", "transcript": "tree",
                      "note": "kzgb200_pipeline_submit / _wait: every ticket is one verify_blob_kzg_proof_batch call; "
-                             "K batches, two in flight, wall time of all K (ramp-up and drain included) / K"}
+                             "K batches, in_flight at a time, wall time of all K (ramp-up and drain included) / K"}
     sampler.stop_flag = True
     sampler.join(timeout=2)
     lib.kzgb200_set_transcript_mode(ctx, 1)

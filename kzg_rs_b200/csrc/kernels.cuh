@@ -23,6 +23,9 @@ struct DeviceTables {
     // group of 2^(k+1) consecutive points starting at index a has prod (z - w_i) = z^(2^(k+1)) - w_a^(2^(k+1)),
     // and w_a^(2^k) = roots_of_unity[2g] for g = a >> (k+1), independent of the level k.
     Fr twiddle[2048];
+    // the same twiddles in the order thread t of eval_kernel consumes them (post-order over its 32-leaf subtree): 31 per
+    // thread + 1 pad, so the stream is sequential and the next one can be fetched while the current merge runs
+    Fr twiddle_po[128][32];
     PairingTables pairing;
     // fixed-base table of the G1 generator: gen_table[w][d-1] = [d * 16^w] G, d = 1..15, w < 64
     G1Affine gen_table[64][15];
@@ -39,6 +42,18 @@ __global__ void setup_tables_kernel(DeviceTables* T, const uint8_t* g2_points /*
         const uint32_t om[8] = KZG_FR_OMEGA_M;
         uint32_t ee[1] = {e};
         T->twiddle[tid] = fr_const(om).pow(ee, 12);
+    }
+    if (tid >= 8192 && tid < 8192 + 4096) {
+        int t = (tid - 8192) >> 5, m = (tid - 8192) & 31, cnt = 0;
+        uint32_t g = 0;                                   // pad entry (m == 31): any valid element
+        for (int j = 0; j < 32; j++)
+            for (int k = 0; (j >> k) & 1; k++, cnt++)
+                if (cnt == m) g = (uint32_t)(t * 32 + j) >> (k + 1);
+        uint32_t i = 2u * g, e = 0;
+        for (int b = 0; b < 12; b++) e |= ((i >> b) & 1u) << (11 - b);
+        const uint32_t om[8] = KZG_FR_OMEGA_M;
+        uint32_t ee[1] = {e};
+        T->twiddle_po[t][m] = fr_const(om).pow(ee, 12);
     }
     if (tid >= 4096 && tid < 4096 + 960) {
         int w = (tid - 4096) / 15, d = (tid - 4096) % 15 + 1;
@@ -63,8 +78,55 @@ __global__ void setup_tables_kernel(DeviceTables* T, const uint8_t* g2_points /*
 // u64be 4096 | blob | commitment) mod q.  One thread per blob: the 2050-block chain is serial per blob, so
 // throughput comes from hashing many blobs at once.  The commitment bytes hashed are the caller's: for
 // every encoding from_compressed accepts, to_compressed(from_compressed(b)) == b.
-__global__ void __launch_bounds__(64) challenge_kernel(const uint8_t* __restrict__ blobs, const uint8_t* __restrict__ commitments,
-                                                       int n, Fr* __restrict__ z_mont, ZY* __restrict__ zy) {
+// z^(2^k), k = 0..12, for the evaluation tree (K1+K3) are produced here too: 12 squarings per blob after the hash.
+// (Measured dead end, tools/microbench/shachain.cu: riding per-element work -- canonicity screen, sum of the elements --
+// on this chain costs 12 % of its speed however it is phrased, IADD3 carry chains or IMAD.WIDE column sums: the chain
+// is one warp per SM sub-partition issuing ALU-pipe instructions back to back, and ptxas' schedule of it is fragile.)
+// Blocks 1..2047 of the challenge hash (99.9 % of the kernel).  The 64 bytes of the blocks ahead are brought in by cp.async
+// into a per-thread ring in shared memory (4 stages, three blocks = ~5 us in flight), so the DRAM latency stays hidden
+// whatever ptxas does with the loop: with register prefetching the same source ran at 3.3 ms per chain when the loads were
+// scheduled at the top of the body and at 4.3 ms when ptxas sank them to the bottom (tools/microbench/shachain.cu).  Each
+// thread reads back only what it copied itself, so no barrier is needed, only cp.async.wait_group.
+constexpr int kShaStages = 4;
+#ifndef KSHA_THREADS
+#define KSHA_THREADS 32
+#endif
+constexpr int kShaThreads = KSHA_THREADS;     // blobs (threads) per CTA of K2
+__device__ __forceinline__ void sha_cp_async16(uint4* smem_dst, const uint4* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void sha256_blob_body(uint32_t st[8], const uint4* __restrict__ bp, uint4 (*ring)[4][kShaThreads] /* [stage][quarter][thread] */,
+                                                 uint32_t one) {
+    const int t = threadIdx.x;
+    uint32_t w[16];
+#pragma unroll
+    for (int k = 1; k < kShaStages; k++) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) sha_cp_async16(&ring[k % kShaStages][q][t], bp + (4 * k - 2) + q);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+#pragma unroll 1
+    for (int k = 1; k < 2048; k++) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kShaStages - 2) : "memory");    // block k has landed
+        uint4 (*sg)[kShaThreads] = ring[k % kShaStages];
+        uint4 a = sg[0][t], b = sg[1][t], c = sg[2][t], d = sg[3][t];
+        if (k + kShaStages - 1 < 2048) {                                               // refill the stage consumed last time
+            const uint4* p = bp + (4 * (k + kShaStages - 1) - 2);
+#pragma unroll
+            for (int q = 0; q < 4; q++) sha_cp_async16(&ring[(k + kShaStages - 1) % kShaStages][q][t], p + q);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");                          // (possibly empty: keeps the group count uniform)
+        w[0] = sha_bswap(a.x); w[1] = sha_bswap(a.y); w[2] = sha_bswap(a.z); w[3] = sha_bswap(a.w);
+        w[4] = sha_bswap(b.x); w[5] = sha_bswap(b.y); w[6] = sha_bswap(b.z); w[7] = sha_bswap(b.w);
+        w[8] = sha_bswap(c.x); w[9] = sha_bswap(c.y); w[10] = sha_bswap(c.z); w[11] = sha_bswap(c.w);
+        w[12] = sha_bswap(d.x); w[13] = sha_bswap(d.y); w[14] = sha_bswap(d.z); w[15] = sha_bswap(d.w);
+        sha256_compress_bal(st, w, one);
+    }
+}
+__global__ void __launch_bounds__(kShaThreads) challenge_kernel(const uint8_t* __restrict__ blobs, const uint8_t* __restrict__ commitments,
+                                                       int n, Fr* __restrict__ z_mont, ZY* __restrict__ zy, Fr* __restrict__ zpow,
+                                                       uint32_t one /* == 1, opaque to the compiler: see sha256_compress_bal */) {
+    __shared__ uint4 ring[kShaStages][4][kShaThreads];
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint4* bp = reinterpret_cast<const uint4*>(blobs + (size_t)i * kBytesPerBlob);
@@ -81,17 +143,7 @@ __global__ void __launch_bounds__(64) challenge_kernel(const uint8_t* __restrict
     }
     sha256_compress(st, w);
     // blocks 1..2047: blob[64k-32 .. 64k+32)
-    // software pipeline: the next block's 64 bytes are in flight while this block is compressed
-    uint4 na = __ldg(bp + 2), nb = __ldg(bp + 3), nc = __ldg(bp + 4), nd = __ldg(bp + 5);
-    for (int k = 1; k < 2048; k++) {
-        uint4 a = na, b = nb, c = nc, d = nd;
-        if (k < 2047) { const uint4* p = bp + (4 * k + 2); na = __ldg(p); nb = __ldg(p + 1); nc = __ldg(p + 2); nd = __ldg(p + 3); }
-        w[0] = sha_bswap(a.x); w[1] = sha_bswap(a.y); w[2] = sha_bswap(a.z); w[3] = sha_bswap(a.w);
-        w[4] = sha_bswap(b.x); w[5] = sha_bswap(b.y); w[6] = sha_bswap(b.z); w[7] = sha_bswap(b.w);
-        w[8] = sha_bswap(c.x); w[9] = sha_bswap(c.y); w[10] = sha_bswap(c.z); w[11] = sha_bswap(c.w);
-        w[12] = sha_bswap(d.x); w[13] = sha_bswap(d.y); w[14] = sha_bswap(d.z); w[15] = sha_bswap(d.w);
-        sha256_compress(st, w);
-    }
+    sha256_blob_body(st, bp, ring, one);
     // block 2048: blob[131040..131072) | commitment[0..32)
     {
         uint4 a = __ldg(bp + 8190), b = __ldg(bp + 8191);
@@ -112,102 +164,9 @@ __global__ void __launch_bounds__(64) challenge_kernel(const uint8_t* __restrict
     Fr zm = Fr::from_raw(raw);
     z_mont[i] = zm;
     zy[i].z = zm.to_raw();
-}
-
-// K2, warp-specialised version.  A single warp can issue one ALU-pipe instruction every other clock, and one SHA-256
-// block costs ~1400 of them in a chain that is serial per blob, so "one thread per blob" leaves the machine at ~55 % of
-// the ALU pipe with n/32 warps.  Here a CTA owns 128 blobs with 4 CONSUMER warps (the 64 rounds: the only truly serial
-// part, ~2/3 of the work) and 4 PRODUCER warps (byte swap + message schedule + K, which do not depend on the chaining
-// value) -- one of each per SM sub-partition -- handing W[t]+K[t] over through a double-buffered shared-memory tile with
-// one named barrier per block and pair.  Additions are issued as IMAD (multiplier = a kernel argument equal to 1, so
-// ptxas cannot turn them back into IADD3): they run on the FMA pipe beside the SHF/LOP3 stream of the other warp.
-constexpr int kWsBlobs = 128, kWsThreads = 256;
-constexpr int kWsSmemBytes = 2 * 64 * kWsBlobs * 4;
-__device__ __forceinline__ uint32_t fadd(uint32_t x, uint32_t y, uint32_t one) {
-    uint32_t r;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(one), "r"(y));
-    return r;
-}
-__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-__global__ void __launch_bounds__(kWsThreads, 1) challenge_ws_kernel(const uint8_t* __restrict__ blobs, const uint8_t* __restrict__ commitments,
-                                                                     int n, Fr* __restrict__ z_mont, ZY* __restrict__ zy, uint32_t one) {
-    extern __shared__ uint32_t wk[];                 // [2][64][kWsBlobs]
-    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int role = warp >> 2, pair = warp & 3;           // role 0 = consumer, 1 = producer; the pair shares an SMSP (warp % 4)
-    int local = pair * 32 + lane;
-    int blob = blockIdx.x * kWsBlobs + local;
-    bool valid = blob < n;
-    int bsafe = valid ? blob : n - 1;                // out-of-range lanes shadow the last blob (barrier counts stay whole)
-    int bar_id = 1 + pair;
-    if (role == 1) {
-        const uint4* bp = reinterpret_cast<const uint4*>(blobs + (size_t)bsafe * kBytesPerBlob);
-        const uint32_t* cp = reinterpret_cast<const uint32_t*>(commitments + (size_t)bsafe * 48);
-        uint4 na = __ldg(bp + 2), nb = __ldg(bp + 3), nc = __ldg(bp + 4), nd = __ldg(bp + 5);   // block 1
-        for (int k = 0; k < 2050; k++) {
-            uint32_t w[16];
-            if (k == 0) {
-                w[0] = 0x4653424c; w[1] = 0x4f425645; w[2] = 0x52494659; w[3] = 0x5f56315f; w[4] = 0; w[5] = 0; w[6] = 0; w[7] = 4096;
-                uint4 a = __ldg(bp), b = __ldg(bp + 1);
-                w[8] = sha_bswap(a.x); w[9] = sha_bswap(a.y); w[10] = sha_bswap(a.z); w[11] = sha_bswap(a.w);
-                w[12] = sha_bswap(b.x); w[13] = sha_bswap(b.y); w[14] = sha_bswap(b.z); w[15] = sha_bswap(b.w);
-            } else if (k < 2048) {
-                uint4 a = na, b = nb, c = nc, d = nd;
-                if (k < 2047) { const uint4* p = bp + (4 * k + 2); na = __ldg(p); nb = __ldg(p + 1); nc = __ldg(p + 2); nd = __ldg(p + 3); }
-                w[0] = sha_bswap(a.x); w[1] = sha_bswap(a.y); w[2] = sha_bswap(a.z); w[3] = sha_bswap(a.w);
-                w[4] = sha_bswap(b.x); w[5] = sha_bswap(b.y); w[6] = sha_bswap(b.z); w[7] = sha_bswap(b.w);
-                w[8] = sha_bswap(c.x); w[9] = sha_bswap(c.y); w[10] = sha_bswap(c.z); w[11] = sha_bswap(c.w);
-                w[12] = sha_bswap(d.x); w[13] = sha_bswap(d.y); w[14] = sha_bswap(d.z); w[15] = sha_bswap(d.w);
-            } else if (k == 2048) {
-                uint4 a = __ldg(bp + 8190), b = __ldg(bp + 8191);
-                w[0] = sha_bswap(a.x); w[1] = sha_bswap(a.y); w[2] = sha_bswap(a.z); w[3] = sha_bswap(a.w);
-                w[4] = sha_bswap(b.x); w[5] = sha_bswap(b.y); w[6] = sha_bswap(b.z); w[7] = sha_bswap(b.w);
-                for (int j = 0; j < 8; j++) w[8 + j] = sha_bswap(__ldg(cp + j));
-            } else {
-                for (int j = 0; j < 4; j++) w[j] = sha_bswap(__ldg(cp + 8 + j));
-                w[4] = 0x80000000u;
-                for (int j = 5; j < 15; j++) w[j] = 0;
-                w[15] = 131152u * 8u;
-            }
-            uint32_t* dst = wk + (size_t)(k & 1) * 64 * kWsBlobs + local;
-#pragma unroll
-            for (int t = 0; t < 64; t++) {
-                if (t >= 16) {
-                    uint32_t w15 = w[(t + 1) & 15], w2 = w[(t + 14) & 15];
-                    uint32_t s0 = sha_rotr(w15, 7) ^ sha_rotr(w15, 18) ^ (w15 >> 3);
-                    uint32_t s1 = sha_rotr(w2, 17) ^ sha_rotr(w2, 19) ^ (w2 >> 10);
-                    w[t & 15] = fadd(fadd(w[t & 15], s0, one), fadd(w[(t + 9) & 15], s1, one), one);
-                }
-                dst[t * kWsBlobs] = fadd(w[t & 15], sha_k(t), one);
-            }
-            pair_barrier(bar_id);
-        }
-    } else {
-        uint32_t st[8];
-        sha256_init(st);
-        for (int k = 0; k < 2050; k++) {
-            pair_barrier(bar_id);
-            const uint32_t* src = wk + (size_t)(k & 1) * 64 * kWsBlobs + local;
-            uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
-#pragma unroll
-            for (int t = 0; t < 64; t++) {
-                uint32_t kw = src[t * kWsBlobs];
-                uint32_t y = fadd(h, kw, one), x = fadd(y, d, one);
-                uint32_t s1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25), ch = (e & f) ^ (~e & g);
-                uint32_t s0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22), mj = (a & b) ^ (a & c) ^ (b & c);
-                uint32_t sc = fadd(s1, ch, one);
-                uint32_t e2 = fadd(x, sc, one), t1 = fadd(y, sc, one), a2 = fadd(t1, fadd(s0, mj, one), one);
-                h = g; g = f; f = e; e = e2; d = c; c = b; b = a; a = a2;
-            }
-            st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
-        }
-        if (valid) {
-            Fr raw;
-            for (int j = 0; j < 8; j++) raw.l[j] = st[7 - j];
-            Fr zm = Fr::from_raw(raw);
-            z_mont[blob] = zm;
-            zy[blob].z = zm.to_raw();
-        }
-    }
+    Fr s = zm;
+#pragma unroll 1
+    for (int k = 0; k <= 12; k++) { zpow[(size_t)i * 13 + k] = s; s = s.mul_inl(s); }
 }
 
 // ------------------------------------------------------------------------------------------------ K1+K3
@@ -232,60 +191,108 @@ __device__ __forceinline__ Fr load_fe_be(const uint4* p) {
     f.l[3] = sha_bswap(lo.x); f.l[2] = sha_bswap(lo.y); f.l[1] = sha_bswap(lo.z); f.l[0] = sha_bswap(lo.w);
     return f;
 }
+__device__ __forceinline__ Fr ldg_fr(const Fr* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    Fr f;
+    f.l[0] = a.x; f.l[1] = a.y; f.l[2] = a.z; f.l[3] = a.w; f.l[4] = b.x; f.l[5] = b.y; f.l[6] = b.z; f.l[7] = b.w;
+    return f;
+}
+__device__ __forceinline__ Fr fr_merge(const Fr& pw, const Fr& a, const Fr& b, const Fr& w) {
+    return Fr::mul_dual_inl(pw, a.add_inl(b), w, a.sub_inl(b));
+}
 
-__global__ void __launch_bounds__(kEvalThreads) eval_kernel(const uint8_t* __restrict__ blobs, int n, const Fr* __restrict__ z_mont,
+// Work split: thread t owns the 32 consecutive leaves [32t, 32t+32) (binary-counter stack of pending left subtrees in shared
+// memory, one 16-byte column per thread and half: conflict-free), then the 128 subtree values are merged by a shrinking set
+// of threads (64 merges on two warps, then one warp finishes).  z^(2^k) come from K2.  The next leaf and the next twiddle
+// (sequential stream twiddle_po) are fetched one merge ahead.  Per leaf beside the merges: the plain sum of the elements is
+// kept unreduced in 9 limbs (one carry chain, reduced once per blob), and the canonicity test is one compare of the top
+// word -- it decides for every canonical element but a 2^-31 fraction -- with the exact comparison off the fast path.
+__global__ void __launch_bounds__(kEvalThreads) eval_kernel(const uint8_t* __restrict__ blobs, int n, const Fr* __restrict__ zpow,
                                                             const DeviceTables* __restrict__ T, ZY* __restrict__ zy,
                                                             uint32_t* __restrict__ status) {
     __shared__ Fr s_pow[13];              // z^(2^k), Montgomery
-    __shared__ Fr s_n[kEvalThreads];
-    __shared__ Fr s_f[kEvalThreads];
+    __shared__ uint4 s_stack[5][2][kEvalThreads];
+    __shared__ Fr s_n[2][kEvalThreads];
+    __shared__ uint32_t s_col[kEvalThreads / 32][9][2];   // per warp: sums of the low / high 16-bit halves of each limb of sum f
     int blob = blockIdx.x, t = threadIdx.x;
     if (blob >= n) return;
-    if (t == 0) {
-        Fr s = z_mont[blob];
-        s_pow[0] = s;
-        for (int k = 1; k <= 12; k++) { s = s.mul_inl(s); s_pow[k] = s; }
-    }
+    if (t < 13) s_pow[t] = ldg_fr(zpow + (size_t)blob * 13 + t);
     const uint4* base = reinterpret_cast<const uint4*>(blobs + (size_t)blob * kBytesPerBlob) + (size_t)t * kLeavesPerThread * 2;
-    // in-thread subtree over 32 consecutive leaves, binary-counter stack
-    Fr stack[5];
-    Fr fsum = Fr::zero();
+    const Fr* tw = T->twiddle_po[t];
+    Fr nxt = load_fe_be(base), wn = ldg_fr(tw), cur;
+    int m = 0;
+    uint32_t fs[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) fs[i] = 0;
     bool bad = false;
+    constexpr uint32_t kQ[8] = KZG_FR_Q;
     __syncthreads();
 #pragma unroll 1
     for (int j = 0; j < kLeavesPerThread; j++) {
-        Fr cur = load_fe_be(base + 2 * j);
-        bad |= cur.geq_modulus();
-        fsum = fsum.add_inl(cur);
-        int leaf = t * kLeavesPerThread + j, k = 0;
+        cur = nxt;
+        if (j + 1 < kLeavesPerThread) nxt = load_fe_be(base + 2 * (j + 1));
+        if (cur.l[7] >= kQ[7]) bad |= cur.geq_modulus();
+        fs[8] += add_n<8>(fs, fs, cur.l);
+        int k = 0;
 #pragma unroll 1
         for (; (j >> k) & 1; k++) {
-            // merge stack[k] (left, earlier leaves) with cur (right) at level k
-            Fr w = T->twiddle[leaf >> (k + 1)];
-            Fr sum = stack[k].add_inl(cur), dif = stack[k].sub_inl(cur);
-            cur = Fr::mul_dual_inl(s_pow[k], sum, w, dif);
+            // merge the pending left subtree of level k with cur (right)
+            Fr w = wn, left;
+            wn = ldg_fr(tw + ++m);                    // m <= 31: the pad entry
+            uint4 a = s_stack[k][0][t], b = s_stack[k][1][t];
+            left.l[0] = a.x; left.l[1] = a.y; left.l[2] = a.z; left.l[3] = a.w; left.l[4] = b.x; left.l[5] = b.y; left.l[6] = b.z; left.l[7] = b.w;
+            cur = fr_merge(s_pow[k], left, cur, w);
         }
-        stack[k < 5 ? k : 0] = cur;   // k = trailing ones of j; j == 31 leaves the finished subtree in stack[0]
-    }
-    s_n[t] = stack[0];
-    s_f[t] = fsum;
-    __syncthreads();
-    // cross-thread levels 5..11
-    for (int k = 5; k < 12; k++) {
-        int span = 1 << (k - 5);
-        if ((t & (2 * span - 1)) == 0) {
-            Fr a = s_n[t], b = s_n[t + span];
-            Fr w = T->twiddle[(t * kLeavesPerThread) >> (k + 1)];
-            s_n[t] = Fr::mul_dual_inl(s_pow[k], a.add_inl(b), w, a.sub_inl(b));
-            s_f[t] = s_f[t].add_inl(s_f[t + span]);
+        if (k < 5) {                                   // k = trailing ones of j; j == 31 ends with the finished subtree in cur
+            s_stack[k][0][t] = make_uint4(cur.l[0], cur.l[1], cur.l[2], cur.l[3]);
+            s_stack[k][1][t] = make_uint4(cur.l[4], cur.l[5], cur.l[6], cur.l[7]);
         }
-        __syncthreads();
     }
+    s_n[0][t] = cur;
     if (bad) atomicOr(&status[blob], kErrBlob);
+#pragma unroll
+    for (int i = 0; i < 9; i++) {                      // warp sums of 16-bit halves (< 2^21 each) on the integer reduction unit
+        uint32_t lo = __reduce_add_sync(0xffffffffu, fs[i] & 0xffffu), hi = __reduce_add_sync(0xffffffffu, fs[i] >> 16);
+        if ((t & 31) == 0) { s_col[t >> 5][i][0] = lo; s_col[t >> 5][i][1] = hi; }
+    }
+    __syncthreads();
+    // levels 5..11: node i of level k merges values 2i, 2i+1 of the level below; its twiddle is twiddle[i]
+    if (t >= 64) return;
+    s_n[1][t] = fr_merge(s_pow[5], s_n[0][2 * t], s_n[0][2 * t + 1], ldg_fr(T->twiddle + t));
+    asm volatile("bar.sync 1, 64;" ::: "memory");
+    if (t >= 32) return;
+    int src = 1;
+#pragma unroll 1
+    for (int k = 6; k < 12; k++, src ^= 1) {
+        if (t < (1 << (11 - k))) s_n[src ^ 1][t] = fr_merge(s_pow[k], s_n[src][2 * t], s_n[src][2 * t + 1], ldg_fr(T->twiddle + t));
+        __syncwarp();
+    }
     if (t == 0) {
+        // sum f as an 8-limb value: carry-propagate the column sums (total < 2^12 q), then subtract q << k where it fits
+        uint32_t acc[9];
+        uint64_t c = 0;
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            for (int wv = 0; wv < kEvalThreads / 32; wv++) c += (uint64_t)s_col[wv][i][0] + ((uint64_t)s_col[wv][i][1] << 16);
+            acc[i] = (uint32_t)c; c >>= 32;
+        }
+#pragma unroll 1
+        for (int k = 11; k >= 0; k--) {
+            uint32_t qs[9], d[9];
+            qs[0] = kQ[0] << k;
+#pragma unroll
+            for (int i = 1; i < 8; i++) qs[i] = __funnelshift_l(kQ[i - 1], kQ[i], k);
+            qs[8] = k ? kQ[7] >> (32 - k) : 0u;
+            uint32_t borrow = sub_n<8>(d, acc, qs);
+            d[8] = acc[8] - qs[8] - borrow;
+            if ((uint64_t)acc[8] >= (uint64_t)qs[8] + borrow) { for (int i = 0; i < 9; i++) acc[i] = d[i]; }   // acc >= q << k
+        }
+        Fr fsum;
+        for (int i = 0; i < 8; i++) fsum.l[i] = acc[i];
         const uint32_t invn[8] = KZG_FR_INV4096_M;
         Fr zn1 = s_pow[12].sub_inl(Fr::one());                              // z^4096 - 1 (Montgomery)
-        Fr num = s_pow[0].mul_inl(s_n[0]).sub_inl(zn1.mul_inl(s_f[0]));    // z N - (z^n - 1) sum f   (normal form)
+        Fr num = s_pow[0].mul_inl(s_n[src][0]).sub_inl(zn1.mul_inl(fsum));  // z N - (z^n - 1) sum f   (normal form)
         zy[blob].y = fr_const(invn).mul_inl(num);
     }
 }
@@ -298,7 +305,8 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const uint8_t* __res
 // saves: the bucket and pairing kernels slow down by more than the checks take.)
 // One thread per point; points [0,n) are commitments, [n,2n) proofs.
 __global__ void __launch_bounds__(128) g1_decompress_kernel(const uint8_t* __restrict__ commitments, const uint8_t* __restrict__ proofs, int n,
-                                                            G1Affine* __restrict__ C, G1Affine* __restrict__ P, uint32_t* __restrict__ status) {
+                                                            G1Affine* __restrict__ C, G1Affine* __restrict__ P, uint32_t* __restrict__ status,
+                                                            bool with_subgroup_check) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 2 * n) return;
     bool is_proof = i >= n;
@@ -312,6 +320,9 @@ __global__ void __launch_bounds__(128) g1_decompress_kernel(const uint8_t* __res
     G1Affine pt;
     bool ok = g1_from_compressed(pt, b, false);
     (is_proof ? P : C)[j] = pt;
+    // fused form (the batch path): every parsing CTA is resident from the start of phase 1, beside the hash chains; as a
+    // second kernel the subgroup checks queue behind the evaluation kernel's 16384 CTAs once the hashing is fast
+    if (ok && with_subgroup_check) ok = g1_in_subgroup(pt);
     if (!ok) atomicOr(&status[j], is_proof ? kErrProof : kErrCommitment);
 }
 __global__ void __launch_bounds__(128) g1_subgroup_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P, int n,

@@ -25,6 +25,7 @@ struct kzgb200_ctx {
     size_t cap = 0, blob_cap = 0, many_cap = 0;
     uint8_t *d_blobs = nullptr, *d_c = nullptr, *d_p = nullptr;     // staging of host inputs
     Fr* d_z_mont = nullptr;
+    Fr* d_zpow = nullptr;           // z^(2^k), k = 0..12, per blob (K2 -> K1/K3)
     ZY* d_zy = nullptr;
     G1Affine *d_C = nullptr, *d_P = nullptr;
     uint32_t* d_status = nullptr;
@@ -47,8 +48,9 @@ struct kzgb200_ctx {
     // optional per-phase timing (CUDA events on the context stream)
     int transcript_mode = KZGB200_TRANSCRIPT_EXACT;
     int num_sms = 148;
-    int sha_variant = 0;            // 0 = one thread per blob (default), 1 = warp-specialised producer/consumer kernel
     cudaEvent_t ev_sha0 = nullptr;
+    int parse_fused = 0;            // tuning: decompression + subgroup check in one kernel (env KZGB200_PARSE_FUSED; measured slower)
+    int parse_first = 0;            // tuning: launch G1 parsing before the first hash launch (env KZGB200_PARSE_FIRST)
     cudaStream_t s_aux = nullptr, s_copy = nullptr, s_work[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_begin = nullptr, ev_parse = nullptr, ev_decomp = nullptr, ev_h2d[64] = {nullptr}, ev_zy[64] = {nullptr};
     uint32_t* d_chain_state = nullptr;
@@ -86,7 +88,7 @@ static int ensure_capacity(kzgb200_ctx* ctx, size_t n, bool need_blob_staging) {
     if (n > ctx->cap) {
         size_t c = n;
         CK(regrow(ctx->d_c, c * 48)); CK(regrow(ctx->d_p, c * 48));
-        CK(regrow(ctx->d_z_mont, c)); CK(regrow(ctx->d_zy, c));
+        CK(regrow(ctx->d_z_mont, c)); CK(regrow(ctx->d_zy, c)); CK(regrow(ctx->d_zpow, c * 13));
         CK(regrow(ctx->d_C, c)); CK(regrow(ctx->d_P, c));
         CK(regrow(ctx->d_status, c)); CK(regrow(ctx->d_ry, c));
         CK(regrow(ctx->d_digits, c * kDigitRows)); CK(regrow(ctx->d_order, c * kDigitRows));
@@ -115,7 +117,9 @@ extern "C" int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_p
         int prio_lo = 0, prio_hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         // the hash chains are the long pole of phase 1: their CTAs go first, G1 parsing fills the rest of the machine
-        CK(cudaStreamCreateWithPriority(&ctx->s_aux, cudaStreamNonBlocking, prio_lo));
+        { const char* v = getenv("KZGB200_PARSE_PRIO"); CK(cudaStreamCreateWithPriority(&ctx->s_aux, cudaStreamNonBlocking, v && atoi(v) ? prio_hi : prio_lo)); }
+        if (const char* v = getenv("KZGB200_PARSE_FIRST")) ctx->parse_first = atoi(v);
+        if (const char* v = getenv("KZGB200_PARSE_FUSED")) ctx->parse_fused = atoi(v);
         CK(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
         for (auto& w : ctx->s_work) CK(cudaStreamCreateWithPriority(&w, cudaStreamNonBlocking, prio_hi));
         CK(cudaEventCreateWithFlags(&ctx->ev_begin, cudaEventDisableTiming));
@@ -127,8 +131,6 @@ extern "C" int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_p
         CK(cudaMalloc(&ctx->d_scratch, 512));
         CK(cudaFuncSetAttribute(batch_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinalSmem)));
         CK(cudaFuncSetAttribute(single_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinalSmem)));
-        CK(cudaFuncSetAttribute(challenge_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes));
-        if (const char* v = getenv("KZGB200_SHA_VARIANT")) ctx->sha_variant = atoi(v);
         CK(cudaEventCreateWithFlags(&ctx->ev_sha0, cudaEventDisableTiming));
         CK(cudaMalloc(&ctx->tables, sizeof(DeviceTables)));
         CK(cudaMalloc(&ctx->d_r, sizeof(Fr)));
@@ -141,7 +143,7 @@ extern "C" int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_p
         uint8_t* d_g2 = nullptr;
         CK(cudaMalloc(&d_g2, 192));
         CK(cudaMemcpyAsync(d_g2, g2_points, 192, cudaMemcpyHostToDevice, ctx->stream));
-        setup_tables_kernel<<<(4096 + 960 + 127) / 128, 128, 0, ctx->stream>>>(ctx->tables, d_g2);
+        setup_tables_kernel<<<(8192 + 4096) / 128, 128, 0, ctx->stream>>>(ctx->tables, d_g2);
         CK(cudaGetLastError());
         uint32_t ok = 0;
         CK(cudaMemcpyAsync(&ok, &ctx->tables->setup_ok, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -168,7 +170,7 @@ extern "C" void kzgb200_destroy(kzgb200_ctx* ctx) {
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     void* ptrs[] = {ctx->tables, ctx->d_blobs, ctx->d_c, ctx->d_p, ctx->d_z_mont, ctx->d_zy, ctx->d_C, ctx->d_P, ctx->d_status,
                     ctx->d_ry, ctx->d_r, ctx->d_partial, ctx->d_result, ctx->d_zout, ctx->d_yout, ctx->d_many, ctx->d_wk,
-                    ctx->d_digits, ctx->d_order, ctx->d_start, ctx->d_buckets, ctx->d_windows, ctx->d_lag_table, ctx->d_scalars};
+                    ctx->d_digits, ctx->d_order, ctx->d_start, ctx->d_buckets, ctx->d_windows, ctx->d_lag_table, ctx->d_scalars, ctx->d_zpow};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -244,6 +246,17 @@ static int launch_phase1(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t
     CK(cudaEventRecord(ctx->ev_begin, ctx->stream));
     if (with_transcript) { int rc = reserve_transcript(ctx, n); if (rc) return rc; }
     if (h_blobs) CK(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_begin, 0));
+    auto launch_parse = [&]() -> int {
+        CK(cudaStreamWaitEvent(ctx->s_aux, ctx->ev_begin, 0));
+        phase_begin(ctx, kPhParse, ctx->s_aux);
+        g1_decompress_kernel<<<(2 * (int)n + 127) / 128, 128, 0, ctx->s_aux>>>(d_c, d_p, (int)n, ctx->d_C, ctx->d_P, ctx->d_status, ctx->parse_fused != 0);
+        CK(cudaEventRecord(ctx->ev_decomp, ctx->s_aux));
+        if (!ctx->parse_fused) g1_subgroup_kernel<<<(2 * (int)n + 127) / 128, 128, 0, ctx->s_aux>>>(ctx->d_C, ctx->d_P, (int)n, ctx->d_status);
+        phase_end(ctx, kPhParse, ctx->s_aux);
+        CK(cudaEventRecord(ctx->ev_parse, ctx->s_aux));
+        return KZGB200_OK;
+    };
+    if (ctx->parse_first) { int rc = launch_parse(); if (rc) return rc; }
     for (size_t c = 0; c < nchunks; c++) {
         size_t lo = c * chunk, cnt = n - lo < chunk ? n - lo : chunk;
         cudaStream_t sw = ctx->s_work[c % kWorkStreams];
@@ -255,28 +268,17 @@ static int launch_phase1(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t
         }
         CK(cudaStreamWaitEvent(sw, ctx->ev_begin, 0));
         phase_begin(ctx, kPhChallenge, sw);
-        if (ctx->sha_variant == 1)
-            challenge_ws_kernel<<<((int)cnt + kWsBlobs - 1) / kWsBlobs, kWsThreads, kWsSmemBytes, sw>>>(d_blobs + lo * kBytesPerBlob, d_c + lo * 48, (int)cnt,
-                                                                                                   ctx->d_z_mont + lo, ctx->d_zy + lo, 1u);
-        else
-            challenge_kernel<<<((int)cnt + 63) / 64, 64, 0, sw>>>(d_blobs + lo * kBytesPerBlob, d_c + lo * 48, (int)cnt, ctx->d_z_mont + lo, ctx->d_zy + lo);
+        challenge_kernel<<<((int)cnt + kShaThreads - 1) / kShaThreads, kShaThreads, 0, sw>>>(d_blobs + lo * kBytesPerBlob, d_c + lo * 48, (int)cnt, ctx->d_z_mont + lo, ctx->d_zy + lo,
+                                                              ctx->d_zpow + lo * 13, 1u);
         phase_end(ctx, kPhChallenge, sw);
         if (c == 0) CK(cudaEventRecord(ctx->ev_sha0, sw));
         phase_begin(ctx, kPhEval, sw);
-        eval_kernel<<<(int)cnt, kEvalThreads, 0, sw>>>(d_blobs + lo * kBytesPerBlob, (int)cnt, ctx->d_z_mont + lo, ctx->tables, ctx->d_zy + lo,
+        eval_kernel<<<(int)cnt, kEvalThreads, 0, sw>>>(d_blobs + lo * kBytesPerBlob, (int)cnt, ctx->d_zpow + lo * 13, ctx->tables, ctx->d_zy + lo,
                                                        ctx->d_status + lo);
         phase_end(ctx, kPhEval, sw);
         CK(cudaEventRecord(ctx->ev_zy[c], sw));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_zy[c], 0));
-        if (c == 0) {   // G1 parsing is queued behind the first hash launch (and on a low-priority stream)
-            CK(cudaStreamWaitEvent(ctx->s_aux, ctx->ev_begin, 0));
-            phase_begin(ctx, kPhParse, ctx->s_aux);
-            g1_decompress_kernel<<<(2 * (int)n + 127) / 128, 128, 0, ctx->s_aux>>>(d_c, d_p, (int)n, ctx->d_C, ctx->d_P, ctx->d_status);
-            CK(cudaEventRecord(ctx->ev_decomp, ctx->s_aux));
-            g1_subgroup_kernel<<<(2 * (int)n + 127) / 128, 128, 0, ctx->s_aux>>>(ctx->d_C, ctx->d_P, (int)n, ctx->d_status);
-            phase_end(ctx, kPhParse, ctx->s_aux);
-            CK(cudaEventRecord(ctx->ev_parse, ctx->s_aux));
-        }
+        if (c == 0 && !ctx->parse_first) { int rc = launch_parse(); if (rc) return rc; }   // G1 parsing queued behind the first hash launch
         if (with_transcript && n >= 2) { int rc = advance_transcript(ctx, d_c, ctx->d_zy, d_p, n, lo + cnt); if (rc) return rc; }
     }
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_decomp, 0));   // the points exist; the subgroup verdicts (ev_parse) are awaited
@@ -495,7 +497,7 @@ extern "C" int kzgb200_harness_generate(kzgb200_ctx* ctx, uint64_t seed, size_t 
     int ni = (int)n;
     harness_blob_kernel<<<ni, 128, 0, ctx->stream>>>(seed, ni, degree, ctx->tables, d_blobs);
     harness_commit_kernel<<<(ni + 63) / 64, 64, 0, ctx->stream>>>(seed, ni, degree, d_M, nullptr, d_commitments, 0);
-    challenge_kernel<<<(ni + 63) / 64, 64, 0, ctx->stream>>>(d_blobs, d_commitments, ni, ctx->d_z_mont, ctx->d_zy);
+    challenge_kernel<<<(ni + kShaThreads - 1) / kShaThreads, kShaThreads, 0, ctx->stream>>>(d_blobs, d_commitments, ni, ctx->d_z_mont, ctx->d_zy, ctx->d_zpow, 1u);
     harness_commit_kernel<<<(ni + 63) / 64, 64, 0, ctx->stream>>>(seed, ni, degree, d_M, ctx->d_z_mont, d_proofs, 1);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -582,8 +584,8 @@ static int commit_or_prove(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8
         if (!want_proof) {
             blob_scalars_kernel<<<(unsigned)(((size_t)cnt * kFieldElementsPerBlob + 127) / 128), 128, 0, ctx->stream>>>(blobs, cnt, ctx->d_scalars, ctx->d_status);
         } else {
-            challenge_kernel<<<(cnt + 63) / 64, 64, 0, ctx->stream>>>(blobs, d_commitments + lo * 48, cnt, ctx->d_z_mont, ctx->d_zy);
-            eval_kernel<<<cnt, kEvalThreads, 0, ctx->stream>>>(blobs, cnt, ctx->d_z_mont, ctx->tables, ctx->d_zy, ctx->d_status);
+            challenge_kernel<<<(cnt + kShaThreads - 1) / kShaThreads, kShaThreads, 0, ctx->stream>>>(blobs, d_commitments + lo * 48, cnt, ctx->d_z_mont, ctx->d_zy, ctx->d_zpow, 1u);
+            eval_kernel<<<cnt, kEvalThreads, 0, ctx->stream>>>(blobs, cnt, ctx->d_zpow, ctx->tables, ctx->d_zy, ctx->d_status);
             quotient_kernel<<<cnt, kEvalThreads, 0, ctx->stream>>>(blobs, cnt, ctx->d_z_mont, ctx->d_zy, ctx->tables, ctx->d_scalars);
         }
         lag_msm_kernel<<<cnt, 256, 0, ctx->stream>>>(ctx->d_scalars, cnt, ctx->d_lag_table, d_out + lo * 48);

@@ -192,6 +192,28 @@ def test_synthetic_batch_64_against_oracle(K, settings, oracle):
     assert e.value.kind == "InvalidBytesLength"
 
 
+def test_canonicity_boundary_elements(K, settings, vectors, oracle):
+    """Blob::as_polynomial (src/dtypes.rs:48-57): q - 1 and values sharing q's top word are canonical (Ok, here false
+    because the commitment no longer matches), q and q + 1 are not (Err(BadArgs)) -- the kernel decides on the top word
+    first and compares exactly only then.  z and y of the accepted blobs against the oracle."""
+    q = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+    case = next(c for c in vectors["verify_blob_kzg_proof"] if c["output"] is True)
+    blob, c, p = vectors.blobs[case["blob"]], unhex(case["commitment"]), unhex(case["proof"])
+    for value, want_err in ((q - 1, False), (q - (1 << 200), False), ((0x73eda753 << 224) | 5, False), (q, True), (q + 1, True),
+                            ((0x73eda754 << 224), True), (2**256 - 1, True)):
+        for idx in (0, 1, 2047, 4095):
+            b = bytearray(blob)
+            b[32 * idx:32 * idx + 32] = value.to_bytes(32, "big")
+            got = tri(lambda: K.KzgProof.verify_blob_kzg_proof(K.Blob.from_slice(bytes(b)), K.Bytes48.from_slice(c), K.Bytes48.from_slice(p),
+                                                               settings, want_zy=True))
+            if want_err:
+                assert got is None, (hex(value), idx, got)
+            else:
+                ok, z, y = got
+                assert ok is False
+                assert z == oracle.compute_challenge(bytes(b), c) and y == oracle.evaluate_polynomial(bytes(b), z)
+
+
 def test_pipeline_matches_blocking_calls(K, settings, oracle):
     """Streaming front-end: batches in flight on two contexts give the verdicts, errors and z / y of the
     blocking entry, whatever the completion order; host and device submissions mixed."""

@@ -171,6 +171,34 @@ template <class F> float timeit(F f) {
     cudaEventRecord(e0); f(); cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1); return ms;
 }
+// Do the two pipes overlap?  Even warps run the ALU stream, odd warps the carry-chained wide MADs (mode 3), or every warp one
+// of them (modes 1, 2): if the pipes are independent, mode 3 takes max(mode 1, mode 2) of the half-populated runs, not the sum.
+template <int ILP> __global__ void k_mix(uint32_t* out, uint32_t a, uint32_t b, int iters, int mode) {
+    int warp = threadIdx.x >> 5;
+    bool do_alu = mode == 1 || (mode == 3 && !(warp & 1)), do_fma = mode == 2 || (mode == 3 && (warp & 1));
+    if (mode != 3 && (warp & 1)) return;             // modes 1, 2: only the even warps work (same warp count per stream as mode 3)
+    uint32_t s = 0;
+    if (do_alu) {
+        uint32_t x[ILP];
+        for (int j = 0; j < ILP; j++) x[j] = threadIdx.x + j;
+        for (int i = 0; i < iters; i++)
+#pragma unroll
+            for (int j = 0; j < ILP; j++) { x[j] = __funnelshift_r(x[j], x[j], 7) ^ a; x[j] = x[j] + b + i; }
+        for (int j = 0; j < ILP; j++) s += x[j];
+    }
+    if (do_fma) {
+        uint32_t lo[ILP], hi[ILP];
+        for (int j = 0; j < ILP; j++) { lo[j] = threadIdx.x + j; hi[j] = j; }
+        for (int i = 0; i < iters; i++)
+#pragma unroll
+            for (int j = 0; j < ILP; j += 2)
+                asm volatile("mad.lo.cc.u32 %0, %4, %5, %0;\n\tmadc.hi.cc.u32 %1, %4, %5, %1;\n\tmadc.lo.cc.u32 %2, %4, %5, %2;\n\tmadc.hi.u32 %3, %4, %5, %3;"
+                             : "+r"(lo[j]), "+r"(hi[j]), "+r"(lo[j + 1]), "+r"(hi[j + 1]) : "r"(a), "r"(b));
+        for (int j = 0; j < ILP; j++) s += lo[j] ^ hi[j];
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 int main() {
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
     int sms = p.multiProcessorCount; int clk_khz; cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
@@ -187,6 +215,14 @@ int main() {
     rep("IMAD.WIDE (mad.wide.u32) ilp8", timeit([&] { k_imadwide<8><<<B, T>>>((uint32_t*)buf, 3, 5, it); }), 8.0 * it, B, T);
     rep("IMAD.WIDE.X carry-chained ilp8", timeit([&] { k_imadwide_cc<8><<<B, T>>>((uint32_t*)buf, 3, 5, it); }), 8.0 * it, B, T);
     rep("ALU (SHF+LOP3+IADD3) ilp8, 3 ops", timeit([&] { k_alu<8><<<B, T>>>((uint32_t*)buf, 3, 5, it); }), 8.0 * 3 * it, B, T);
+    {   // pipe overlap: 8 warps per SM sub-partition in mode 3 (4 ALU + 4 FMA), 4 in modes 1 / 2
+        const int Tm = 1024, Bm = sms;
+        float t1 = timeit([&] { k_mix<8><<<Bm, Tm>>>((uint32_t*)buf, 3, 5, it, 1); });
+        float t2 = timeit([&] { k_mix<8><<<Bm, Tm>>>((uint32_t*)buf, 3, 5, it, 2); });
+        float t3 = timeit([&] { k_mix<8><<<Bm, Tm>>>((uint32_t*)buf, 3, 5, it, 3); });
+        printf("pipe overlap: ALU stream alone %.3f ms, IMAD.WIDE.X stream alone %.3f ms, both on the same sub-partitions %.3f ms (sum %.3f, max %.3f)\n",
+               t1, t2, t3, t1 + t2, t1 > t2 ? t1 : t2);
+    }
     for (int occ : {1, 2, 4, 8}) {
         int Bf = sms * occ, Tf = 128, itf = 512; char nm[64];
         snprintf(nm, 64, "Fp mul inl, %d CTA/SM x128", occ); rep(nm, timeit([&] { k_fpmul<<<Bf, Tf>>>((Fp*)buf, fin, itf); }), itf, Bf, Tf);
