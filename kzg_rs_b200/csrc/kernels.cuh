@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(128) g1_decompress_kernel(const uint8_t* __res
     if (ok && with_subgroup_check) ok = g1_in_subgroup(pt);
     if (!ok) atomicOr(&status[j], is_proof ? kErrProof : kErrCommitment);
 }
-__global__ void __launch_bounds__(128) g1_subgroup_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P, int n,
+__global__ void __launch_bounds__(256) g1_subgroup_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P, int n,
                                                           uint32_t* __restrict__ status) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n; i += gridDim.x * blockDim.x) {
         bool is_proof = i >= n;

@@ -17,6 +17,10 @@ using namespace kzgb200;
 static_assert(sizeof(Partial) == KZGB200_PARTIAL_BYTES, "Partial layout is part of the ABI");
 static_assert(sizeof(ZY) == 64, "ZY layout is part of the ABI");
 
+constexpr int kTailSms = 8;                    // SMs kept free of deferred subgroup checks for the latency-bound tail kernels
+constexpr int kTailHogSmem = 200 * 1024;       // dynamic shared memory of a subgroup-check CTA in deferred mode (never touched)
+constexpr int kTailPadSmem = 28 * 1024;        // ... and of the tail kernels: 200 KB + 28 KB do not fit one SM
+static_assert(sizeof(FinalSmem) >= (size_t)kTailPadSmem, "the pairing kernel must not fit beside a subgroup-check CTA");
 struct kzgb200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -50,6 +54,9 @@ struct kzgb200_ctx {
     int num_sms = 148;
     cudaEvent_t ev_sha0 = nullptr;
     int parse_fused = 0;            // tuning: decompression + subgroup check in one kernel (env KZGB200_PARSE_FUSED; measured slower)
+    int defer_subgroup = 1;         // single-GPU batches: subgroup checks run beside the latency-bound tail on their own SMs (env KZGB200_DEFER_SUBGROUP)
+    bool subgroup_pending = false;
+    cudaEvent_t ev_bucket = nullptr;
     int parse_first = 0;            // tuning: launch G1 parsing before the first hash launch (env KZGB200_PARSE_FIRST)
     cudaStream_t s_aux = nullptr, s_copy = nullptr, s_work[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_begin = nullptr, ev_parse = nullptr, ev_decomp = nullptr, ev_h2d[64] = {nullptr}, ev_zy[64] = {nullptr};
@@ -120,6 +127,9 @@ extern "C" int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_p
         { const char* v = getenv("KZGB200_PARSE_PRIO"); CK(cudaStreamCreateWithPriority(&ctx->s_aux, cudaStreamNonBlocking, v && atoi(v) ? prio_hi : prio_lo)); }
         if (const char* v = getenv("KZGB200_PARSE_FIRST")) ctx->parse_first = atoi(v);
         if (const char* v = getenv("KZGB200_PARSE_FUSED")) ctx->parse_fused = atoi(v);
+        if (const char* v = getenv("KZGB200_DEFER_SUBGROUP")) ctx->defer_subgroup = atoi(v);
+        CK(cudaEventCreateWithFlags(&ctx->ev_bucket, cudaEventDisableTiming));
+        CK(cudaFuncSetAttribute(g1_subgroup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailHogSmem));
         CK(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
         for (auto& w : ctx->s_work) CK(cudaStreamCreateWithPriority(&w, cudaStreamNonBlocking, prio_hi));
         CK(cudaEventCreateWithFlags(&ctx->ev_begin, cudaEventDisableTiming));
@@ -161,7 +171,7 @@ extern "C" void kzgb200_destroy(kzgb200_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (cudaStream_t st : {ctx->s_aux, ctx->s_copy, ctx->s_work[0], ctx->s_work[1], ctx->s_work[2], ctx->s_work[3]}) if (st) cudaStreamDestroy(st);
-    for (cudaEvent_t e : {ctx->ev_begin, ctx->ev_parse, ctx->ev_decomp, ctx->ev_sha0}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {ctx->ev_begin, ctx->ev_parse, ctx->ev_decomp, ctx->ev_sha0, ctx->ev_bucket}) if (e) cudaEventDestroy(e);
     for (auto e : ctx->ev_h2d) if (e) cudaEventDestroy(e);
     for (auto e : ctx->ev_zy) if (e) cudaEventDestroy(e);
     for (auto e : ctx->ev_s) if (e) cudaEventDestroy(e);
@@ -231,7 +241,7 @@ static int reserve_transcript(kzgb200_ctx* ctx, size_t n) {
 // phase 1 for blobs [0, n): K4 on s_aux; per chunk K2 -> K1/K3 on a work stream; optionally the transcript advances
 // on the main stream as chunks complete.  h_blobs != nullptr: the blobs are copied chunk by chunk from the host.
 static int launch_phase1(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t* h_blobs, const uint8_t* d_c, const uint8_t* d_p, size_t n,
-                         bool with_transcript) {
+                         bool with_transcript, bool defer_subgroup = false) {
     for (int i = 0; i < kPhCount; i++) ctx->ph_started[i] = false;
     size_t chunk = n;
     if (h_blobs) { chunk = (n + kMaxChunks - 1) / kMaxChunks; if (chunk < kMinChunk) chunk = kMinChunk; }
@@ -251,7 +261,8 @@ static int launch_phase1(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t
         phase_begin(ctx, kPhParse, ctx->s_aux);
         g1_decompress_kernel<<<(2 * (int)n + 127) / 128, 128, 0, ctx->s_aux>>>(d_c, d_p, (int)n, ctx->d_C, ctx->d_P, ctx->d_status, ctx->parse_fused != 0);
         CK(cudaEventRecord(ctx->ev_decomp, ctx->s_aux));
-        if (!ctx->parse_fused) g1_subgroup_kernel<<<(2 * (int)n + 127) / 128, 128, 0, ctx->s_aux>>>(ctx->d_C, ctx->d_P, (int)n, ctx->d_status);
+        if (defer_subgroup && !ctx->parse_fused) { ctx->subgroup_pending = true; return KZGB200_OK; }   // launched by launch_lincomb
+        if (!ctx->parse_fused) g1_subgroup_kernel<<<(2 * (int)n + 255) / 256, 256, 0, ctx->s_aux>>>(ctx->d_C, ctx->d_P, (int)n, ctx->d_status);
         phase_end(ctx, kPhParse, ctx->s_aux);
         CK(cudaEventRecord(ctx->ev_parse, ctx->s_aux));
         return KZGB200_OK;
@@ -300,10 +311,22 @@ static int launch_lincomb(kzgb200_ctx* ctx, size_t offset, Partial* d_out, bool 
     msm_sort_kernel<<<kDigitRows, 256, 0, ctx->stream>>>(ctx->d_digits, n, ctx->d_order, ctx->d_start);
     msm_bucket_kernel<<<(kMsmSets * kWindows * kBuckets * kBucketSplit + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_C, ctx->d_P, n, ctx->d_order, ctx->d_start, ctx->d_buckets);
     phase_end(ctx, kPhLincomb, ctx->stream);
+    if (ctx->subgroup_pending) {
+        // Deferred subgroup checks: from here on the batch is latency-bound (window sums, Horner combination, one pairing: a
+        // few CTAs), so the checks get the rest of the machine.  They run one CTA per SM on all but kTailSms SMs -- each CTA
+        // asks for kTailHogSmem of shared memory it never touches, and the tail kernels ask for kTailPadSmem, so that the two
+        // cannot share an SM: the tail keeps SMs of its own and is not slowed down (sharing SMs cost more than the deferral saved).
+        CK(cudaEventRecord(ctx->ev_bucket, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->s_aux, ctx->ev_bucket, 0));
+        g1_subgroup_kernel<<<ctx->num_sms - kTailSms, 256, kTailHogSmem, ctx->s_aux>>>(ctx->d_C, ctx->d_P, n, ctx->d_status);
+        phase_end(ctx, kPhParse, ctx->s_aux);
+        CK(cudaEventRecord(ctx->ev_parse, ctx->s_aux));
+        ctx->subgroup_pending = false;
+    }
     phase_begin(ctx, kPhReduce, ctx->stream);
-    msm_window_kernel<<<kMsmSets * kWindows, 32, 0, ctx->stream>>>(ctx->d_buckets, ctx->d_windows);
+    msm_window_kernel<<<kMsmSets * kWindows, 32, kTailPadSmem, ctx->stream>>>(ctx->d_buckets, ctx->d_windows);
     if (wait_subgroup) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_parse, 0));    // combine ORs the per-blob error flags
-    msm_combine_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_windows, ctx->d_ry, ctx->d_status, n, d_out);
+    msm_combine_kernel<<<1, 256, kTailPadSmem, ctx->stream>>>(ctx->d_windows, ctx->d_ry, ctx->d_status, n, d_out);
     phase_end(ctx, kPhReduce, ctx->stream);
     CK(cudaGetLastError());
     return KZGB200_OK;
@@ -324,7 +347,8 @@ static int export_zy(kzgb200_ctx* ctx, size_t n, uint8_t* d_z, uint8_t* d_y) {
 // whole batch on one GPU, n >= 1; blobs either resident (h_blobs == nullptr) or streamed from the host
 static int batch_locked(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t* h_blobs, const uint8_t* d_c, const uint8_t* d_p, size_t n, int* ok,
                         uint8_t* d_z_out, uint8_t* d_y_out) {
-    int rc = launch_phase1(ctx, d_blobs, h_blobs, d_c, d_p, n, true);
+    const bool defer = n >= 2 && ctx->defer_subgroup;
+    int rc = launch_phase1(ctx, d_blobs, h_blobs, d_c, d_p, n, true, defer);
     if (rc) return rc;
     if ((rc = export_zy(ctx, n, d_z_out, d_y_out))) return rc;
     phase_begin(ctx, kPhFinal, ctx->stream);
@@ -333,7 +357,7 @@ static int batch_locked(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t*
         single_final_kernel<<<1, kFinalThreads, sizeof(FinalSmem), ctx->stream>>>(ctx->d_C, ctx->d_P, ctx->d_zy, ctx->d_status, ctx->tables, ctx->d_result);
     } else {
         ctx->ph_started[kPhFinal] = false;
-        if ((rc = launch_lincomb(ctx, 0, ctx->d_partial, true))) return rc;
+        if ((rc = launch_lincomb(ctx, 0, ctx->d_partial, !defer))) return rc;   // deferred: the flags are merged by status_or below
         phase_begin(ctx, kPhFinal, ctx->stream);
         batch_final_kernel<<<1, kFinalThreads, sizeof(FinalSmem), ctx->stream>>>(ctx->d_partial, 1, ctx->tables, ctx->d_result, reinterpret_cast<long long*>(ctx->d_scratch + 128));
     }
