@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 BLOB = 131072
 ALGO_BYTES_PER_BLOB = 131072 + 48 + 48
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at 16384 blobs from the ncu --set full captures under profiles/
-TRAFFIC_BYTES = {"challenge_sha256": 2148582000 + 4388608, "evaluate_barycentric": 2150107000 + 157516800}   # profiles/ncu_full_r01_summary.txt
+TRAFFIC_BYTES = {"challenge_sha256": 2148375000 + 4876800, "evaluate_barycentric": 2154585000 + 4713984}   # profiles/ncu_full_r01_summary.txt
 PHASES = ["parse_g1", "challenge_sha256", "evaluate_barycentric", "transcript_r", "lincomb_terms", "reduce", "final_pairing"]
 
 
@@ -269,6 +269,7 @@ def main():
     # headline (which stays one blocking call at a time).
     pipelined = None
     if world == 1 and not args.no_pipeline:
+        pipe_batches = max(args.steps, 12)      # enough batches for the ramp-up and drain not to dominate
         with K.BatchPipeline(S, depth=args.inflight, device=local_rank, transcript_mode=1) as pipe:
             def run(submit, steps):
                 tickets = [submit() for _ in range(steps)]        # submit blocks while two batches are in flight
@@ -280,18 +281,18 @@ def main():
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                run(submit, args.steps)
+                run(submit, pipe_batches)
                 torch.cuda.synchronize()
                 e1.record()
                 torch.cuda.synchronize()
-                return e0.elapsed_time(e1) / args.steps
+                return e0.elapsed_time(e1) / pipe_batches
 
             ms_p = timed_pipe(lambda: pipe.submit_device(d_blobs, d_cs, d_ps, n))
             ms_pe = timed_pipe(lambda: pipe.submit(h_blobs, n, h_cs, n, h_ps, n))
         pipelined = {"in_flight": args.inflight, "value": n / (ms_p / 1e3), "ms_per_step": ms_p, "e2e": n / (ms_pe / 1e3), "e2e_ms_per_step": ms_pe,
-                     "unit": "blobs/s", "transcript": "tree",
+                     "unit": "blobs/s", "transcript": "tree", "batches": pipe_batches,
                      "note": "kzgb200_pipeline_submit / _wait: every ticket is one verify_blob_kzg_proof_batch call; "
-                             "K batches, in_flight at a time, wall time of all K (ramp-up and drain included) / K"}
+                             "`batches` batches, in_flight at a time, wall time of all of them (ramp-up and drain included) / batches"}
     sampler.stop_flag = True
     sampler.join(timeout=2)
     lib.kzgb200_set_transcript_mode(ctx, 1)
@@ -312,7 +313,9 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        top = max(range(7), key=lambda i: phases[i]) if world == 1 else None
+        # dominant kernel = the longest compute phase of the blocking call; parse_g1 is excluded: its phase spans the deferred
+        # subgroup checks, which run beside the tail on SMs of their own
+        top = max(range(1, 7), key=lambda i: phases[i]) if world == 1 else None
         roof = int_pipe = None
         if top is not None and phases[top] > 0:
             ach = n * ALGO_BYTES_PER_BLOB / (phases[top] / 1e3) / 1e9
@@ -322,7 +325,7 @@ def main():
             # algorithmic integer work of the two blob-streaming kernels against the MEASURED pipe peaks (tools/microbench/intpipe.cu,
             # profiles/intpipe_r01.txt): ALU 69.2 thread-ops/clk/SM, carry-chained IMAD.WIDE.X 31.0 /clk/SM, 148 SMs
             clk = 1.965e9
-            sha_ops = n * 2050 * 1400.0          # ALU-pipe instructions per 64-byte block (SASS count), per thread
+            sha_ops = n * 2050 * 1218.0          # ALU-pipe instructions per 64-byte block (SASS count: 672 SHF + 352 LOP3 + 178 IADD3 + 16 PRMT)
             fr_ops = n * 4095 * 192.0            # IMAD.WIDE.X per fused dual Fr product
             int_pipe = {"challenge_sha256": {"achieved_ops_per_s": sha_ops / (phases[1] / 1e3), "peak_ops_per_s": 69.2 * 148 * clk,
                                              "frac": sha_ops / (phases[1] / 1e3) / (69.2 * 148 * clk), "pipe": "ALU (SHF/LOP3/IADD3)"},

@@ -85,12 +85,12 @@ class ShardedBatch:
     def count_launches(n, resident, tree):
         """Kernels of libkzgb200.so launched by one batch on one rank (mirrors launch_phase1 / advance_transcript /
         launch_lincomb in csrc/kzgb200.cu): G1 decompress + subgroup, per chunk challenge + evaluation, export of z/y,
-        transcript (tree: leaf per chunk + root; exact: schedule + chain per chunk), 5 MSM kernels, pairing, flag merge."""
+        transcript (tree: words + leaf per chunk, then root; exact: schedule + chain per chunk), 5 MSM kernels, pairing, flag merge."""
         if resident:
             chunks = 1 if (tree or n < 4096) else math.ceil(n / max(1024, math.ceil(n / 8)))
         else:
             chunks = math.ceil(n / max(1024, math.ceil(n / 64)))
-        transcript = (chunks + 1) if tree else 2 * chunks
+        transcript = (2 * chunks + 1) if tree else 2 * chunks
         return 2 + 2 * chunks + 1 + transcript + 5 + 2
 
     def _check(self, rc):
