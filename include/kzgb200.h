@@ -98,7 +98,10 @@ int kzgb200_shard_challenge(kzgb200_ctx* ctx, const uint8_t* d_all_commitments, 
                             const uint8_t* d_all_proofs, size_t n_total);
 /* phase 2: this rank's partial sums with r_i = r^(global_offset + i); writes KZGB200_PARTIAL_BYTES to d_partial_out. */
 int kzgb200_shard_lincomb(kzgb200_ctx* ctx, size_t global_offset, uint8_t* d_partial_out);
-/* final: sum the gathered partials (n_ranks x KZGB200_PARTIAL_BYTES) and run the single pairing check. */
+/* final: sum the gathered partials (n_ranks x KZGB200_PARTIAL_BYTES) and run the single pairing check.  The subgroup checks of
+ * this rank's own points run beside the tail (they may still be running when the partial is exported), so a rank whose shard
+ * holds a point outside the subgroup learns it here: it returns KZGB200_BAD_ARGS while the other ranks see the flags only if they
+ * were known at export time -- the caller combines the return codes of all ranks (kzg_rs_b200/sharded.py: one 4-byte all-reduce). */
 int kzgb200_shard_finalize(kzgb200_ctx* ctx, const uint8_t* d_partials, size_t n_ranks, int* ok);
 
 /* ---- transcript mode of the batch challenge r -----------------------------------------------------------------

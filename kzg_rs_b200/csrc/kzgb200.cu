@@ -455,7 +455,7 @@ extern "C" int kzgb200_shard_evaluate(kzgb200_ctx* ctx, const uint8_t* d_blobs, 
     CK(cudaSetDevice(ctx->device));
     int rc = ensure_capacity(ctx, n_local, false);
     if (rc) return rc;
-    if ((rc = launch_phase1(ctx, d_blobs, nullptr, d_commitments, d_proofs, n_local, false))) return rc;
+    if ((rc = launch_phase1(ctx, d_blobs, nullptr, d_commitments, d_proofs, n_local, false, ctx->defer_subgroup != 0))) return rc;
     if (d_zy_out) CK(cudaMemcpyAsync(d_zy_out, ctx->d_zy, n_local * sizeof(ZY), cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return KZGB200_OK;
@@ -470,7 +470,7 @@ extern "C" int kzgb200_shard_evaluate_host(kzgb200_ctx* ctx, const uint8_t* blob
     if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->d_c, commitments, n_local * 48, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_p, proofs, n_local * 48, cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = launch_phase1(ctx, ctx->d_blobs, blobs, ctx->d_c, ctx->d_p, n_local, false))) return rc;
+    if ((rc = launch_phase1(ctx, ctx->d_blobs, blobs, ctx->d_c, ctx->d_p, n_local, false, ctx->defer_subgroup != 0))) return rc;
     if (d_commitments_out) CK(cudaMemcpyAsync(d_commitments_out, ctx->d_c, n_local * 48, cudaMemcpyDeviceToDevice, ctx->stream));
     if (d_proofs_out) CK(cudaMemcpyAsync(d_proofs_out, ctx->d_p, n_local * 48, cudaMemcpyDeviceToDevice, ctx->stream));
     if (d_zy_out) CK(cudaMemcpyAsync(d_zy_out, ctx->d_zy, n_local * sizeof(ZY), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -491,7 +491,9 @@ extern "C" int kzgb200_shard_lincomb(kzgb200_ctx* ctx, size_t global_offset, uin
     if (!ctx || !d_partial_out || ctx->cur_n == 0) return KZGB200_BAD_ARGS;
     std::lock_guard<std::mutex> g(ctx->lock);
     CK(cudaSetDevice(ctx->device));
-    int rc = launch_lincomb(ctx, global_offset, reinterpret_cast<Partial*>(d_partial_out), true);
+    // deferred subgroup checks (launched in here, beside the tail): the partial then carries only the flags known so far;
+    // kzgb200_shard_finalize merges this rank's late flags into its own return code
+    int rc = launch_lincomb(ctx, global_offset, reinterpret_cast<Partial*>(d_partial_out), !ctx->subgroup_pending);
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     return KZGB200_OK;
@@ -501,6 +503,8 @@ extern "C" int kzgb200_shard_finalize(kzgb200_ctx* ctx, const uint8_t* d_partial
     std::lock_guard<std::mutex> g(ctx->lock);
     CK(cudaSetDevice(ctx->device));
     batch_final_kernel<<<1, kFinalThreads, sizeof(FinalSmem), ctx->stream>>>(reinterpret_cast<const Partial*>(d_partials), (int)n_ranks, ctx->tables, ctx->d_result, nullptr);
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_parse, 0));
+    status_or_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_status, (int)ctx->cur_n, ctx->d_result + 2);
     CK(cudaGetLastError());
     return read_result(ctx, ok);
 }

@@ -17,6 +17,7 @@ import torch
 BLOB = 131072
 PARTIAL_BYTES = 352
 FR_MODULUS_BE = bytes.fromhex("73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001")
+NOT_IN_G1 = bytes.fromhex("8123456789abcdef" + "0123456789abcdef" * 5)      # decompresses to a curve point of the wrong order
 
 
 class GpuBackend:
@@ -119,7 +120,13 @@ class ShardedBatch:
         be.lincomb(self.rank * self.n, self.partial)
         dist.all_gather_into_tensor(self.partials, self.partial)
         be.sync_collectives()
-        return be.finalize(self.partials, self.world)
+        res = be.finalize(self.partials, self.world)
+        # a rank's own subgroup checks may finish after its partial was exported (they run beside the tail): agree on the
+        # outcome -- Err(BadArgs) on any rank is Err(BadArgs) for the batch (reference: first failure aborts, src/kzg_proof.rs:503-516)
+        code = torch.tensor([2 if res is None else int(res)], dtype=torch.int32, device=self.partials.device)
+        dist.all_reduce(code, op=dist.ReduceOp.MAX)
+        worst = int(code.item())
+        return None if worst == 2 else (res if worst == int(bool(res)) else bool(worst))
 
     def verify_host(self, h_blobs, h_cs, h_ps):
         """Inputs in (pinned) host memory; host->device copies are part of the call."""
@@ -154,4 +161,13 @@ class ShardedBatch:
         r = self.verify_device(d_blobs, d_cs, d_ps)
         res["element_equal_to_modulus"] = "Err(BadArgs)" if r is None else r
         d_blobs[pos:pos + 32] = saved
+        # a commitment that is on the curve but outside the subgroup (c-kzg vector invalid_commitment_32afa9561a4b3b91), in the
+        # LAST rank's shard: found by the deferred subgroup checks, must be Err(BadArgs) on every rank
+        k = (self.n - 1) * 48
+        saved = d_cs[k:k + 48].clone()
+        if self.rank == self.world - 1:
+            d_cs[k:k + 48] = torch.tensor(list(NOT_IN_G1), dtype=torch.uint8, device=d_cs.device)
+        r = self.verify_device(d_blobs, d_cs, d_ps)
+        res["commitment_outside_subgroup"] = "Err(BadArgs)" if r is None else r
+        d_cs[k:k + 48] = saved
         return res

@@ -190,6 +190,16 @@ def test_synthetic_batch_64_against_oracle(K, settings, oracle):
     with pytest.raises(K.KzgError) as e:
         K.KzgProof.verify_blob_kzg_proof_batch_raw(hb, n, hc, n - 1, hp, n, settings)
     assert e.value.kind == "InvalidBytesLength"
+    # a commitment / a proof on the curve but outside the subgroup (found by the deferred subgroup checks) -> Err(BadArgs)
+    from kzg_rs_b200.sharded import NOT_IN_G1
+    for which in (0, 1):
+        for idx in (0, 40, 63):
+            arrs = [bytearray(hc), bytearray(hp)]
+            arrs[which][idx * 48:idx * 48 + 48] = NOT_IN_G1
+            with pytest.raises(K.KzgError) as e:
+                K.KzgProof.verify_blob_kzg_proof_batch_raw(hb, n, bytes(arrs[0]), n, bytes(arrs[1]), n, settings)
+            assert e.value.kind == "BadArgs"
+    assert K.KzgProof.verify_blob_kzg_proof_batch_raw(hb, n, hc, n, hp, n, settings) is True      # and the flags do not leak into the next call
 
 
 def test_canonicity_boundary_elements(K, settings, vectors, oracle):

@@ -19,7 +19,9 @@ Q = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
 class OracleBackend:
     """CPU stand-in for GpuBackend: same methods, same payload sizes (64 B per blob of zy, 352 B partials)."""
 
-    def __init__(self):
+    def __init__(self, late_flags=False):
+        # late_flags: the rank's own error flags are known only at finalize (deferred subgroup checks in the CUDA backend)
+        self.late_flags = late_flags
         sys.path.insert(0, ROOT)
         from oracle import oracle as O
         from oracle import pyref as R
@@ -69,11 +71,13 @@ class OracleBackend:
             A = O.g1_lincomb(self.p, [be(x) for x in ri])
             Bp = O.g1_lincomb(self.c + self.p, [be(x) for x in ri] + [be(x * z % Q) for x, z in zip(ri, self.z)])
             s = sum(x * y for x, y in zip(ri, self.y)) % Q
-        raw = A + Bp + be(s) + self.err.to_bytes(4, "little")
+        raw = A + Bp + be(s) + (0 if self.late_flags else self.err).to_bytes(4, "little")
         partial_out.copy_(torch.frombuffer(bytearray(raw + bytes(352 - len(raw))), dtype=torch.uint8))
 
     def finalize(self, partials, world):
         O, R = self.O, self.R
+        if self.late_flags and self.err:
+            return None
         raw = self._b(partials)
         parts = [raw[352 * k:352 * (k + 1)] for k in range(world)]
         if any(int.from_bytes(p[128:132], "little") for p in parts):
@@ -96,11 +100,12 @@ def _worker(rank, world, port, cases, results):
     sys.path.insert(0, ROOT)
     from kzg_rs_b200.sharded import ShardedBatch
     out = []
-    for blobs, cs, ps in cases:
-        n_local = len(cs) // 48 // world
-        sl = lambda raw, k: torch.frombuffer(bytearray(raw[k * n_local * rank:k * n_local * (rank + 1)]), dtype=torch.uint8)
-        plan = ShardedBatch(None, None, n_local, rank, world, dist, device=torch.device("cpu"), backend=OracleBackend())
-        out.append(plan.verify_device(sl(blobs, 131072), sl(cs, 48), sl(ps, 48)))
+    for late in (False, True):
+        for blobs, cs, ps in cases:
+            n_local = len(cs) // 48 // world
+            sl = lambda raw, k: torch.frombuffer(bytearray(raw[k * n_local * rank:k * n_local * (rank + 1)]), dtype=torch.uint8)
+            plan = ShardedBatch(None, None, n_local, rank, world, dist, device=torch.device("cpu"), backend=OracleBackend(late))
+            out.append(plan.verify_device(sl(blobs, 131072), sl(cs, 48), sl(ps, 48)))
     results[rank] = out
     dist.destroy_process_group()
 
@@ -131,4 +136,4 @@ def test_two_rank_sharded_batch_matches_unsharded(vectors, oracle):
     for p in procs:
         p.join(timeout=300)
         assert p.exitcode == 0
-    assert results[0] == want and results[1] == want
+    assert results[0] == want + want and results[1] == want + want      # flags in the partial / flags known only at finalize
