@@ -11,6 +11,7 @@
 #include <cstdint>
 #include <cstring>
 #include <fstream>
+#include <map>
 #include <memory>
 #include <string>
 #include <utility>
@@ -40,6 +41,7 @@ public:
     bool is_ok() const { return ok_; }
     bool is_err() const { return !ok_; }
     const T& unwrap() const { return value_; }
+    T& unwrap() { return value_; }
     const KzgError& unwrap_err() const { return err_; }
 };
 
@@ -118,6 +120,44 @@ struct KzgProof {
                                                      reinterpret_cast<const uint8_t*>(proofs_bytes.data()), proofs_bytes.size(), &ok,
                                                      nullptr, nullptr);
         return detail::to_result(rc, ok, blobs.size() != commitments_bytes.size() ? "Invalid commitments length" : "Invalid proofs length");
+    }
+};
+
+// Streaming front-end (include/kzgb200.h, kzgb200_pipeline_*): `depth` verify_blob_kzg_proof_batch calls in flight on one GPU.
+// The pipeline owns the submitted vectors until the ticket has been waited for (the C ABI reads them asynchronously).
+class BatchPipeline {
+    struct Deleter { void operator()(kzgb200_pipeline* p) const { kzgb200_pipeline_destroy(p); } };
+    struct Held { std::vector<Blob> blobs; std::vector<Bytes48> commitments, proofs; };
+    std::shared_ptr<kzgb200_pipeline> p_;
+    std::map<uint64_t, Held> held_;
+public:
+    using Ticket = uint64_t;
+    static Result<BatchPipeline> create(const KzgSettings& kzg_settings, int depth = 2, int device = 0) {
+        kzgb200_pipeline* raw = nullptr;
+        int rc = kzgb200_pipeline_create(&raw, device, kzg_settings.g2_points.data(), 192, depth);
+        if (rc) return KzgError{rc == KZGB200_INVALID_SETUP ? KzgError::InvalidTrustedSetup : KzgError::InternalError, "kzgb200_pipeline_create failed"};
+        BatchPipeline bp;
+        bp.p_ = std::shared_ptr<kzgb200_pipeline>(raw, Deleter());
+        return bp;
+    }
+    // same arguments as KzgProof::verify_blob_kzg_proof_batch (reference src/kzg_proof.rs:472-477), taken by value like there
+    Result<Ticket> submit(std::vector<Blob> blobs, std::vector<Bytes48> commitments_bytes, std::vector<Bytes48> proofs_bytes) {
+        Held h{std::move(blobs), std::move(commitments_bytes), std::move(proofs_bytes)};
+        uint64_t t = 0;
+        int rc = kzgb200_pipeline_submit(p_.get(), reinterpret_cast<const uint8_t*>(h.blobs.data()), h.blobs.size(),
+                                         reinterpret_cast<const uint8_t*>(h.commitments.data()), h.commitments.size(),
+                                         reinterpret_cast<const uint8_t*>(h.proofs.data()), h.proofs.size(), nullptr, nullptr, &t);
+        if (rc) return KzgError{KzgError::InternalError, "kzgb200_pipeline_submit failed"};
+        held_.emplace(t, std::move(h));          // moving a vector keeps its buffer where it is
+        return t;
+    }
+    Result<bool> wait(Ticket t) {
+        int ok = 0;
+        int rc = kzgb200_pipeline_wait(p_.get(), t, &ok);
+        auto it = held_.find(t);
+        bool c_len = it != held_.end() && it->second.blobs.size() != it->second.commitments.size();
+        if (it != held_.end()) held_.erase(it);
+        return detail::to_result(rc, ok, c_len ? "Invalid commitments length" : "Invalid proofs length");
     }
 };
 

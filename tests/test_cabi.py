@@ -93,7 +93,11 @@ int main(int argc, char** argv) {
     if (settings.is_err()) { std::puts("no-gpu"); return 0; }       // fails loudly without a GPU: that is the contract
     std::vector<Blob> blobs; std::vector<Bytes48> cs, ps;
     auto r = KzgProof::verify_blob_kzg_proof_batch(blobs, cs, ps, settings.unwrap());   // n = 0 -> Ok(true)
-    std::puts(r.is_ok() && r.unwrap() ? "ok-true" : "unexpected");
+    auto pipe = BatchPipeline::create(settings.unwrap(), 2);
+    if (pipe.is_err()) { std::puts("unexpected"); return 0; }
+    auto t = pipe.unwrap().submit(blobs, cs, ps);
+    auto w = pipe.unwrap().wait(t.unwrap());
+    std::puts(r.is_ok() && r.unwrap() && w.is_ok() && w.unwrap() ? "ok-true" : "unexpected");
     return 0;
 }
 ''')

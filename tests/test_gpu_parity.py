@@ -404,6 +404,16 @@ int main(int argc, char** argv) {
     b2.resize(2); c2.resize(1); p2.resize(2);
     auto r = KzgProof::verify_blob_kzg_proof_batch(b2, c2, p2, ks);                      // length mismatch
     putchar(r.is_err() && r.unwrap_err().kind == KzgError::InvalidBytesLength ? 'L' : '?');
+    // streaming front-end: three tickets in flight on two contexts, waited for in reverse order
+    auto pipe = BatchPipeline::create(ks, 2).unwrap();
+    std::vector<Blob> e0; std::vector<Bytes48> e1, e2;
+    auto t1 = pipe.submit(e0, e1, e2).unwrap();                                          // empty -> Ok(true)
+    auto t2 = pipe.submit(std::vector<Blob>(2), std::vector<Bytes48>(1), std::vector<Bytes48>(2)).unwrap();   // length mismatch
+    auto t3 = pipe.submit(std::vector<Blob>(2), std::vector<Bytes48>(2), std::vector<Bytes48>(2)).unwrap();   // zero blobs, zero points: Err(BadArgs)
+    auto r3 = pipe.wait(t3); auto r2 = pipe.wait(t2); auto r1 = pipe.wait(t1);
+    putchar(r1.is_ok() && r1.unwrap() ? '1' : '?');
+    putchar(r2.is_err() && r2.unwrap_err().kind == KzgError::InvalidBytesLength ? 'L' : '?');
+    putchar(r3.is_err() && r3.unwrap_err().kind == KzgError::BadArgs ? 'B' : '?');
     putchar('\n');
     return 0;
 }
@@ -424,4 +434,4 @@ int main(int argc, char** argv) {
     code = {True: "1", False: "0", None: "2"}
     assert l1 == "".join(code[c["output"]] for c in k_cases)
     assert l2 == "".join(code[c["output"]] * 2 for c in b_cases)
-    assert l3 == "1L"
+    assert l3 == "1L1LB"
