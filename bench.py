@@ -253,7 +253,7 @@ def main():
             ms = float(t.item())
         return ms, [a / steps for a in phase_acc]
 
-    # Headline = the throughput configuration: KZGB200_TRANSCRIPT_TREE (batch challenge r hashed as a 2-level tree; verdict, z,
+    # Headline = the throughput configuration: KZGB200_TRANSCRIPT_TREE (batch challenge r hashed as a 3-level tree; verdict, z,
     # y identical to kzg-rs, r itself not).  The library default (EXACT: r bit-identical, one serial SHA-256 chain over all
     # blobs of all ranks) is timed in the same run and reported under "exact_transcript".
     sampler = ClockSampler(local_rank)
@@ -333,7 +333,7 @@ def main():
                                                  "frac": fr_ops / (phases[2] / 1e3) / (31.0 * 148 * clk), "pipe": "FMA-heavy (IMAD.WIDE.U32.X)"}}
         cfg = workload_config(args, n, world)
         cfg["host_affinity"] = numa_cpus
-        cfg["transcript"] = "tree (opt-in KZGB200_TRANSCRIPT_TREE: same verdict / z / y as kzg-rs, r hashed as a 2-level tree)"
+        cfg["transcript"] = "tree (opt-in KZGB200_TRANSCRIPT_TREE: same verdict / z / y as kzg-rs, r hashed as a 3-level tree)"
         ex_ms, ex_ph, ex_e2e = res["exact"]
         out = {"metric": "blobs verified/sec (verify_blob_kzg_proof_batch)", "value": value, "unit": "blobs/s", "n_gpus": world,
                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",

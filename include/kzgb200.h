@@ -108,7 +108,7 @@ int kzgb200_shard_finalize(kzgb200_ctx* ctx, const uint8_t* d_partials, size_t n
  * EXACT (default): r = SHA-256 over the serial transcript exactly as compute_r_powers (reference
  *   src/kzg_proof.rs:291-348) -- r, its powers and both MSM sums are bit-identical to kzg-rs.  The hash is one
  *   serial chain of 2.5 SHA-256 blocks per blob.
- * TREE (opt-in): same transcript bytes hashed as a two-level tree (64-entry leaves in parallel).  r differs from
+ * TREE (opt-in): same transcript bytes hashed as a three-level tree (16-entry leaves, then 32 digests per middle hash, in parallel; then the root).  r differs from
  *   kzg-rs's; verdicts do not (z, y are unaffected).  For throughput at large n / many GPUs. */
 #define KZGB200_TRANSCRIPT_EXACT 0
 #define KZGB200_TRANSCRIPT_TREE 1

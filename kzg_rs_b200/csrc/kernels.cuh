@@ -465,7 +465,8 @@ __global__ void __launch_bounds__(32) transcript_chain_kernel(const uint32_t* __
 // u64be n | leaf digests).  The leaves hash in parallel, so the serial part shrinks from 2.5 to 0.008 SHA blocks
 // per blob.  r then differs from kzg-rs's r (the verdict does not: both are Fiat-Shamir challenges over the
 // same data), so this mode is NOT the default; see DESIGN.md "transcript modes".
-constexpr int kTreeGroup = 64;
+constexpr int kTreeGroup = 16;      // transcript entries (160 B each) per leaf hash: 40 compressions
+constexpr int kTreeMid = 32;        // leaf digests per middle-level hash: 17 compressions
 // entry words of the transcript (40 big-endian words per blob), written once in parallel so that the leaf hashes read
 // their blocks with plain vector loads
 __global__ void __launch_bounds__(256) transcript_words_kernel(const uint8_t* __restrict__ commitments, const ZY* __restrict__ zy,
@@ -501,26 +502,41 @@ __global__ void __launch_bounds__(64) transcript_tree_leaf_words_kernel(const ui
     }
     for (int j = 0; j < 8; j++) digests[g * 8 + j] = st[j];
 }
-__global__ void transcript_tree_root_kernel(const uint32_t* __restrict__ digests, uint64_t n, Fr* __restrict__ r_mont) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    uint64_t ngroups = (n + kTreeGroup - 1) / kTreeGroup;
-    size_t len = 32 + (size_t)ngroups * 32, nblk = (len + 9 + 63) / 64;
+// SHA-256 of `nwords` big-endian words (optionally preceded by an 8-word header) by ONE thread; digest words to out[0..8)
+__device__ __forceinline__ void sha256_words_serial(const uint32_t* hdr8, const uint32_t* __restrict__ src, size_t nwords, uint32_t* out) {
+    size_t total = nwords + (hdr8 ? 8 : 0), nblk = (total * 4 + 9 + 63) / 64;
     uint32_t st[8], w[16];
     sha256_init(st);
     for (size_t blk = 0; blk < nblk; blk++) {
         for (int j = 0; j < 16; j++) {
-            size_t pos = blk * 64 + 4 * j;    // word-aligned: header is 8 words, digests are whole words
+            size_t wi = blk * 16 + j;
             uint32_t v;
-            if (pos < 32) {
-                const uint32_t hdr[8] = {0x52434b5a, 0x47424154, 0x43485f5f, 0x5f56315f, 0, 4096, (uint32_t)(n >> 32), (uint32_t)n};  // "RCKZGBATCH___V1_"
-                v = hdr[pos / 4];
-            } else if (pos < len) v = digests[(pos - 32) / 4];
-            else v = pos == len ? 0x80000000u : 0;
+            if (hdr8 && wi < 8) v = hdr8[wi];
+            else if (wi < total) v = src[wi - (hdr8 ? 8 : 0)];
+            else v = wi == total ? 0x80000000u : 0u;
             w[j] = v;
         }
-        if (blk == nblk - 1) { w[14] = (uint32_t)(((uint64_t)len * 8) >> 32); w[15] = (uint32_t)((uint64_t)len * 8); }
+        if (blk == nblk - 1) { w[14] = (uint32_t)(((uint64_t)total * 32) >> 32); w[15] = (uint32_t)((uint64_t)total * 32); }
         sha256_compress(st, w);
     }
+    for (int j = 0; j < 8; j++) out[j] = st[j];
+}
+// middle level (kTreeMid leaf digests per hash, in parallel) and root ("RCKZGBATCH___V1_" | u64be 4096 | u64be n | middle digests).
+// The tree shape is a function of n alone, and n is hashed into the root.  16384 blobs: 40 + 17 + 18 dependent compressions
+// instead of the 40 961 of the serial transcript.
+__global__ void __launch_bounds__(256) transcript_tree_root_kernel(const uint32_t* __restrict__ digests, uint64_t n, uint32_t* __restrict__ mid,
+                                                                   Fr* __restrict__ r_mont) {
+    uint64_t ngroups = (n + kTreeGroup - 1) / kTreeGroup, nmid = (ngroups + kTreeMid - 1) / kTreeMid;
+    for (uint64_t m = threadIdx.x; m < nmid; m += blockDim.x) {
+        uint64_t first = m * kTreeMid, cnt = ngroups - first < (uint64_t)kTreeMid ? ngroups - first : (uint64_t)kTreeMid;
+        sha256_words_serial(nullptr, digests + first * 8, (size_t)cnt * 8, mid + m * 8);
+    }
+    __threadfence_block();
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const uint32_t hdr[8] = {0x52434b5a, 0x47424154, 0x43485f5f, 0x5f56315f, 0, 4096, (uint32_t)(n >> 32), (uint32_t)n};  // "RCKZGBATCH___V1_"
+    uint32_t st[8];
+    sha256_words_serial(hdr, mid, (size_t)nmid * 8, st);
     Fr raw;
     for (int j = 0; j < 8; j++) raw.l[j] = st[7 - j];
     *r_mont = Fr::from_raw(raw);

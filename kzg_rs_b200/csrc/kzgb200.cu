@@ -213,7 +213,8 @@ static int advance_transcript(kzgb200_ctx* ctx, const uint8_t* d_c, const ZY* d_
             ctx->tr_done = ready;
         }
         if (avail >= n) {
-            transcript_tree_root_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_wk, (uint64_t)n, ctx->d_r);
+            transcript_tree_root_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_wk, (uint64_t)n, ctx->d_wk + ((n + kTreeGroup - 1) / kTreeGroup) * 8 + 64 + n * 40 + 64,
+                                                                   ctx->d_r);
             phase_end(ctx, kPhTranscript, ctx->stream);
         }
     } else {
@@ -232,7 +233,7 @@ static int advance_transcript(kzgb200_ctx* ctx, const uint8_t* d_c, const ZY* d_
     return KZGB200_OK;
 }
 static int reserve_transcript(kzgb200_ctx* ctx, size_t n) {
-    size_t words = ctx->transcript_mode == KZGB200_TRANSCRIPT_TREE ? ((n + kTreeGroup - 1) / kTreeGroup) * 8 + 64 + n * 40 + 64
+    size_t words = ctx->transcript_mode == KZGB200_TRANSCRIPT_TREE ? ((n + kTreeGroup - 1) / kTreeGroup) * 8 + 64 + n * 40 + 64 + ((n + kTreeGroup * kTreeMid - 1) / (kTreeGroup * kTreeMid)) * 8 + 8
                                                                    : ((32 + n * 160 + 9 + 63) / 64) * 64;
     if (words > ctx->wk_cap) { CK(regrow(ctx->d_wk, words)); ctx->wk_cap = words; }
     ctx->tr_done = 0;
