@@ -737,32 +737,40 @@ __global__ void __launch_bounds__(256) msm_combine_kernel(const G1* __restrict__
                                                           int n, Partial* __restrict__ out) {
     __shared__ uint32_t s_err;
     __shared__ Fr s_ry[256];
-    __shared__ CoopPoint cp[2];
-    int t = threadIdx.x;
+    __shared__ CoopPoint cp[3];
+    int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     if (t == 0) s_err = 0;
     __syncthreads();
-    uint32_t e = 0;
-    Fr acc_ry = Fr::zero();
-    for (int i = t; i < n; i += blockDim.x) { e |= status[i]; acc_ry = acc_ry.add_inl(ry[i]); }
-    if (e) atomicOr(&s_err, e);
-    s_ry[t] = acc_ry;
-    __syncthreads();
-    for (int span = 128; span >= 1; span >>= 1) {
-        if (t < span) s_ry[t] = s_ry[t].add_inl(s_ry[t + span]);
-        __syncthreads();
-    }
-    if (t < 64) {
-        int warp = t >> 5, lane = t & 31;
+    if (warp < kMsmSets) {
+        // warps 0..2: Horner recombination of one point set each (15 x 8 doublings + 16 additions, the serial part of the tail)
         CoopPoint* s = &cp[warp];
         if (lane == 0) { s->v[0] = Fp::one(); s->v[1] = Fp::one(); s->v[2] = Fp::zero(); }
         __syncwarp();
         for (int w = kWindows - 1; w >= 0; w--) {
             if (w != kWindows - 1) for (int k = 0; k < 8; k++) coop_dbl(s, lane);
-            if (warp == 1) { coop_add(s, windows[1 * kWindows + w], lane); coop_add(s, windows[2 * kWindows + w], lane); }
-            else coop_add(s, windows[w], lane);
+            coop_add(s, windows[warp * kWindows + w], lane);
         }
-        if (lane == 0) { G1 r = {s->v[0], s->v[1], s->v[2]}; if (warp == 1) out->b = r; else out->a = r; }
+    } else {
+        // warps 3..7, beside the recombination: OR of the per-blob error flags and sum r_i y_i
+        constexpr int kHelpers = 256 - 32 * kMsmSets;
+        int h = t - 32 * kMsmSets;
+        uint32_t e = 0;
+        Fr acc_ry = Fr::zero();
+        for (int i = h; i < n; i += kHelpers) { e |= status[i]; acc_ry = acc_ry.add_inl(ry[i]); }
+        if (e) atomicOr(&s_err, e);
+        s_ry[h] = acc_ry;
+        asm volatile("bar.sync 1, %0;" ::"n"(kHelpers) : "memory");
+        for (int span = 128; span >= 1; span >>= 1) {
+            if (h < span && h + span < kHelpers) s_ry[h] = s_ry[h].add_inl(s_ry[h + span]);
+            asm volatile("bar.sync 1, %0;" ::"n"(kHelpers) : "memory");
+        }
     }
+    __syncthreads();
+    if (warp == 1) {          // B' = set 1 + set 2
+        G1 q = {cp[2].v[0], cp[2].v[1], cp[2].v[2]};
+        coop_add(&cp[1], q, lane);
+    }
+    if (warp < 2 && lane == 0) { G1 r = {cp[warp].v[0], cp[warp].v[1], cp[warp].v[2]}; if (warp == 1) out->b = r; else out->a = r; }
     if (t == 0) { out->ry = s_ry[0]; out->err = s_err; }
 }
 
