@@ -626,23 +626,24 @@ __global__ void __launch_bounds__(128) msm_bucket_kernel(const G1Affine* __restr
     __syncthreads();
     if (part == 0 && live) buckets[bucket_id] = sm[threadIdx.x].add(sm[threadIdx.x + 1]);
 }
-// one warp per (set, window): W = sum_b b * bucket[b].  Lane l owns buckets 8l .. 8l+7 (running-sum trick inside
+// two warps per (set, window): W = sum_b b * bucket[b].  Lane l owns buckets 4l .. 4l+3 (running-sum trick inside
 // the segment, then the segment's offset 8l by a short double-and-add), then a shared-memory tree over the lanes.
-__global__ void __launch_bounds__(32) msm_window_kernel(const G1* __restrict__ buckets, G1* __restrict__ windows /* [3][16] */) {
-    __shared__ G1 sm[32];
+constexpr int kWinLanes = 64, kWinPer = kBuckets / kWinLanes;     // 64 lanes x 4 buckets: 48 CTAs still fit the tail's 8 SMs in one wave
+__global__ void __launch_bounds__(kWinLanes) msm_window_kernel(const G1* __restrict__ buckets, G1* __restrict__ windows /* [3][16] */) {
+    __shared__ G1 sm[kWinLanes];
     int l = threadIdx.x, sw = blockIdx.x;          // sw = set * kWindows + window
-    const G1* bk = buckets + (size_t)sw * kBuckets + 8 * l;
+    const G1* bk = buckets + (size_t)sw * kBuckets + kWinPer * l;
     G1 run = G1::identity(), acc = G1::identity();
-    for (int j = 7; j >= 0; j--) {
+    for (int j = kWinPer - 1; j >= 0; j--) {
         run = run.add(bk[j]);                      // bucket 0 holds the identity
         acc = acc.add(run);                        // after the loop: acc = sum_j (j+1) bk[j], run = sum_j bk[j]
     }
-    // sum_j (8l + j) bk[j] = acc + (8l - 1) run
-    uint32_t k[1] = {(uint32_t)(8 * l)};
+    // sum_j (kWinPer l + j) bk[j] = acc + (kWinPer l - 1) run
+    uint32_t k[1] = {(uint32_t)(kWinPer * l)};
     G1 off = scalar_mul(run, k, 8);
     sm[l] = acc.add(off).add(run.neg());
     __syncthreads();
-    for (int span = 16; span >= 1; span >>= 1) {
+    for (int span = kWinLanes / 2; span >= 1; span >>= 1) {
         if (l < span) sm[l] = sm[l].add(sm[l + span]);
         __syncthreads();
     }

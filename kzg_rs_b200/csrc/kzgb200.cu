@@ -325,7 +325,7 @@ static int launch_lincomb(kzgb200_ctx* ctx, size_t offset, Partial* d_out, bool 
         ctx->subgroup_pending = false;
     }
     phase_begin(ctx, kPhReduce, ctx->stream);
-    msm_window_kernel<<<kMsmSets * kWindows, 32, kTailPadSmem, ctx->stream>>>(ctx->d_buckets, ctx->d_windows);
+    msm_window_kernel<<<kMsmSets * kWindows, kWinLanes, kTailPadSmem, ctx->stream>>>(ctx->d_buckets, ctx->d_windows);
     if (wait_subgroup) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_parse, 0));    // combine ORs the per-blob error flags
     msm_combine_kernel<<<1, 256, kTailPadSmem, ctx->stream>>>(ctx->d_windows, ctx->d_ry, ctx->d_status, n, d_out);
     phase_end(ctx, kPhReduce, ctx->stream);
