@@ -208,7 +208,7 @@ __device__ __forceinline__ Fr fr_merge(const Fr& pw, const Fr& a, const Fr& b, c
 // (sequential stream twiddle_po) are fetched one merge ahead.  Per leaf beside the merges: the plain sum of the elements is
 // kept unreduced in 9 limbs (one carry chain, reduced once per blob), and the canonicity test is one compare of the top
 // word -- it decides for every canonical element but a 2^-31 fraction -- with the exact comparison off the fast path.
-__global__ void __launch_bounds__(kEvalThreads) eval_kernel(const uint8_t* __restrict__ blobs, int n, const Fr* __restrict__ zpow,
+__global__ void __launch_bounds__(kEvalThreads, 6) eval_kernel(const uint8_t* __restrict__ blobs, int n, const Fr* __restrict__ zpow,
                                                             const DeviceTables* __restrict__ T, ZY* __restrict__ zy,
                                                             uint32_t* __restrict__ status) {
     __shared__ Fr s_pow[13];              // z^(2^k), Montgomery
