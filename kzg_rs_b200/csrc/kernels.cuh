@@ -821,14 +821,15 @@ __global__ void __launch_bounds__(kFinalThreads) batch_final_kernel(const Partia
     __syncthreads();
     if (s_err) { if (t == 0) { result[0] = kBadArgs; result[1] = s_err; } return; }
     G1 sg = coop_fixed_base_mul(s_sum, T, sm);
-    if (t < 2) {
+    if ((t & 31) == 0) {     // lane 0 of warp 0 and of warp 1: the two data-dependent inversion loops run side by side, not serialised
+        int w = t >> 5;
         G1 acc = G1::identity();
-        for (int k = 0; k < nparts; k++) acc = acc.add(t == 0 ? parts[k].a : parts[k].b);
-        if (t == 1) acc = acc.add(sg.neg());
+        for (int k = 0; k < nparts; k++) acc = acc.add(w == 0 ? parts[k].a : parts[k].b);
+        if (w == 1) acc = acc.add(sg.neg());
         Fp zi = vliw::fp_inv_bingcd(acc.z), zi2 = zi.sqr();
         G1Affine a = acc.is_identity() ? G1Affine{Fp::zero(), Fp::zero(), 1} : G1Affine{acc.x * zi2, acc.y * zi2 * zi, 0};
-        if (t == 0 && !a.inf) a.y = a.y.neg();     // -A
-        pts[t] = a;
+        if (w == 0 && !a.inf) a.y = a.y.neg();     // -A
+        pts[w] = a;
     }
     __syncthreads();
     vliw::Lanes L{t, kFinalThreads, tab, ticks};
