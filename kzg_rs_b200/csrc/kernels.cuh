@@ -300,9 +300,10 @@ __global__ void __launch_bounds__(kEvalThreads, 6) eval_kernel(const uint8_t* __
 // ------------------------------------------------------------------------------------------------ K4
 // G1 decompression + subgroup check for commitments and proofs (reference src/kzg_proof.rs:17-25), as two kernels:
 // the decompression (Fp square root) produces the affine points the MSM needs; the subgroup check (two 64-bit scalar
-// multiplications, ~2/3 of the work) only feeds the error flags.  Both run on a low-priority stream beside the hashing.
-// (Measured: deferring the subgroup checks into the latency-bound tail -- transcript, MSM, pairing -- costs more than it
-// saves: the bucket and pairing kernels slow down by more than the checks take.)
+// multiplications, ~2/3 of the work) only feeds the error flags.  The decompression runs on a low-priority stream beside
+// the hashing; the subgroup checks are deferred beside the latency-bound tail (window sums, Horner, pairing) on SMs of their
+// own -- sharing SMs with the tail's few CTAs costs more than the deferral saves, so the host keeps the two apart with a
+// shared-memory reservation (kzgb200.cu, launch_lincomb).
 // One thread per point; points [0,n) are commitments, [n,2n) proofs.
 __global__ void __launch_bounds__(128) g1_decompress_kernel(const uint8_t* __restrict__ commitments, const uint8_t* __restrict__ proofs, int n,
                                                             G1Affine* __restrict__ C, G1Affine* __restrict__ P, uint32_t* __restrict__ status,
@@ -460,10 +461,10 @@ __global__ void __launch_bounds__(32) transcript_chain_kernel(const uint32_t* __
     }
 }
 
-// K5' (optional, opt-in): the same transcript hashed as a two-level tree.  Leaf j = SHA-256 of entries
-// [64 j, 64 j + 64) (each entry = C_i | z_i LE | y_i LE | pi_i, 160 bytes); root = SHA-256(domain | u64be 4096 |
-// u64be n | leaf digests).  The leaves hash in parallel, so the serial part shrinks from 2.5 to 0.008 SHA blocks
-// per blob.  r then differs from kzg-rs's r (the verdict does not: both are Fiat-Shamir challenges over the
+// K5' (optional, opt-in): the same transcript hashed as a three-level tree.  Leaf j = SHA-256 of entries
+// [16 j, 16 j + 16) (each entry = C_i | z_i LE | y_i LE | pi_i, 160 bytes); middle m = SHA-256 of leaf digests
+// [32 m, 32 m + 32); root = SHA-256(domain | u64be 4096 | u64be n | middle digests).  Leaves and middle hashes run in
+// parallel, so the dependent chain shrinks from 2.5 compressions per blob to 40 + 17 + 18 in total at n = 16384.  r then differs from kzg-rs's r (the verdict does not: both are Fiat-Shamir challenges over the
 // same data), so this mode is NOT the default; see DESIGN.md "transcript modes".
 constexpr int kTreeGroup = 16;      // transcript entries (160 B each) per leaf hash: 40 compressions
 constexpr int kTreeMid = 32;        // leaf digests per middle-level hash: 17 compressions

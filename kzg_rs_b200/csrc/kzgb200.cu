@@ -190,7 +190,8 @@ extern "C" void kzgb200_destroy(kzgb200_ctx* ctx) {
 extern "C" const char* kzgb200_last_error(const kzgb200_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 
 // ---- phases ---------------------------------------------------------------------------------------------------
-// Streams: `stream` (main: transcript, MSM, pairing, result), `s_aux` (G1 parsing, runs beside the hashing),
+// Streams: `stream` (main: transcript, MSM, pairing, result), `s_aux` (G1 decompression beside the hashing; the subgroup
+// checks beside the tail, see launch_lincomb),
 // `s_work[k]` (per-chunk challenge -> evaluation), `s_copy` (host->device blob chunks).  A device-resident batch is one
 // chunk (the per-blob SHA-256 chain is latency-bound: splitting it buys nothing); a host batch is cut into chunks so
 // that hashing / evaluation / the serial transcript chain of chunk c overlap the PCIe copy of chunk c+1.
