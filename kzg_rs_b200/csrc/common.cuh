@@ -1,0 +1,128 @@
+// Shared declarations of the sm_100a kernels of the kzg-rs verification hot path (K1..K8 of SURVEY.md section 2.1):
+// constants, device-resident structures, small load helpers and the prototypes of every kernel.  The kernels live in
+// k_*.cu (one translation unit per group so that they compile in parallel); kzgb200.cu is the host runtime.
+#pragma once
+#include <cuda_runtime.h>
+#include "sha256.cuh"
+#include "verify.cuh"
+#include "vliw.cuh"
+#include "glv.cuh"
+
+namespace kzgb200 {
+
+constexpr int kFieldElementsPerBlob = 4096;       // reference src/consts.rs:7
+constexpr int kBytesPerBlob = 4096 * 32;          // src/consts.rs:8
+constexpr uint32_t kErrBlob = 1, kErrCommitment = 2, kErrProof = 4, kErrScalar = 8;
+// canonical (non-Montgomery) z_i, y_i; the memory image is 2 x 32 little-endian bytes, which is exactly what
+// the batch transcript hashes (reference src/kzg_proof.rs:320-328) and what ranks exchange
+struct ZY { Fr z, y; };
+
+// Device-resident trusted-setup tables (K8; replaces KzgSettings::load_trusted_setup_file,
+// reference src/trusted_setup.rs:94-98 and build.rs:131-170).
+struct DeviceTables {
+    // twiddle[g] = roots_of_unity[2g] = omega^bitrev12(2g), Montgomery form.  In the bit-reversed domain the
+    // group of 2^(k+1) consecutive points starting at index a has prod (z - w_i) = z^(2^(k+1)) - w_a^(2^(k+1)),
+    // and w_a^(2^k) = roots_of_unity[2g] for g = a >> (k+1), independent of the level k.
+    Fr twiddle[2048];
+    // the same twiddles in the order thread t of eval_kernel consumes them (post-order over its 32-leaf subtree): 31 per
+    // thread + 1 pad, so the stream is sequential and the next one can be fetched while the current merge runs
+    Fr twiddle_po[128][32];
+    PairingTables pairing;
+    // fixed-base table of the G1 generator: gen_table[w][d-1] = [d * 16^w] G, d = 1..15, w < 64
+    G1Affine gen_table[64][15];
+    uint32_t setup_ok;
+};
+
+// ---- launch shapes shared by kernels and host ---------------------------------------------------------------
+#ifndef KSHA_THREADS
+#define KSHA_THREADS 32
+#endif
+constexpr int kShaThreads = KSHA_THREADS;     // blobs (threads) per CTA of K2
+constexpr int kEvalThreads = 128;
+constexpr int kLeavesPerThread = kFieldElementsPerBlob / kEvalThreads;  // 32
+constexpr int kTreeGroup = 16;      // transcript entries (160 B each) per leaf hash: 40 compressions
+constexpr int kTreeMid = 32;        // leaf digests per middle-level hash: 17 compressions
+constexpr int kWindows = 16, kBuckets = 256, kMsmSets = 3, kDigitRows = 4 * kWindows;   // rows: (kind r|rz) x (half lo|hi) x window
+constexpr int kBucketSplit = 4;
+constexpr int kWinLanes = 64, kWinPer = kBuckets / kWinLanes;     // 64 lanes x 4 buckets: 48 CTAs still fit the tail's 8 SMs in one wave
+constexpr int kFinalThreads = 64;
+constexpr int kHarnessMaxDegree = 16;
+constexpr int kLagWindows = 32, kLagEntries = 255;
+
+__device__ __forceinline__ Fr load_fe_be(const uint4* p) {
+    uint4 hi = __ldg(p), lo = __ldg(p + 1);   // 32 big-endian bytes: hi holds the most significant 16
+    Fr f;
+    f.l[7] = sha_bswap(hi.x); f.l[6] = sha_bswap(hi.y); f.l[5] = sha_bswap(hi.z); f.l[4] = sha_bswap(hi.w);
+    f.l[3] = sha_bswap(lo.x); f.l[2] = sha_bswap(lo.y); f.l[1] = sha_bswap(lo.z); f.l[0] = sha_bswap(lo.w);
+    return f;
+}
+__device__ __forceinline__ Fr ldg_fr(const Fr* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    Fr f;
+    f.l[0] = a.x; f.l[1] = a.y; f.l[2] = a.z; f.l[3] = a.w; f.l[4] = b.x; f.l[5] = b.y; f.l[6] = b.z; f.l[7] = b.w;
+    return f;
+}
+
+// per-rank partial result exchanged between ranks (the payload of the allgather)
+struct Partial {
+    G1 a, b;          // sum r_i pi_i ; sum (r_i C_i + r_i z_i pi_i)
+    Fr ry;            // sum r_i y_i (normal form)
+    uint32_t err;     // OR of the per-blob error flags of this rank
+    uint32_t pad[7];
+};
+
+// dynamic shared memory of the final kernels: engine register file, program tables, G1 tree scratch (> 48 KB: opt-in)
+struct FinalSmem {
+    Fp regs[vliw::kTotalRegs];
+    G1 sm[kFinalThreads];
+    vliw::SharedTables stab;
+};
+
+// ---- kernels (k_*.cu) ----------------------------------------------------------------------------------------
+__global__ void setup_tables_kernel(DeviceTables* T, const uint8_t* g2_points);
+__global__ void challenge_kernel(const uint8_t* __restrict__ blobs, const uint8_t* __restrict__ commitments, int n, Fr* __restrict__ z_mont,
+                                 ZY* __restrict__ zy, Fr* __restrict__ zpow, uint32_t one);
+__global__ void eval_kernel(const uint8_t* __restrict__ blobs, int n, const Fr* __restrict__ zpow, const DeviceTables* __restrict__ T,
+                            ZY* __restrict__ zy, uint32_t* __restrict__ status);
+__global__ void g1_decompress_kernel(const uint8_t* __restrict__ commitments, const uint8_t* __restrict__ proofs, int n, G1Affine* __restrict__ C,
+                                     G1Affine* __restrict__ P, uint32_t* __restrict__ status, bool with_subgroup_check);
+__global__ void g1_subgroup_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P, int n, uint32_t* __restrict__ status);
+__global__ void transcript_schedule_kernel(const uint8_t* __restrict__ commitments, const ZY* __restrict__ zy, const uint8_t* __restrict__ proofs,
+                                           uint64_t n, uint32_t* __restrict__ wk, uint64_t first_blk, uint64_t blk_count);
+__global__ void transcript_chain_kernel(const uint32_t* __restrict__ wk_all, uint64_t n, Fr* __restrict__ r_mont, uint32_t* __restrict__ state,
+                                        uint64_t first_blk, uint64_t blk_count);
+__global__ void transcript_words_kernel(const uint8_t* __restrict__ commitments, const ZY* __restrict__ zy, const uint8_t* __restrict__ proofs,
+                                        uint64_t first_entry, uint64_t entry_count, uint32_t* __restrict__ words);
+__global__ void transcript_tree_leaf_words_kernel(const uint32_t* __restrict__ words, uint64_t n, uint32_t* __restrict__ digests,
+                                                  uint64_t first_group, uint64_t group_count);
+__global__ void transcript_tree_root_kernel(const uint32_t* __restrict__ digests, uint64_t n, uint32_t* __restrict__ mid, Fr* __restrict__ r_mont);
+__global__ void msm_scalars_kernel(const Fr* __restrict__ z_mont, const ZY* __restrict__ zy, const Fr* __restrict__ r_mont, uint64_t offset, int n,
+                                   uint8_t* __restrict__ digits, Fr* __restrict__ ry);
+__global__ void msm_sort_kernel(const uint8_t* __restrict__ digits, int n, uint32_t* __restrict__ order, uint32_t* __restrict__ start);
+__global__ void msm_bucket_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P, int n, const uint32_t* __restrict__ order,
+                                  const uint32_t* __restrict__ start, G1* __restrict__ buckets);
+__global__ void msm_window_kernel(const G1* __restrict__ buckets, G1* __restrict__ windows);
+__global__ void msm_combine_kernel(const G1* __restrict__ windows, const Fr* __restrict__ ry, const uint32_t* __restrict__ status, int n,
+                                   Partial* __restrict__ out);
+__global__ void batch_final_kernel(const Partial* __restrict__ parts, int nparts, const DeviceTables* __restrict__ T, uint32_t* __restrict__ result,
+                                   long long* __restrict__ ticks);
+__global__ void single_final_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P, const ZY* __restrict__ zy,
+                                    const uint32_t* __restrict__ status, const DeviceTables* __restrict__ T, uint32_t* __restrict__ result);
+__global__ void verify_many_kernel(const uint8_t* __restrict__ c, const uint8_t* __restrict__ z, const uint8_t* __restrict__ y,
+                                   const uint8_t* __restrict__ p, size_t m, const DeviceTables* __restrict__ T, uint8_t* __restrict__ verdicts);
+__global__ void export_scalars_kernel(const ZY* __restrict__ zy, int n, uint8_t* __restrict__ z_out, uint8_t* __restrict__ y_out);
+__global__ void r_to_raw_kernel(const Fr* __restrict__ r_mont, ZY* __restrict__ out);
+__global__ void status_or_kernel(const uint32_t* __restrict__ status, int n, uint32_t* __restrict__ out);
+__global__ void harness_parse_points_kernel(const uint8_t* bytes, int n, G1Affine* out, uint32_t* bad);
+__global__ void harness_blob_kernel(uint64_t seed, int n, int D, const DeviceTables* __restrict__ T, uint8_t* __restrict__ blobs);
+__global__ void harness_commit_kernel(uint64_t seed, int n, int D, const G1Affine* __restrict__ M, const Fr* __restrict__ z_mont,
+                                      uint8_t* __restrict__ out, int want_proof);
+__global__ void lag_parse_kernel(const uint8_t* __restrict__ bytes, G1Affine* __restrict__ out, uint32_t* __restrict__ bad);
+__global__ void lag_table_kernel(const G1Affine* __restrict__ L, G1* __restrict__ table);
+__global__ void blob_scalars_kernel(const uint8_t* __restrict__ blobs, int n, Fr* __restrict__ scalars, uint32_t* __restrict__ status);
+__global__ void quotient_kernel(const uint8_t* __restrict__ blobs, int n, const Fr* __restrict__ z_mont, const ZY* __restrict__ zy,
+                                const DeviceTables* __restrict__ T, Fr* __restrict__ scalars);
+__global__ void lag_msm_kernel(const Fr* __restrict__ scalars, int n, const G1* __restrict__ table, uint8_t* __restrict__ out48);
+
+}  // namespace kzgb200

@@ -1,0 +1,155 @@
+// K6: random linear combination (Pippenger MSM with GLV).
+#include "common.cuh"
+#include "coop.cuh"
+
+namespace kzgb200 {
+
+// ------------------------------------------------------------------------------------------------ K6
+// Random linear combination (reference src/kzg_proof.rs:399-433), regrouped so that it needs no per-blob
+// [y_i]G:   A = sum r_i pi_i ,  B = sum (r_i C_i + (r_i z_i) pi_i) - [sum r_i y_i] G ,  r_i = r^(offset+i).
+// v1: one thread per blob does its scalar multiplications (Shamir's trick for the pair), results are then
+// tree-summed by pair_sum_kernel.
+// Pippenger bucket method with the GLV split: every scalar k = k1 + k2 x^2 (glv.cuh), so a point P contributes
+// [k1]P + [k2](-phi(P)) with two 128-bit halves -> 16 windows of 8 bits x 255 buckets.  Three point/scalar sets per rank:
+//   set 0: pi_i with r_i  (-> A),   set 1: C_i with r_i,   set 2: pi_i with r_i z_i   (sets 1+2 -> B').
+// No sorting network and no atomics on points: a counting sort of the digits per (scalar kind, half, window) gives
+// every bucket two contiguous index lists (low halves -> P_i, high halves -> -phi(P_i)); threads own buckets.
+__global__ void __launch_bounds__(128) msm_scalars_kernel(const Fr* __restrict__ z_mont, const ZY* __restrict__ zy, const Fr* __restrict__ r_mont,
+                                                          uint64_t offset, int n, uint8_t* __restrict__ digits /* [4*16][n] */,
+                                                          Fr* __restrict__ ry) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t e = offset + (uint64_t)i;
+    uint32_t ee[2] = {(uint32_t)e, (uint32_t)(e >> 32)};
+    Fr ri = r_mont->pow(ee, 64);              // r^(offset+i), Montgomery   (compute_powers, kzg_proof.rs:279-289)
+    Fr ri_raw = ri.to_raw();
+    Fr rz_raw = (ri * z_mont[i]).to_raw();    // r_i z_i   (kzg_proof.rs:425)
+    ry[i] = ri * zy[i].y;                     // r_i y_i in normal form
+    uint32_t h[2][2][4];
+    glv_split(ri_raw.l, h[0][0], h[0][1]);
+    glv_split(rz_raw.l, h[1][0], h[1][1]);
+    for (int kind = 0; kind < 2; kind++)
+        for (int half = 0; half < 2; half++)
+            for (int w = 0; w < kWindows; w++)
+                digits[((size_t)(kind * 2 + half) * kWindows + w) * n + i] = (uint8_t)(h[kind][half][w >> 2] >> (8 * (w & 3)));
+}
+// counting sort of one digit row: grid = kDigitRows; order[row][*] = blob indices grouped by digit,
+// start[row][b] = first position of digit b (start[row][256] = n)
+__global__ void __launch_bounds__(256) msm_sort_kernel(const uint8_t* __restrict__ digits, int n, uint32_t* __restrict__ order,
+                                                       uint32_t* __restrict__ start) {
+    __shared__ uint32_t hist[kBuckets], cursor[kBuckets];
+    int row_id = blockIdx.x, t = threadIdx.x;
+    const uint8_t* row = digits + (size_t)row_id * n;
+    uint32_t* ord = order + (size_t)row_id * n;
+    uint32_t* st = start + (size_t)row_id * (kBuckets + 1);
+    hist[t] = 0;
+    __syncthreads();
+    for (int i = t; i < n; i += blockDim.x) atomicAdd(&hist[row[i]], 1u);
+    __syncthreads();
+    if (t == 0) {
+        uint32_t acc = 0;
+        for (int b = 0; b < kBuckets; b++) { cursor[b] = acc; st[b] = acc; acc += hist[b]; }
+        st[kBuckets] = acc;
+    }
+    __syncthreads();
+    for (int i = t; i < n; i += blockDim.x) ord[atomicAdd(&cursor[row[i]], 1u)] = (uint32_t)i;
+}
+// four threads per (set, window, bucket b >= 1): threads 0,1 walk the low-half list (points P_i), threads 2,3 the
+// high-half list (points -phi(P_i)), each taking every second entry; a shared-memory tree joins the four partial sums
+// (splitting the lists shortens the serial chain of point additions between "r is known" and the pairing check)
+__global__ void __launch_bounds__(128) msm_bucket_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P, int n,
+                                                         const uint32_t* __restrict__ order, const uint32_t* __restrict__ start,
+                                                         G1* __restrict__ buckets /* [3][16][256] */) {
+    __shared__ G1 sm[128];
+    int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    int bucket_id = tid / kBucketSplit, part = tid % kBucketSplit;
+    bool live = bucket_id < kMsmSets * kWindows * kBuckets;
+    G1 acc = G1::identity();
+    if (live) {
+        int b = bucket_id % kBuckets, w = (bucket_id / kBuckets) % kWindows, set = bucket_id / (kBuckets * kWindows);
+        int kind = set == 2 ? 1 : 0, half = part >> 1;
+        const G1Affine* pts = set == 1 ? C : P;
+        int row_id = (kind * 2 + half) * kWindows + w;
+        const uint32_t* ord = order + (size_t)row_id * n;
+        const uint32_t* st = start + (size_t)row_id * (kBuckets + 1);
+        if (b != 0) {
+            uint32_t lo = st[b], hi = st[b + 1];
+            for (uint32_t k = lo + (part & 1); k < hi; k += 2) {
+                G1Affine q = pts[ord[k]];
+                acc = acc.add_mixed(half ? glv_endo_neg(q) : q);
+            }
+        }
+    }
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    if (part < 2) sm[threadIdx.x] = sm[threadIdx.x].add(sm[threadIdx.x + 2]);
+    __syncthreads();
+    if (part == 0 && live) buckets[bucket_id] = sm[threadIdx.x].add(sm[threadIdx.x + 1]);
+}
+// two warps per (set, window): W = sum_b b * bucket[b].  Lane l owns buckets 4l .. 4l+3 (running-sum trick inside
+// the segment, then the segment's offset 8l by a short double-and-add), then a shared-memory tree over the lanes.
+__global__ void __launch_bounds__(kWinLanes) msm_window_kernel(const G1* __restrict__ buckets, G1* __restrict__ windows /* [3][16] */) {
+    __shared__ G1 sm[kWinLanes];
+    int l = threadIdx.x, sw = blockIdx.x;          // sw = set * kWindows + window
+    const G1* bk = buckets + (size_t)sw * kBuckets + kWinPer * l;
+    G1 run = G1::identity(), acc = G1::identity();
+    for (int j = kWinPer - 1; j >= 0; j--) {
+        run = run.add(bk[j]);                      // bucket 0 holds the identity
+        acc = acc.add(run);                        // after the loop: acc = sum_j (j+1) bk[j], run = sum_j bk[j]
+    }
+    // sum_j (kWinPer l + j) bk[j] = acc + (kWinPer l - 1) run
+    uint32_t k[1] = {(uint32_t)(kWinPer * l)};
+    G1 off = scalar_mul(run, k, 8);
+    sm[l] = acc.add(off).add(run.neg());
+    __syncthreads();
+    for (int span = kWinLanes / 2; span >= 1; span >>= 1) {
+        if (l < span) sm[l] = sm[l].add(sm[l + span]);
+        __syncthreads();
+    }
+    if (l == 0) windows[sw] = sm[0];
+}
+// window sums -> A = sum_w 256^w W[0][w], B' = sum_w 256^w (W[1][w] + W[2][w]) (Horner, 8 doublings per window):
+// warp 0 does A, warp 1 does B' with the cooperative point operations above; the other warps OR the per-blob error
+// flags and tree-sum the r_i y_i.
+__global__ void __launch_bounds__(256) msm_combine_kernel(const G1* __restrict__ windows, const Fr* __restrict__ ry, const uint32_t* __restrict__ status,
+                                                          int n, Partial* __restrict__ out) {
+    __shared__ uint32_t s_err;
+    __shared__ Fr s_ry[256];
+    __shared__ CoopPoint cp[3];
+    int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    if (t == 0) s_err = 0;
+    __syncthreads();
+    if (warp < kMsmSets) {
+        // warps 0..2: Horner recombination of one point set each (15 x 8 doublings + 16 additions, the serial part of the tail)
+        CoopPoint* s = &cp[warp];
+        if (lane == 0) { s->v[0] = Fp::one(); s->v[1] = Fp::one(); s->v[2] = Fp::zero(); }
+        __syncwarp();
+        for (int w = kWindows - 1; w >= 0; w--) {
+            if (w != kWindows - 1) for (int k = 0; k < 8; k++) coop_dbl(s, lane);
+            coop_add(s, windows[warp * kWindows + w], lane);
+        }
+    } else {
+        // warps 3..7, beside the recombination: OR of the per-blob error flags and sum r_i y_i
+        constexpr int kHelpers = 256 - 32 * kMsmSets;
+        int h = t - 32 * kMsmSets;
+        uint32_t e = 0;
+        Fr acc_ry = Fr::zero();
+        for (int i = h; i < n; i += kHelpers) { e |= status[i]; acc_ry = acc_ry.add_inl(ry[i]); }
+        if (e) atomicOr(&s_err, e);
+        s_ry[h] = acc_ry;
+        asm volatile("bar.sync 1, %0;" ::"n"(kHelpers) : "memory");
+        for (int span = 128; span >= 1; span >>= 1) {
+            if (h < span && h + span < kHelpers) s_ry[h] = s_ry[h].add_inl(s_ry[h + span]);
+            asm volatile("bar.sync 1, %0;" ::"n"(kHelpers) : "memory");
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {          // B' = set 1 + set 2
+        G1 q = {cp[2].v[0], cp[2].v[1], cp[2].v[2]};
+        coop_add(&cp[1], q, lane);
+    }
+    if (warp < 2 && lane == 0) { G1 r = {cp[warp].v[0], cp[warp].v[1], cp[warp].v[2]}; if (warp == 1) out->b = r; else out->a = r; }
+    if (t == 0) { out->ry = s_ry[0]; out->err = s_err; }
+}
+
+}  // namespace kzgb200

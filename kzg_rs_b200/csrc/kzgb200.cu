@@ -10,7 +10,7 @@
 #include <mutex>
 #include <new>
 #include "../../include/kzgb200.h"
-#include "kernels.cuh"
+#include "common.cuh"
 
 using namespace kzgb200;
 
