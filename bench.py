@@ -1,23 +1,27 @@
 #!/usr/bin/env python3
 """bench.py -- blobs verified / second through verify_blob_kzg_proof_batch (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--blobs B] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--blobs B] [--impl b200|reference] [--config batch|tuples]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-A step = one verify_blob_kzg_proof_batch over B synthetic blobs per GPU (default 16384 = 2 GiB of blob
-bytes per GPU, BASELINE.json configs[3]); with N ranks the batch is N*B blobs sharded by contiguous ranges,
-(z,y) and the per-rank partial sums are exchanged with NCCL allgathers and every rank runs the final pairing
-check ("scaling": "weak").  `value` times the step with inputs resident in HBM; `e2e` times the same call
-from pinned HOST buffers (host->device copies inside the timed region).  Timing: CUDA events on the library's
-stream, barrier + synchronize on both sides, max over ranks.
+A step = one blocking verify_blob_kzg_proof_batch over B synthetic blobs per GPU (default 16384 = 2 GiB of blob bytes per
+GPU, BASELINE.json configs[3]) in the library's DEFAULT mode: exact transcript, r bit-identical to kzg-rs.  With N ranks the
+batch is N*B blobs sharded by contiguous ranges through the library's group API (csrc/group.cu: transcript entries to the
+leader's host hash, partial sums stored over NVLink into the leader GPU, one pairing check) -- `value`, "scaling": "weak";
+the `strong` record beside it runs BASELINE's fixed 16384 blobs TOTAL split over the N GPUs.  `value` times the step with
+inputs resident in HBM; `e2e` times the same call from pinned HOST buffers (host->device copies inside the timed region), with
+a pageable-memory leg and the PCIe roofline beside it.  Timing: CUDA events on the library's stream, barrier + synchronize
+on both sides, max over ranks.
 
---impl reference times the reference's CPU algorithm (the C oracle port, kind "port": the Rust crate cannot be
-built here) with all host threads on a bounded sample of the same workload.
+--impl reference times the reference's CPU algorithm (the C oracle port, kind "port": the Rust crate cannot be built here)
+with all host threads on the same number of blobs per step; it does not load libkzgb200.so.
+--config tuples: BASELINE configs[4], m independent verify_kzg_proof tuples (checks / second).
 """
 import argparse
 import ctypes as C
 import json
+import math
 import os
 import subprocess
 import sys
@@ -28,9 +32,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 BLOB = 131072
 ALGO_BYTES_PER_BLOB = 131072 + 48 + 48
-# dram__bytes_read.sum + dram__bytes_write.sum per launch at 16384 blobs from the ncu --set full captures under profiles/
-TRAFFIC_BYTES = {"challenge_sha256": 2148375000 + 4876800, "evaluate_barycentric": 2154585000 + 4713984}   # profiles/ncu_full_r01_summary.txt
-PHASES = ["parse_g1", "challenge_sha256", "evaluate_barycentric", "transcript_r", "lincomb_terms", "reduce", "final_pairing"]
+PHASES = ["g1_decompress", "challenge_sha256", "evaluate_barycentric", "transcript_r_exposed", "lincomb_terms", "reduce", "final_pairing",
+          "g1_subgroup_deferred"]
+Q = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+DTYPE = "u32-limb modular integer (Fr 255-bit / Fp 381-bit) + SHA-256"
+METRIC = "blobs verified/sec (verify_blob_kzg_proof_batch)"
 
 
 def parse_args():
@@ -38,11 +44,13 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--blobs", type=int, default=16384, help="blobs per GPU")
+    ap.add_argument("--blobs", type=int, default=16384, help="blobs per GPU (weak record); the strong record splits this many over all GPUs")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=8192, help="blobs in the CPU-baseline sample (~19 s of CPU work)")
+    ap.add_argument("--config", default="batch", choices=["batch", "tuples"])
+    ap.add_argument("--tuples", type=int, default=1000000, help="--config tuples: number of (C, z, y, proof) tuples")
+    ap.add_argument("--cpu-sample", type=int, default=4096, help="blobs in the CPU-baseline sample of the b200 arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-pipeline", action="store_true", help="skip the streaming front-end measurement")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (transcript modes, pipeline, pageable leg)")
     ap.add_argument("--inflight", type=int, default=2, help="batches in flight in the streaming front-end measurement")
     ap.add_argument("--lowdegree-blobs", action="store_true",
                     help="blobs = evaluations of random degree<8 polynomials (cheap generator) instead of uniformly random "
@@ -103,16 +111,51 @@ def bind_to_gpu_numa_node(index):
     return None
 
 
+def workload_config(args, n, world, reference=False):
+    cfg = {"workload": "verify_blob_kzg_proof_batch on %d synthetic blobs per GPU (%d total, %.2f GiB of blob bytes per GPU), "
+                       "BASELINE.json configs[3]" % (n, n * world, n * BLOB / 2**30),
+           "blobs_per_gpu": n, "total_blobs": n * world, "parallelism": "blob-sharded x%d" % world,
+           "cache": "inputs (>= 2 GiB per step) are larger than the 126 MB L2",
+           "transcript": "exact (library default: r bit-identical to kzg-rs compute_r_powers)"}
+    if reference:
+        cfg["generator"] = ("64 distinct uniformly random blobs, commitments / proofs by the oracle's commit/prove over the mainnet setup, "
+                            "repeated to %d blobs (the verifier does identical work for every blob; no result is cached)" % n)
+    else:
+        cfg["generator"] = ("uniformly random field elements, commitments/proofs by the GPU commit/prove path over the mainnet setup" if not args.lowdegree_blobs
+                            else "harness: random degree<8 polynomials in evaluation form, commitments/proofs over the mainnet setup, seed 0x4B5A47")
+    return cfg
+
+
+def oracle_workload(n, distinct=64):
+    """Reference arm's inputs without any GPU code: `distinct` uniformly random blobs with oracle-side commitments / proofs, tiled."""
+    import random
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    rnd = random.Random(0x4B5A47)
+    distinct = min(distinct, n)
+    blobs = [b"".join(rnd.randrange(Q).to_bytes(32, "big") for _ in range(4096)) for _ in range(distinct)]
+
+    def make(blob):
+        c = O.blob_to_kzg_commitment(blob)
+        return blob, c, O.compute_blob_kzg_proof(blob, c)
+    O.lib()
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:      # ctypes releases the GIL
+        uniq = list(ex.map(make, blobs))
+    seq = [uniq[i % distinct] for i in range(n)]
+    return b"".join(x[0] for x in seq), b"".join(x[1] for x in seq), b"".join(x[2] for x in seq)
+
+
 def run_reference(args, rank, world):
-    """The reference's CPU path (oracle port), all host threads, bounded sample per step."""
+    """The reference's CPU path (oracle port), all host threads, the same number of blobs per step as the b200 arm."""
     if rank != 0:
         return
     from oracle import oracle as O
-    import torch
     O.build()
     cores = os.cpu_count() or 1
-    n = min(args.blobs, args.cpu_sample)
-    blobs, cs, ps = make_workload_host(args, n)
+    if args.config == "tuples":
+        return run_reference_tuples(args, O, cores)
+    n = args.blobs
+    blobs, cs, ps = oracle_workload(n)
     times = []
     for i in range(args.warmup + args.steps):
         t = time.perf_counter()
@@ -123,25 +166,140 @@ def run_reference(args, rank, world):
             times.append(dt)
     ms = 1e3 * sum(times) / len(times)
     val = n / (ms / 1e3)
-    sample = "%d of %d blobs per step (same generator/seed), %d threads, SHA-NI=%d" % (n, args.blobs, cores, O.lib().kzgo_sha256_uses_shani())
+    sample = "%d blobs per step (the b200 arm's size), %d threads (blob-parallel; the reference itself is single-threaded), SHA-NI=%d" % (
+        n, cores, O.lib().kzgo_sha256_uses_shani())
     print(json.dumps({
-        "impl": "reference", "metric": "blobs verified/sec (verify_blob_kzg_proof_batch)", "value": val, "unit": "blobs/s",
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "blobs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32-limb modular integer (Fr 255-bit / Fp 381-bit) + SHA-256", "data": "synthetic",
-        "config": workload_config(args, n, world),
+        "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+        "config": workload_config(args, n, world, reference=True),
         "cpu_baseline": {"value": val, "unit": "blobs/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "blobs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def workload_config(args, n, world):
-    return {"workload": "verify_blob_kzg_proof_batch on %d synthetic blobs per GPU (%d total, %.2f GiB of blob bytes per GPU), "
-                        "BASELINE.json configs[3]" % (n, n * world, n * BLOB / 2**30),
-            "blobs_per_gpu": n, "total_blobs": n * world, "parallelism": "blob-sharded x%d" % world,
-            "generator": ("uniformly random field elements, commitments/proofs by the GPU commit/prove path over the mainnet setup" if not args.lowdegree_blobs
-                          else "harness: random degree<8 polynomials in evaluation form, commitments/proofs over the mainnet setup, seed 0x4B5A47"),
-            "cache": "inputs (>= 2 GiB per step) are larger than the 126 MB L2"}
+# ------------------------------------------------------------------------------------------------ config 5: tuples
+def make_tuples(m, seed=0x7e57):
+    """BASELINE configs[4] / SURVEY 8d: m (C, z, y, pi) tuples without per-tuple MSMs: C = aG + bT, y = a + b z, pi = bG with T = [tau]G1
+    (then e(C - yG, G2) = e(pi, [tau - z]G2)); ~1 % negatives (y + 1), ~0.1 % malformed (z >= q).  Built from a pool of 256 distinct
+    (a, b) pairs with fresh z per tuple -- points are pooled (host-side scalar multiplications in Python are slow), scalars are not.
+    Returns (commitments, zs, ys, proofs, expected verdict bytes)."""
+    import random
+    from oracle import oracle as O
+    from oracle import pyref as R
+    rnd = random.Random(seed)
+    T = R.g1_from_compressed(O.tau_power_g1(1))[1]
+    pool = []
+    for _ in range(256):
+        a, b = rnd.randrange(Q), rnd.randrange(Q)
+        pool.append((a, b, R.g1_to_compressed(R.g1_add(R.g1_mul(R.G1_GEN, a), R.g1_mul(T, b))), R.g1_to_compressed(R.g1_mul(R.G1_GEN, b))))
+    cs, zs, ys, ps, want = bytearray(), bytearray(), bytearray(), bytearray(), bytearray()
+    for i in range(m):
+        a, b, c48, p48 = pool[rnd.randrange(256)]
+        z = rnd.randrange(Q)
+        y = (a + b * z) % Q
+        v = 1
+        u = rnd.random()
+        if u < 0.01:
+            y, v = (y + 1) % Q, 0
+        elif u < 0.011:
+            z, v = Q + rnd.randrange(1000), 2
+        cs += c48; ps += p48
+        zs += z.to_bytes(32, "big"); ys += y.to_bytes(32, "big")
+        want.append(v)
+    return bytes(cs), bytes(zs), bytes(ys), bytes(ps), bytes(want)
 
 
+def run_reference_tuples(args, O, cores):
+    from concurrent.futures import ThreadPoolExecutor
+    m = min(args.tuples, 2048 * cores // 16 or 128)
+    cs, zs, ys, ps, want = make_tuples(m)
+
+    def one(i):
+        r = O.verify_kzg_proof(cs[48 * i:48 * i + 48], zs[32 * i:32 * i + 32], ys[32 * i:32 * i + 32], ps[48 * i:48 * i + 48])
+        return 2 if r is None else int(r)
+    times = []
+    O.lib()
+    for it in range(args.warmup + args.steps):
+        t = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=cores) as ex:
+            got = bytes(ex.map(one, range(m)))
+        dt = time.perf_counter() - t
+        assert got == want
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    val = m / (ms / 1e3)
+    print(json.dumps({"impl": "reference", "metric": "verify_kzg_proof checks/sec (independent tuples)", "value": val, "unit": "checks/s", "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": DTYPE, "data": "synthetic", "config": {"workload": "BASELINE.json configs[4]: independent verify_kzg_proof tuples", "tuples": m},
+                      "cpu_baseline": {"value": val, "unit": "checks/s", "cores": cores, "kind": "port", "sample": "%d tuples per step, %d threads" % (m, cores)},
+                      "e2e": {"value": val, "unit": "checks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def run_tuples(args, rank, world, local_rank):
+    """m independent verify_kzg_proof tuples per GPU (pure replicas across ranks: no exchange)."""
+    import torch
+    import kzg_rs_b200 as K
+    from kzg_rs_b200.api import Library
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = Library.get().dll
+    S = K.KzgSettings.load_trusted_setup_file()
+    ctx = S.context(local_rank)
+    m = args.tuples
+    cs, zs, ys, ps, want = make_tuples(m, seed=0x7e57 + rank)
+    pin = lambda b: torch.frombuffer(bytearray(b), dtype=torch.uint8).pin_memory()
+    hc, hz, hy, hp = pin(cs), pin(zs), pin(ys), pin(ps)
+    out = torch.empty(m, dtype=torch.uint8).pin_memory()
+    stream = torch.cuda.ExternalStream(lib.kzgb200_stream(ctx), device=torch.device("cuda", local_rank))
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    def step():
+        rc = lib.kzgb200_verify_kzg_proof_many(ctx, hc.data_ptr(), hz.data_ptr(), hy.data_ptr(), hp.data_ptr(), m, out.data_ptr())
+        assert rc == 0
+    for _ in range(max(args.warmup, 3)):
+        step()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    ok = out.numpy().tobytes() == want
+    kernel_ms = (C.c_float * 8)()
+    lib.kzgb200_get_phase_ms(ctx, kernel_ms)
+    if rank == 0:
+        val = m * world / (ms / 1e3)
+        # integer roofline: ~25 k Fp multiplications per check (SURVEY 8d) against the measured Fp multiplication rate of the chip
+        fp_mul_peak = 2.9e10
+        res = {"metric": "verify_kzg_proof checks/sec (independent tuples)", "value": val, "unit": "checks/s", "n_gpus": world, "steps": args.steps,
+               "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE,
+               "data": "synthetic", "config": {"workload": "BASELINE.json configs[4]: %d independent verify_kzg_proof tuples per GPU (160 B each), host buffers" % m,
+                                               "tuples_per_gpu": m, "negatives": "1 % wrong y, 0.1 % non-canonical z"},
+               "e2e": {"value": val, "unit": "checks/s", "ms_per_step": ms, "h2d_bytes_per_step": 160 * m * world, "d2h_bytes_per_step": m * world},
+               "verdicts_match_construction": ok, "clocks": sampler.summary(),
+               "roofline": {"bound": "integer (FMA-heavy pipe)", "achieved": val / world * 25000, "peak": fp_mul_peak, "unit": "Fp mul/s", "frac": val / world * 25000 / fp_mul_peak,
+                            "note": "~25 k Fp multiplications per check (SURVEY.md 8d) against the measured 2.9e10 Fp mul/s (profiles/intpipe_r01.txt)"}}
+        print(json.dumps(res))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ the batch path
 def make_workload_device(lib, ctx, args, n, rank):
     import torch
     import kzg_rs_b200 as K
@@ -164,25 +322,43 @@ def make_workload_device(lib, ctx, args, n, rank):
     return blobs, cs, ps
 
 
-def make_workload_host(args, n):
-    """Reference arm: same generator (GPU harness) when a GPU is present, else oracle-side commit/prove."""
-    import torch
-    if torch.cuda.is_available():
-        import kzg_rs_b200 as K
-        from kzg_rs_b200.api import Library
-        S = K.KzgSettings.load_trusted_setup_file()
-        b, c, p = make_workload_device(Library.get().dll, S.context(0), args, n, 0)
-        return b.cpu().numpy().tobytes(), c.cpu().numpy().tobytes(), p.cpu().numpy().tobytes()
-    from oracle import oracle as O
-    import random
-    rnd, Q = random.Random(0x4B5A47), 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
-    uniq = []
-    for _ in range(min(n, 4)):
-        blob = b"".join(rnd.randrange(Q).to_bytes(32, "big") for _ in range(4096))
-        c = O.blob_to_kzg_commitment(blob)
-        uniq.append((blob, c, O.compute_blob_kzg_proof(blob, c)))
-    seq = [uniq[i % len(uniq)] for i in range(n)]
-    return b"".join(x[0] for x in seq), b"".join(x[1] for x in seq), b"".join(x[2] for x in seq)
+def resident_chunks(n, mode):
+    """mirror of plan_chunks (csrc/kzgb200.cu) for resident inputs"""
+    if n < 2048 or mode == "tree":
+        return 1
+    if mode == "device":
+        return math.ceil(n / (math.ceil(math.ceil(n / 8) / 16) * 16))
+    k, lo, quarter = 0, 0, n // 4 // 16 * 16
+    while lo < n:
+        rem = n - lo
+        take = quarter if k < 3 else rem // 2 // 16 * 16
+        take = max(take, 256)
+        if rem - min(take, rem) < 256:
+            take = rem
+        k += 1
+        lo += take
+    return k
+
+
+def count_launches(n, resident, mode, world=1, leader=True):
+    """Kernels of libkzgb200.so launched by one batch on one rank (mirrors launch_phase1 / transcript_enqueue_chunk / launch_lincomb)."""
+    if resident:
+        chunks = resident_chunks(n, mode)
+        head = 1 + chunks                      # one challenge launch, evaluation per chunk
+    else:
+        chunks = math.ceil(n / (math.ceil(max(1024, math.ceil(n / 64)) / 16) * 16))
+        head = 2 * chunks
+    transcript = {"exact": 1, "tree": 2 * chunks + 1, "device": 2 * chunks}[mode]
+    tail = 5 + 1 + 1 if world == 1 else (5 + (3 if leader else 1))     # msm x5, pairing, flag merge | + wait_flags on the leader
+    return 2 + head + (1 if resident else 0) + transcript + tail        # 2 = G1 decompression + subgroup checks; export of z / y on resident calls
+
+
+def load_profiled_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels, from the committed ncu --set full summary of this round"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_full_r02_traffic.json")))
+    except Exception:
+        return {}
 
 
 def main():
@@ -192,7 +368,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    if args.config == "tuples":
+        return run_tuples(args, rank, world, local_rank)
 
+    import numpy as np
     import torch
     import kzg_rs_b200 as K
     from kzg_rs_b200.api import Library
@@ -203,11 +382,12 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))     # barrier / max over ranks only: not on the data path
     lib = Library.get().dll
     S = K.KzgSettings.load_trusted_setup_file()
-    ctx = S.context(local_rank)
     n = args.blobs
+    plan = sharded.ShardedBatch(lib, S, n, rank, world, local_rank, session=sharded.session_name() + "w")
+    ctx = plan.ctx
     d_blobs, d_cs, d_ps = make_workload_device(lib, ctx, args, n, rank)
     # pinned host copies for the end-to-end leg
     h_blobs = torch.empty(n * BLOB, dtype=torch.uint8).pin_memory()
@@ -215,8 +395,8 @@ def main():
     h_ps = torch.empty(n * 48, dtype=torch.uint8).pin_memory()
     h_blobs.copy_(d_blobs); h_cs.copy_(d_cs); h_ps.copy_(d_ps)
     torch.cuda.synchronize()
-    stream = torch.cuda.ExternalStream(lib.kzgb200_stream(ctx), device=torch.device("cuda", local_rank))
-    plan = sharded.ShardedBatch(lib, ctx, n, rank, world, dist)
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.ExternalStream(lib.kzgb200_stream(ctx), device=dev)
     lib.kzgb200_set_profiling(ctx, 1)
 
     def barrier():
@@ -224,27 +404,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
-        ok = plan.verify_device(d_blobs, d_cs, d_ps)
-        assert ok is True, "valid batch rejected"
-
-    def step_e2e():
-        ok = plan.verify_host(h_blobs, h_cs, h_ps)
-        assert ok is True, "valid batch rejected (e2e)"
-
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, st=stream, cx=ctx):
         for _ in range(warmup):
             fn()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        phase_acc = [0.0] * 7
+        e0.record(st)
+        phase_acc = [0.0] * 8
         for _ in range(steps):
             fn()
-            ph = (C.c_float * 7)()
-            lib.kzgb200_get_phase_ms(ctx, ph)
+            ph = (C.c_float * 8)()
+            lib.kzgb200_get_phase_ms(cx, ph)
             phase_acc = [a + b for a, b in zip(phase_acc, ph)]
-        e1.record(stream)
+        e1.record(st)
         barrier()
         ms = e0.elapsed_time(e1) / steps
         if dist is not None:
@@ -253,31 +425,65 @@ def main():
             ms = float(t.item())
         return ms, [a / steps for a in phase_acc]
 
-    # Headline = the throughput configuration: KZGB200_TRANSCRIPT_TREE (batch challenge r hashed as a 3-level tree; verdict, z,
-    # y identical to kzg-rs, r itself not).  The library default (EXACT: r bit-identical, one serial SHA-256 chain over all
-    # blobs of all ranks) is timed in the same run and reported under "exact_transcript".
+    def must(v, what):
+        assert v is True, "valid batch rejected (%s)" % what
+
+    W = max(args.warmup, 3)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    res = {}
-    for mode_name, mode in (("tree", 1), ("exact", 0)):
-        lib.kzgb200_set_transcript_mode(ctx, mode)
-        ms, phases = timed(step_resident, args.steps, max(args.warmup, 3))
-        ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
-        res[mode_name] = (ms, phases, ms_e2e)
-    # Streaming front-end (kzgb200_pipeline_*), single GPU: the same K batches through two contexts, two in
-    # flight, so the latency-bound tail of one batch runs under the head / the PCIe copy of the next.  Reported beside the
-    # headline (which stays one blocking call at a time).
+    # ---- headline: library default (exact transcript), one blocking call at a time ----------------------------------
+    plan.set_transcript_mode(0)
+    ms, phases = timed(lambda: must(plan.verify_device(d_blobs, d_cs, d_ps), "resident"), args.steps, W)
+    ms_e2e, _ = timed(lambda: must(plan.verify_host(h_blobs, h_cs, h_ps), "e2e pinned"), args.steps, W)
+    launches = args.steps * (count_launches(n, True, "exact", world, rank == 0) + count_launches(n, False, "exact", world, rank == 0))
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # PCIe roofline of the end-to-end leg: pinned host -> device copy of the same blob buffer, same run
+    d_tmp = torch.empty(n * BLOB, dtype=torch.uint8, device=dev)
+    best = 0.0
+    for _ in range(4):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        d_tmp.copy_(h_blobs, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, n * BLOB / (e0.elapsed_time(e1) / 1e3) / 1e9)
+    del d_tmp
+    pcie_peak = best
+
+    extras = {}
+    if not args.no_extras:
+        # pageable caller memory (an ordinary Vec<Blob>): the library's pinned staging ring
+        p_blobs = torch.from_numpy(np.empty(n * BLOB, dtype=np.uint8))
+        p_blobs.copy_(h_blobs)
+        ms_pg, _ = timed(lambda: must(plan.verify_host(p_blobs, h_cs, h_ps), "e2e pageable"), max(2, args.steps // 2), 2)
+        extras["pageable"] = ms_pg
+        del p_blobs
+        # the other transcript modes, same workload
+        for name, mode in (("tree", 1), ("device", 2)):
+            if world > 1 and mode == 2:
+                continue
+            plan.set_transcript_mode(mode)
+            st = args.steps if mode == 1 else min(args.steps, 3)
+            m1, ph1 = timed(lambda: must(plan.verify_device(d_blobs, d_cs, d_ps), name), st, 2)
+            m2 = timed(lambda: must(plan.verify_host(h_blobs, h_cs, h_ps), name + " e2e"), st, 2)[0] if mode == 1 else None
+            extras[name] = (m1, ph1, m2)
+        plan.set_transcript_mode(0)
+
+    # Streaming front-end (kzgb200_pipeline_*), single GPU, default transcript: several batches in flight
     pipelined = None
-    if world == 1 and not args.no_pipeline:
-        pipe_batches = max(args.steps, 12)      # enough batches for the ramp-up and drain not to dominate
-        with K.BatchPipeline(S, depth=args.inflight, device=local_rank, transcript_mode=1) as pipe:
+    if world == 1 and not args.no_extras:
+        pipe_batches = max(args.steps, 12)
+        with K.BatchPipeline(S, depth=args.inflight, device=local_rank) as pipe:
             def run(submit, steps):
-                tickets = [submit() for _ in range(steps)]        # submit blocks while two batches are in flight
+                tickets = [submit() for _ in range(steps)]
                 for t in tickets:
                     assert pipe.wait(t) is True, "valid batch rejected (pipeline)"
 
             def timed_pipe(submit):
-                run(submit, args.inflight * max(args.warmup, 3))    # warm-up on every context
+                run(submit, args.inflight * W)
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -286,23 +492,43 @@ def main():
                 e1.record()
                 torch.cuda.synchronize()
                 return e0.elapsed_time(e1) / pipe_batches
-
             ms_p = timed_pipe(lambda: pipe.submit_device(d_blobs, d_cs, d_ps, n))
             ms_pe = timed_pipe(lambda: pipe.submit(h_blobs, n, h_cs, n, h_ps, n))
         pipelined = {"in_flight": args.inflight, "value": n / (ms_p / 1e3), "ms_per_step": ms_p, "e2e": n / (ms_pe / 1e3), "e2e_ms_per_step": ms_pe,
-                     "unit": "blobs/s", "transcript": "tree", "batches": pipe_batches,
+                     "unit": "blobs/s", "transcript": "exact", "batches": pipe_batches,
                      "note": "kzgb200_pipeline_submit / _wait: every ticket is one verify_blob_kzg_proof_batch call; "
                              "`batches` batches, in_flight at a time, wall time of all of them (ramp-up and drain included) / batches"}
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
-    lib.kzgb200_set_transcript_mode(ctx, 1)
-    step_resident()
-    zy_sample = plan.last_zy_host(min(n, args.cpu_sample)) if world == 1 else None
+
+    # ---- strong scaling: BASELINE configs[3] as written -- args.blobs blobs TOTAL split over the ranks ------------------
+    strong = None
+    if world > 1:
+        lo, hi = sharded.shard_ranges(n, world)[rank]
+        ns = hi - lo
+        plan_s = sharded.ShardedBatch(lib, S, ns, rank, world, local_rank, session=sharded.session_name() + "s", cap=sharded.shard_ranges(n, world)[0][1])
+        lib.kzgb200_set_profiling(plan_s.ctx, 1)
+        st_s = torch.cuda.ExternalStream(lib.kzgb200_stream(plan_s.ctx), device=dev)
+        sb, sc, sp = d_blobs[:ns * BLOB], d_cs[:ns * 48], d_ps[:ns * 48]
+        hb, hc, hp = h_blobs[:ns * BLOB], h_cs[:ns * 48], h_ps[:ns * 48]
+        ms_s, ph_s = timed(lambda: must(plan_s.verify_device(sb, sc, sp), "strong resident"), args.steps, W, st_s, plan_s.ctx)
+        ms_se, _ = timed(lambda: must(plan_s.verify_host(hb, hc, hp), "strong e2e"), args.steps, W, st_s, plan_s.ctx)
+        strong = {"scaling": "strong", "total_blobs": n, "blobs_per_gpu": ns, "value": n / (ms_s / 1e3), "ms_per_step": ms_s,
+                  "e2e": {"value": n / (ms_se / 1e3), "ms_per_step": ms_se, "h2d_bytes_per_step": n * ALGO_BYTES_PER_BLOB, "d2h_bytes_per_step": n * 64 + 16 * world},
+                  "unit": "blobs/s", "phases_ms_rank0": dict(zip(PHASES, ph_s)),
+                  "peer_stores": bool(plan_s.group.uses_peer_stores(0)),
+                  "note": "BASELINE.json configs[3] as written: %d blobs (2 GiB) in total, sharded over %d GPUs; the per-blob SHA-256 chain "
+                          "(2050 dependent compressions, ~2.9 ms) does not shrink with the shard" % (n, world)}
+        launches += args.steps * (count_launches(ns, True, "exact", world, rank == 0) + count_launches(ns, False, "exact", world, rank == 0))
+        plan_s.close()
+
+    must(plan.verify_device(d_blobs, d_cs, d_ps), "parity run")
+    m_par = min(n, args.cpu_sample if world == 1 else 512)
+    zy_sample = plan.last_zy_host(m_par) if rank == 0 else None
+    r_gpu = C.create_string_buffer(32)
+    lib.kzgb200_last_r(ctx, r_gpu)
     # negatives on the same workload (verdict only, untimed)
     neg = plan.check_negatives(d_blobs, d_cs, d_ps)
 
     total = n * world
-    ms, phases, ms_e2e = res["tree"]
     value = total / (ms / 1e3)
     e2e = total / (ms_e2e / 1e3)
     out = None
@@ -313,64 +539,76 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        # dominant kernel = the longest compute phase of the blocking call; parse_g1 is excluded: its phase spans the deferred
-        # subgroup checks, which run beside the tail on SMs of their own
-        top = max(range(1, 7), key=lambda i: phases[i]) if world == 1 else None
-        roof = int_pipe = None
-        if top is not None and phases[top] > 0:
-            ach = n * ALGO_BYTES_PER_BLOB / (phases[top] / 1e3) / 1e9
-            roof = {"bound": "hbm", "kernel": PHASES[top], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": TRAFFIC_BYTES.get(PHASES[top]), "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
-                    "note": "the path is integer-pipe / latency bound, not HBM bound; see int_pipe and DESIGN.md section 4"}
-            # algorithmic integer work of the two blob-streaming kernels against the MEASURED pipe peaks (tools/microbench/intpipe.cu,
-            # profiles/intpipe_r01.txt): ALU 69.2 thread-ops/clk/SM, carry-chained IMAD.WIDE.X 31.0 /clk/SM, 148 SMs
-            clk = 1.965e9
-            sha_ops = n * 2050 * 1218.0          # ALU-pipe instructions per 64-byte block (SASS count: 672 SHF + 352 LOP3 + 178 IADD3 + 16 PRMT)
-            fr_ops = n * 4095 * 192.0            # IMAD.WIDE.X per fused dual Fr product
-            int_pipe = {"challenge_sha256": {"achieved_ops_per_s": sha_ops / (phases[1] / 1e3), "peak_ops_per_s": 69.2 * 148 * clk,
-                                             "frac": sha_ops / (phases[1] / 1e3) / (69.2 * 148 * clk), "pipe": "ALU (SHF/LOP3/IADD3)"},
-                        "evaluate_barycentric": {"achieved_ops_per_s": fr_ops / (phases[2] / 1e3), "peak_ops_per_s": 31.0 * 148 * clk,
-                                                 "frac": fr_ops / (phases[2] / 1e3) / (31.0 * 148 * clk), "pipe": "FMA-heavy (IMAD.WIDE.U32.X)"}}
+        # dominant kernel = the longest phase of the blocking call (rank 0's phases at N > 1)
+        top = max(range(0, 7), key=lambda i: phases[i])
+        traffic = load_profiled_traffic()
+        ach = n * ALGO_BYTES_PER_BLOB / (phases[top] / 1e3) / 1e9
+        roof = {"bound": "hbm", "kernel": PHASES[top], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic.get(PHASES[top]), "traffic_source": "profiles/ncu_full_r02_traffic.json (ncu --set full, same workload)" if traffic.get(PHASES[top]) else None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
+                "note": "the path is integer-pipe / latency bound, not HBM bound; see int_pipe and DESIGN.md section 4"}
+        # algorithmic integer work of the two blob-streaming kernels against the MEASURED pipe peaks (tools/microbench/intpipe.cu,
+        # profiles/intpipe_r01.txt): ALU 69.2 thread-ops/clk/SM, carry-chained IMAD.WIDE.X 31.0 /clk/SM, 148 SMs
+        clk = 1.965e9
+        sha_ops = n * 2050 * 1218.0          # ALU-pipe instructions per 64-byte block (SASS count: 672 SHF + 352 LOP3 + 178 IADD3 + 16 PRMT)
+        fr_ops = n * 4095 * 192.0            # IMAD.WIDE.X per fused dual Fr product
+        int_pipe = {"challenge_sha256": {"achieved_ops_per_s": sha_ops / (phases[1] / 1e3), "peak_ops_per_s": 69.2 * 148 * clk,
+                                         "frac": sha_ops / (phases[1] / 1e3) / (69.2 * 148 * clk), "pipe": "ALU (SHF/LOP3/IADD3)"},
+                    "evaluate_barycentric": {"achieved_ops_per_s": fr_ops / (phases[2] / 1e3), "peak_ops_per_s": 31.0 * 148 * clk,
+                                             "frac": fr_ops / (phases[2] / 1e3) / (31.0 * 148 * clk), "pipe": "FMA-heavy (IMAD.WIDE.U32.X)"}}
         cfg = workload_config(args, n, world)
         cfg["host_affinity"] = numa_cpus
-        cfg["transcript"] = "tree (opt-in KZGB200_TRANSCRIPT_TREE: same verdict / z / y as kzg-rs, r hashed as a 3-level tree)"
-        ex_ms, ex_ph, ex_e2e = res["exact"]
-        out = {"metric": "blobs verified/sec (verify_blob_kzg_proof_batch)", "value": value, "unit": "blobs/s", "n_gpus": world,
-               "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-               "vs_baseline": None, "dtype": "u32-limb modular integer (Fr 255-bit / Fp 381-bit) + SHA-256", "data": "synthetic",
-               "config": cfg,
-               "e2e": {"value": e2e, "unit": "blobs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": n * ALGO_BYTES_PER_BLOB * world,
-                       "d2h_bytes_per_step": 8 * world},
-               "gpu_launches": args.steps * sum(plan.count_launches(n, resident=r, tree=t) for r in (True, False) for t in (True, False)),
-               "clocks": sampler.summary(),
-               "phases_ms": dict(zip(PHASES, phases)) if world == 1 else None, "roofline": roof, "int_pipe": int_pipe, "negatives": neg,
-               "pipelined": pipelined,
-               "exact_transcript": {"value": total / (ex_ms / 1e3), "e2e": total / (ex_e2e / 1e3), "unit": "blobs/s",
-                                    "ms_per_step": ex_ms, "e2e_ms_per_step": ex_e2e,
-                                    "phases_ms": dict(zip(PHASES, ex_ph)) if world == 1 else None,
-                                    "note": "library default KZGB200_TRANSCRIPT_EXACT: r, its powers and both MSM sums bit-identical to "
-                                            "kzg-rs; the transcript is ONE serial SHA-256 chain over all blobs of all ranks"}}
-    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        e2e_gbs = n * ALGO_BYTES_PER_BLOB / (ms_e2e / 1e3) / 1e9       # per GPU (each rank feeds its own GPU over its own link)
+        out = {"metric": METRIC, "value": value, "unit": "blobs/s", "n_gpus": world,
+               "steps": args.steps, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": DTYPE, "data": "synthetic", "config": cfg,
+               "e2e": {"value": e2e, "unit": "blobs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": (n * ALGO_BYTES_PER_BLOB + 32) * world,
+                       "d2h_bytes_per_step": (n * 64 + 16) * world, "host_memory": "pinned",
+                       "roofline": {"bound": "pcie", "achieved": e2e_gbs, "peak": pcie_peak, "unit": "GB/s per GPU", "frac": e2e_gbs / pcie_peak,
+                                    "peak_source": "pinned host->device copy of the same 2 GiB buffer, timed in this run (best of 4)"}},
+               "gpu_launches": launches, "clocks": sampler.summary(),
+               "phases_ms": dict(zip(PHASES, phases)), "roofline": roof, "int_pipe": int_pipe, "negatives": neg,
+               "pipelined": pipelined, "strong": strong,
+               "group": None if world == 1 else {"peer_stores": bool(plan.group.uses_peer_stores(0)), "exchange": "library group API (csrc/group.cu): "
+                                                 "transcript entries -> shared host block -> leader's host hash; partials -> NVLink peer stores into the leader GPU"}}
+        if "pageable" in extras:
+            out["e2e"]["pageable"] = {"value": total / (extras["pageable"] / 1e3), "ms_per_step": extras["pageable"],
+                                      "note": "same call from ordinary (unpinned) host memory: pinned staging ring inside the library"}
+        modes = {}
+        for name in ("tree", "device"):
+            if name in extras:
+                m1, ph1, m2 = extras[name]
+                modes[name] = {"value": total / (m1 / 1e3), "ms_per_step": m1, "e2e": (total / (m2 / 1e3)) if m2 else None, "phases_ms": dict(zip(PHASES, ph1))}
+        if modes:
+            out["other_transcript_modes"] = {"note": "tree: opt-in KZGB200_TRANSCRIPT_TREE (r differs from kzg-rs's, verdict / z / y do not); device: "
+                                                     "the exact chain on one warp of the GPU (round 1's default)", **modes}
+    if rank == 0 and not args.no_cpu_baseline:
         from oracle import oracle as O
         O.build()
         cores = os.cpu_count() or 1
-        m = min(n, args.cpu_sample)
+        m = m_par
         hb = h_blobs[:m * BLOB].numpy().tobytes(); hc = h_cs[:m * 48].numpy().tobytes(); hp = h_ps[:m * 48].numpy().tobytes()
         t = time.perf_counter()
         rc, ok, z, y = O.verify_batch_raw(hb, hc, hp, m, nthreads=cores)
         dt = time.perf_counter() - t
         assert rc == 0 and ok
-        m1 = min(m, 64)
-        t = time.perf_counter()
-        O.verify_batch_raw(hb[:m1 * BLOB], hc[:m1 * 48], hp[:m1 * 48], m1, nthreads=1)
-        dt1 = time.perf_counter() - t
-        out["cpu_baseline"] = {"value": m / dt, "unit": "blobs/s", "cores": cores, "kind": "port",
-                               "sample": "first %d of the %d blobs, %d threads (blob-parallel); single thread on %d blobs: %.1f blobs/s; SHA-NI=%d"
-                                         % (m, n, cores, m1, m1 / dt1, O.lib().kzgo_sha256_uses_shani())}
         # bit-exactness of z, y on the sample against the oracle
         out["parity_sample"] = {"blobs": m, "z_y_bit_exact": zy_sample == (z, y)}
+        if world == 1:
+            m1 = min(m, 64)
+            t = time.perf_counter()
+            O.verify_batch_raw(hb[:m1 * BLOB], hc[:m1 * 48], hp[:m1 * 48], m1, nthreads=1)
+            dt1 = time.perf_counter() - t
+            out["cpu_baseline"] = {"value": m / dt, "unit": "blobs/s", "cores": cores, "kind": "port",
+                                   "sample": "first %d of the %d blobs, %d threads (blob-parallel); single thread on %d blobs: %.1f blobs/s; SHA-NI=%d"
+                                             % (m, n, cores, m1, m1 / dt1, O.lib().kzgo_sha256_uses_shani())}
+            if m == n:      # the whole batch went through the oracle: r too
+                rr, _ = O.compute_r_powers([hc[48 * i:48 * i + 48] for i in range(n)], [z[32 * i:32 * i + 32] for i in range(n)],
+                                           [y[32 * i:32 * i + 32] for i in range(n)], [hp[48 * i:48 * i + 48] for i in range(n)])
+                out["parity_sample"]["r_bit_exact"] = rr == r_gpu.raw
     if rank == 0:
         print(json.dumps(out))
+    plan.close()
     if dist is not None:
         dist.destroy_process_group()
 

@@ -4,7 +4,8 @@
  *
  * Conventions
  *   - plain pointers and sizes only; the library never frees or retains caller memory past return;
- *   - "host" entry points take host memory (pageable or pinned) and do their own staging;
+ *   - "host" entry points take host memory (pinned: copied straight by the DMA engine; pageable: through a ring of pinned staging
+ *     buffers filled by a few memcpy threads -- env KZGB200_PAGEABLE=direct|register selects the driver's staging / in-place pinning);
  *     "_device" entry points take device pointers on the context's GPU (inputs already resident in HBM).  The library
  *     works on its own CUDA streams: device inputs must be complete before the call (synchronise the stream that
  *     produced them); every entry point returns only after its outputs are complete;
@@ -77,44 +78,86 @@ int kzgb200_verify_blob_kzg_proof_batch_device(kzgb200_ctx* ctx, const uint8_t* 
 int kzgb200_verify_kzg_proof_many(kzgb200_ctx* ctx, const uint8_t* commitments, const uint8_t* zs, const uint8_t* ys,
                                   const uint8_t* proofs, size_t m, uint8_t* verdicts);
 
-/* ---- sharded batch: one context (= one rank) per GPU, blobs partitioned by contiguous ranges -------------
- * The batch is verified as   phase 1 (per rank)  -> exchange (z,y)  -> r  -> phase 2 (per rank partial sums)
- * -> allgather of KZGB200_PARTIAL_BYTES per rank -> one final pairing check.  All pointers are device
- * pointers on the rank's GPU; the caller moves the small payloads between ranks (NCCL allgather).
- *
- * phase 1: parse C/pi, canonicity, z_i, y_i for this rank's n_local blobs.  d_zy_out = n_local x 64 bytes:
- *          z_i then y_i as 32-byte little-endian canonical scalars (the byte order the batch transcript
- *          hashes, reference src/kzg_proof.rs:320-328). */
-int kzgb200_shard_evaluate(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t* d_commitments,
-                           const uint8_t* d_proofs, size_t n_local, uint8_t* d_zy_out);
-/* phase 1 with the shard's inputs in HOST memory (pageable or pinned): the blobs are copied in chunks while earlier
- * chunks are hashed / evaluated.  The device copies of the commitments / proofs (n_local x 48 each) and zy are written
- * to the given device buffers for the exchange. */
-int kzgb200_shard_evaluate_host(kzgb200_ctx* ctx, const uint8_t* blobs, const uint8_t* commitments, const uint8_t* proofs,
-                                size_t n_local, uint8_t* d_commitments_out, uint8_t* d_proofs_out, uint8_t* d_zy_out);
-/* r = SHA-256 transcript over ALL n_total blobs in global order (reference src/kzg_proof.rs:291-348), from the
- * gathered commitments (n_total x 48), zy (n_total x 64, as produced by phase 1) and proofs (n_total x 48). */
-int kzgb200_shard_challenge(kzgb200_ctx* ctx, const uint8_t* d_all_commitments, const uint8_t* d_all_zy,
-                            const uint8_t* d_all_proofs, size_t n_total);
-/* phase 2: this rank's partial sums with r_i = r^(global_offset + i); writes KZGB200_PARTIAL_BYTES to d_partial_out. */
-int kzgb200_shard_lincomb(kzgb200_ctx* ctx, size_t global_offset, uint8_t* d_partial_out);
-/* final: sum the gathered partials (n_ranks x KZGB200_PARTIAL_BYTES) and run the single pairing check.  The subgroup checks of
- * this rank's own points run beside the tail (they may still be running when the partial is exported), so a rank whose shard
- * holds a point outside the subgroup learns it here: it returns KZGB200_BAD_ARGS while the other ranks see the flags only if they
- * were known at export time -- the caller combines the return codes of all ranks (kzg_rs_b200/sharded.py: one 4-byte all-reduce). */
-int kzgb200_shard_finalize(kzgb200_ctx* ctx, const uint8_t* d_partials, size_t n_ranks, int* ok);
+/* KzgProof::verify_kzg_proof_batch on ALREADY-PARSED inputs (reference src/kzg_proof.rs:399-444).  Inputs in the
+ * reference's in-memory layout on a little-endian host (build.rs:185-203): a G1Affine is 104 bytes = x (6 x u64 Montgomery limbs) |
+ * y (6 x u64) | infinity flag byte | 7 bytes padding; a Scalar is 4 x u64 Montgomery limbs (32 bytes).  Like the reference it does
+ * not validate the points or check the subgroup (the arguments are typed values there).  Host pointers; n == 0 -> Ok(true). */
+int kzgb200_verify_kzg_proof_batch(kzgb200_ctx* ctx, const uint8_t* commitments104, const uint8_t* zs32, const uint8_t* ys32,
+                                   const uint8_t* proofs104, size_t n, int* ok);
+
+/* Per-blob verdicts: verdicts[i] = what KzgProof::verify_blob_kzg_proof(blob_i, commitment_i, proof_i) returns
+ * (src/kzg_proof.rs:446-470): 1 = Ok(true), 0 = Ok(false), 2 = Err(BadArgs).  The batch equation is checked first (one MSM, one pairing);
+ * only a failing batch is bisected down to the blob, on the GPU, from the already-parsed points and already-computed z_i, y_i.
+ * Host pointers; z_out / y_out nullable (n x 32 big-endian). */
+int kzgb200_verify_blob_kzg_proof_batch_each(kzgb200_ctx* ctx, const uint8_t* blobs, const uint8_t* commitments, const uint8_t* proofs,
+                                             size_t n, uint8_t* verdicts, uint8_t* z_out, uint8_t* y_out);
+
+/* The reference's public helpers (src/lib.rs:8): compute_challenge (src/kzg_proof.rs:46-72) and
+ * evaluate_polynomial_in_evaluation_form (:94-133, including z inside the evaluation domain, :109-111), one blob each, host pointers,
+ * 32-byte big-endian scalars.  Non-canonical blob elements / z -> KZGB200_BAD_ARGS. */
+int kzgb200_compute_challenge(kzgb200_ctx* ctx, const uint8_t* blob, const uint8_t* commitment48, uint8_t* z_out32);
+int kzgb200_evaluate_polynomial_in_evaluation_form(kzgb200_ctx* ctx, const uint8_t* blob, const uint8_t* z32, uint8_t* y_out32);
+
+/* ---- multi-GPU: blob-sharded batches -----------------------------------------------------------------
+ * A group is one context per GPU; rank k owns a contiguous range of the batch's blobs and never sees the others'.  The ranks meet
+ * twice per batch: (1) their transcript entries (C_i, z_i, y_i, pi_i: 160 bytes per blob) flow, chunk by chunk behind the evaluation
+ * kernels, into a shared host block where the leader (rank 0) hashes them in global order into r (compute_r_powers, reference
+ * src/kzg_proof.rs:291-348); (2) every rank's 352-byte partial (sum r_i pi_i, sum r_i C_i + r_i z_i pi_i, sum r_i y_i, flags) is the last
+ * store of its reduction kernel, over NVLink straight into the leader GPU's memory, where the single pairing check runs.  No
+ * collective library, no host synchronisation between the phases.
+ *   kzgb200_group_create: ONE process drives n GPUs (what a Rust caller of verify_blob_kzg_proof_batch uses to reach 8 GPUs).
+ *   kzgb200_group_join:   one process PER GPU (torchrun-style); every rank calls it with the same session string, world and
+ *                         max_blobs_per_rank; the ranks find each other in a POSIX shared-memory segment named after the session.
+ * Every verify call on a joined group is collective: all ranks call it, each with its own shard (>= 1 blob), and all return the
+ * same verdict / error.  Waits are bounded (30 s) and fail with KZGB200_INTERNAL_ERROR. */
+typedef struct kzgb200_group kzgb200_group;
+int kzgb200_group_create(kzgb200_group** out, const int* device_ids, int n_devices, const uint8_t* g2_points, size_t g2_points_len,
+                         size_t max_blobs_per_device);
+int kzgb200_group_join(kzgb200_group** out, const char* session, int rank, int world, int device, const uint8_t* g2_points,
+                       size_t g2_points_len, size_t max_blobs_per_rank);
+void kzgb200_group_destroy(kzgb200_group* g);
+int kzgb200_group_size(const kzgb200_group* g);               /* ranks in the group */
+int kzgb200_group_local_members(const kzgb200_group* g);      /* contexts driven by this process: all of them, or 1 */
+kzgb200_ctx* kzgb200_group_context(kzgb200_group* g, int local_index);
+const char* kzgb200_group_last_error(const kzgb200_group* g);
+int kzgb200_group_uses_peer_stores(const kzgb200_group* g, int local_index);
+/* KzgProof::verify_blob_kzg_proof_batch over all GPUs of a created (single-process) group: the whole batch in host memory, same
+ * argument checks and return codes as kzgb200_verify_blob_kzg_proof_batch; batches below 32 blobs run on the first GPU. */
+int kzgb200_group_verify_blob_kzg_proof_batch(kzgb200_group* g, const uint8_t* blobs, size_t n_blobs, const uint8_t* commitments,
+                                              size_t n_commitments, const uint8_t* proofs, size_t n_proofs, int* ok, uint8_t* z_out,
+                                              uint8_t* y_out);
+/* Per-shard entry: arrays with one element per LOCAL member (n GPUs for a created group, 1 for a joined rank); shard k of the
+ * batch = rank k's blobs, in rank order.  device_pointers != 0: inputs (and z_out / y_out) are device pointers on that member's GPU,
+ * complete before the call; else host memory.  z_out / y_out arrays (or their elements) may be null. */
+int kzgb200_group_verify_shards(kzgb200_group* g, const uint8_t* const* blobs, const uint8_t* const* commitments,
+                                const uint8_t* const* proofs, const size_t* n_local, int device_pointers, int* ok,
+                                uint8_t* const* z_out, uint8_t* const* y_out);
+/* the gathered partials of the last collective call, n_ranks x KZGB200_PARTIAL_BYTES (leader's process only); for parity tests */
+int kzgb200_group_last_partials(kzgb200_group* g, uint8_t* out, size_t n_ranks);
+/* host-side protocol of a joined group without any GPU (CPU tests of the N > 1 path): the ranks pass the transcript entries of their
+ * shards -- commitments (n_local x 48), zy (n_local x 64: z_i, y_i little-endian), proofs (n_local x 48) -- in chunks of `chunk`
+ * entries through the shared block; every rank receives the transcript digest the leader hashed over all ranks' entries. */
+int kzgb200_group_host_protocol_test(const char* session, int rank, int world, const uint8_t* commitments, const uint8_t* zy,
+                                     const uint8_t* proofs, size_t n_local, size_t chunk, uint8_t* digest_out32);
 
 /* ---- transcript mode of the batch challenge r -----------------------------------------------------------------
- * EXACT (default): r = SHA-256 over the serial transcript exactly as compute_r_powers (reference
- *   src/kzg_proof.rs:291-348) -- r, its powers and both MSM sums are bit-identical to kzg-rs.  The hash is one
- *   serial chain of 2.5 SHA-256 blocks per blob.
- * TREE (opt-in): same transcript bytes hashed as a three-level tree (16-entry leaves, then 32 digests per middle hash, in parallel; then the root).  r differs from
- *   kzg-rs's; verdicts do not (z, y are unaffected).  For throughput at large n / many GPUs. */
+ * EXACT (default): r = SHA-256 over the serial transcript exactly as compute_r_powers (reference src/kzg_proof.rs:291-348) -- r, its
+ *   powers and both MSM sums are bit-identical to kzg-rs.  The hash is ONE serial chain of 2.5 SHA-256 blocks per blob over data of
+ *   every blob; it is run by a host thread (SHA-NI when the CPU has it) incrementally behind the evaluation kernels, chunk by chunk
+ *   as the (z, y) pairs leave the GPU; only the last small chunk's hash is exposed.
+ * EXACT_DEVICE: the same chain on one warp of the GPU (~2.4 us per blob: 40 ms at 16384 blobs; round 1's default).  Same r.
+ * TREE (opt-in): the same entries hashed as a two-level tree with domain separation -- leaf j = SHA-256("RCKZGBATCH_LEAF_" | 16
+ *   entries) on the GPU in parallel, r = SHA-256("RCKZGBATCH___V1_" | u64be 4096 | u64be n | leaves) mod q.  r differs from kzg-rs's;
+ *   verdicts, z, y do not.  For very large multi-GPU batches, where even the host chain (2 GB/s) would limit. */
 #define KZGB200_TRANSCRIPT_EXACT 0
 #define KZGB200_TRANSCRIPT_TREE 1
+#define KZGB200_TRANSCRIPT_EXACT_DEVICE 2
 int kzgb200_set_transcript_mode(kzgb200_ctx* ctx, int mode);
 /* canonical big-endian r of the last batch verified on this context (n >= 2) */
 int kzgb200_last_r(kzgb200_ctx* ctx, uint8_t* r_out32);
+/* test hook: SHA-256 of msg by the host code that hashes the transcript; force_portable = 1 selects the portable compression
+ * function; returns 1 if the SHA-NI path was used */
+int kzgb200_host_sha256(const uint8_t* msg, size_t len, uint8_t* out32, int force_portable);
 
 /* raw partial of the last single-GPU batch (n >= 2), KZGB200_PARTIAL_BYTES: Jacobian A = sum r_i pi_i and
  * B' = sum r_i C_i + r_i z_i pi_i as 3 x 12 little-endian u32 Montgomery limbs each (R = 2^384), then
@@ -137,10 +180,11 @@ int kzgb200_blob_to_kzg_commitment_batch(kzgb200_ctx* ctx, const uint8_t* d_blob
 int kzgb200_compute_blob_kzg_proof_batch(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t* d_commitments, size_t n,
                                          uint8_t* d_proofs_out);
 
-/* per-phase device timing of single-GPU batch calls (CUDA events on the context stream).  out7 = milliseconds of
- * {parse G1, challenge, evaluate, transcript r, lincomb terms, reduce, final pairing} of the last call. */
+/* per-phase device timing of batch calls (CUDA event pairs on the stream each phase runs on).  out8 = milliseconds of
+ * {G1 decompression, challenge, evaluate, transcript r (exposed part: last chunk copy + host hash + upload), lincomb terms, reduce,
+ * final pairing, deferred subgroup checks (run beside the last three)} of the last call. */
 int kzgb200_set_profiling(kzgb200_ctx* ctx, int on);
-int kzgb200_get_phase_ms(kzgb200_ctx* ctx, float* out7);
+int kzgb200_get_phase_ms(kzgb200_ctx* ctx, float* out8);
 /* profiling aid: SM clock stamps of the sections of the last single-GPU final pairing kernel */
 int kzgb200_debug_final_ticks(kzgb200_ctx* ctx, long long* out14);
 /* the cudaStream_t all work of this context is issued on (for CUDA-event timing by the caller) */

@@ -68,11 +68,26 @@ class Library:
         d.kzgb200_verify_blob_kzg_proof_batch.argtypes = [p, p, sz, p, sz, p, sz, ip, p, p]
         d.kzgb200_verify_blob_kzg_proof_batch_device.argtypes = [p, p, p, p, sz, ip, p, p]
         d.kzgb200_verify_kzg_proof_many.argtypes = [p, p, p, p, p, sz, p]
-        d.kzgb200_shard_evaluate.argtypes = [p, p, p, p, sz, p]
-        d.kzgb200_shard_evaluate_host.argtypes = [p, p, p, p, sz, p, p, p]
-        d.kzgb200_shard_challenge.argtypes = [p, p, p, p, sz]
-        d.kzgb200_shard_lincomb.argtypes = [p, sz, p]
-        d.kzgb200_shard_finalize.argtypes = [p, p, sz, ip]
+        d.kzgb200_verify_kzg_proof_batch.argtypes = [p, p, p, p, p, sz, ip]
+        d.kzgb200_verify_blob_kzg_proof_batch_each.argtypes = [p, p, p, p, sz, p, p, p]
+        d.kzgb200_compute_challenge.argtypes = [p, p, C.c_char_p, C.c_char_p]
+        d.kzgb200_evaluate_polynomial_in_evaluation_form.argtypes = [p, p, C.c_char_p, C.c_char_p]
+        d.kzgb200_host_sha256.argtypes = [C.c_char_p, sz, C.c_char_p, C.c_int]
+        pp, psz = C.POINTER(p), C.POINTER(sz)
+        d.kzgb200_group_create.argtypes = [C.POINTER(p), C.POINTER(C.c_int), C.c_int, C.c_char_p, sz, sz]
+        d.kzgb200_group_join.argtypes = [C.POINTER(p), C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, sz, sz]
+        d.kzgb200_group_destroy.argtypes = [p]
+        d.kzgb200_group_size.argtypes = [p]
+        d.kzgb200_group_local_members.argtypes = [p]
+        d.kzgb200_group_context.argtypes = [p, C.c_int]
+        d.kzgb200_group_context.restype = p
+        d.kzgb200_group_last_error.argtypes = [p]
+        d.kzgb200_group_last_error.restype = C.c_char_p
+        d.kzgb200_group_uses_peer_stores.argtypes = [p, C.c_int]
+        d.kzgb200_group_verify_blob_kzg_proof_batch.argtypes = [p, p, sz, p, sz, p, sz, ip, p, p]
+        d.kzgb200_group_verify_shards.argtypes = [p, pp, pp, pp, psz, C.c_int, ip, pp, pp]
+        d.kzgb200_group_last_partials.argtypes = [p, C.c_char_p, sz]
+        d.kzgb200_group_host_protocol_test.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, sz, sz, C.c_char_p]
         d.kzgb200_harness_generate.argtypes = [p, C.c_uint64, sz, C.c_int, C.c_char_p, p, p, p]
         d.kzgb200_set_profiling.argtypes = [p, C.c_int]
         d.kzgb200_get_phase_ms.argtypes = [p, C.POINTER(C.c_float)]
@@ -270,6 +285,31 @@ class KzgProof:
         return bool(ok.value)
 
     @staticmethod
+    def verify_kzg_proof_batch(commitments, zs, ys, proofs, n, kzg_settings, device=0):
+        """src/kzg_proof.rs:399-444 on already-parsed inputs in the reference's in-memory layout: commitments / proofs =
+        n x 104 bytes (G1Affine: x, y as 6 x u64 Montgomery limbs, infinity byte, padding), zs / ys = n x 32 bytes (Scalar:
+        4 x u64 Montgomery limbs).  Contiguous host buffers."""
+        ctx, ok = kzg_settings.context(device), C.c_int(0)
+        rc = Library.get().dll.kzgb200_verify_kzg_proof_batch(ctx, _ptr(commitments), _ptr(zs), _ptr(ys), _ptr(proofs), n, C.byref(ok))
+        if rc:
+            _raise(rc, ctx)
+        return bool(ok.value)
+
+    @staticmethod
+    def verify_blob_kzg_proof_batch_each(blobs, commitments, proofs, n, kzg_settings, device=0, want_zy=False):
+        """Per-blob verdicts of a batch (contiguous host buffers): list of True / False / None, None = the reference's
+        verify_blob_kzg_proof would return Err(BadArgs) for that blob."""
+        ctx = kzg_settings.context(device)
+        out = C.create_string_buffer(max(n, 1))
+        z = C.create_string_buffer(32 * max(n, 1)) if want_zy else None
+        y = C.create_string_buffer(32 * max(n, 1)) if want_zy else None
+        rc = Library.get().dll.kzgb200_verify_blob_kzg_proof_batch_each(ctx, _ptr(blobs), _ptr(commitments), _ptr(proofs), n, out, z, y)
+        if rc:
+            _raise(rc, ctx)
+        verdicts = [{0: False, 1: True, 2: None}[v] for v in out.raw[:n]]
+        return (verdicts, z.raw, y.raw) if want_zy else verdicts
+
+    @staticmethod
     def verify_kzg_proof_many(commitments, zs, ys, proofs, m, kzg_settings, device=0):
         """m independent (C, z, y, proof) tuples in contiguous buffers -> bytes of m verdicts (0/1/2=BadArgs)."""
         ctx = kzg_settings.context(device)
@@ -280,7 +320,123 @@ class KzgProof:
         return out.raw[:m]
 
 
-TRANSCRIPT_EXACT, TRANSCRIPT_TREE = 0, 1
+def compute_challenge(blob, commitment_bytes, kzg_settings, device=0):
+    """src/kzg_proof.rs:46-72 (re-exported by src/lib.rs:8): the Fiat-Shamir challenge z, 32 bytes big-endian."""
+    b, c = _b(blob, BYTES_PER_BLOB, "blob"), _b(commitment_bytes, 48, "commitment")
+    ctx, z = kzg_settings.context(device), C.create_string_buffer(32)
+    rc = Library.get().dll.kzgb200_compute_challenge(ctx, b, c, z)
+    if rc:
+        _raise(rc, ctx)
+    return z.raw
+
+
+def evaluate_polynomial_in_evaluation_form(blob, z_bytes, kzg_settings, device=0):
+    """src/kzg_proof.rs:94-133 (re-exported by src/lib.rs:8) on the blob's 4096 field elements at z: y, 32 bytes big-endian."""
+    b, z = _b(blob, BYTES_PER_BLOB, "blob"), _b(z_bytes, 32, "z")
+    ctx, y = kzg_settings.context(device), C.create_string_buffer(32)
+    rc = Library.get().dll.kzgb200_evaluate_polynomial_in_evaluation_form(ctx, b, z, y)
+    if rc:
+        _raise(rc, ctx)
+    return y.raw
+
+
+TRANSCRIPT_EXACT, TRANSCRIPT_TREE, TRANSCRIPT_EXACT_DEVICE = 0, 1, 2
+
+
+class DeviceGroup:
+    """Blob-sharded batches over several GPUs (include/kzgb200.h "multi-GPU").
+
+        DeviceGroup.create(settings, [0, 1, ..., 7], max_blobs_per_device)       one process drives all GPUs
+        DeviceGroup.join(settings, session, rank, world, device, max_blobs)      one process per GPU (collective calls)
+    """
+
+    def __init__(self, handle):
+        self.lib = Library.get().dll
+        self.h = handle
+        self.world = self.lib.kzgb200_group_size(handle)
+        self.local = self.lib.kzgb200_group_local_members(handle)
+
+    @classmethod
+    def create(cls, kzg_settings, device_ids, max_blobs_per_device):
+        lib, h = Library.get().dll, C.c_void_p()
+        ids = (C.c_int * len(device_ids))(*device_ids)
+        rc = lib.kzgb200_group_create(C.byref(h), ids, len(device_ids), kzg_settings.g2_monomial_bytes[:192], 192, max_blobs_per_device)
+        if rc:
+            _raise(rc)
+        return cls(h)
+
+    @classmethod
+    def join(cls, kzg_settings, session, rank, world, device, max_blobs_per_rank):
+        lib, h = Library.get().dll, C.c_void_p()
+        rc = lib.kzgb200_group_join(C.byref(h), session.encode(), rank, world, device, kzg_settings.g2_monomial_bytes[:192], 192, max_blobs_per_rank)
+        if rc:
+            _raise(rc)
+        return cls(h)
+
+    def context(self, i=0):
+        return C.c_void_p(self.lib.kzgb200_group_context(self.h, i))
+
+    def uses_peer_stores(self, i=0):
+        return bool(self.lib.kzgb200_group_uses_peer_stores(self.h, i))
+
+    def set_transcript_mode(self, mode):
+        for i in range(self.local):
+            self.lib.kzgb200_set_transcript_mode(self.context(i), mode)
+
+    def _fail(self, rc):
+        if rc == 2:
+            raise KzgError("InternalError", "Internal error: " + self.lib.kzgb200_group_last_error(self.h).decode(errors="replace"))
+        _raise(rc)
+
+    def verify_blob_kzg_proof_batch_raw(self, blobs, n_blobs, commitments, n_commitments, proofs, n_proofs, want_zy=False):
+        """The whole batch in contiguous host buffers (created group): same semantics as KzgProof.verify_blob_kzg_proof_batch_raw."""
+        ok = C.c_int(0)
+        z = C.create_string_buffer(32 * max(n_blobs, 1)) if want_zy else None
+        y = C.create_string_buffer(32 * max(n_blobs, 1)) if want_zy else None
+        rc = self.lib.kzgb200_group_verify_blob_kzg_proof_batch(self.h, _ptr(blobs), n_blobs, _ptr(commitments), n_commitments, _ptr(proofs),
+                                                                n_proofs, C.byref(ok), z, y)
+        if rc:
+            self._fail(rc)
+        return (bool(ok.value), z.raw, y.raw) if want_zy else bool(ok.value)
+
+    def verify_shards(self, blobs, commitments, proofs, n_local, device_pointers, z_out=None, y_out=None):
+        """One shard per local member (lists); device_pointers: the buffers are device memory on each member's GPU.
+        Returns True / False, raises KzgError (BadArgs on any rank raises on every rank)."""
+        k = self.local
+        assert len(blobs) == len(commitments) == len(proofs) == len(n_local) == k
+        arr = lambda xs: (C.c_void_p * k)(*[_ptr(x) for x in xs]) if xs is not None else None
+        ok = C.c_int(0)
+        rc = self.lib.kzgb200_group_verify_shards(self.h, arr(blobs), arr(commitments), arr(proofs), (C.c_size_t * k)(*n_local),
+                                                  int(bool(device_pointers)), C.byref(ok), arr(z_out), arr(y_out))
+        if rc:
+            self._fail(rc)
+        return bool(ok.value)
+
+    def last_partials(self, n_ranks=None):
+        n_ranks = n_ranks or self.world
+        out = C.create_string_buffer(PARTIAL_BYTES * n_ranks)
+        rc = self.lib.kzgb200_group_last_partials(self.h, out, n_ranks)
+        if rc:
+            self._fail(rc)
+        return [out.raw[PARTIAL_BYTES * i:PARTIAL_BYTES * (i + 1)] for i in range(n_ranks)]
+
+    def close(self):
+        if self.h:
+            self.lib.kzgb200_group_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def host_sha256(msg, portable=False):
+    """(digest, used_sha_ni) by the host code that hashes the batch transcript."""
+    out = C.create_string_buffer(32)
+    used = Library.get().dll.kzgb200_host_sha256(bytes(msg), len(msg), out, int(portable))
+    return out.raw, bool(used)
 
 
 class BatchPipeline:
@@ -360,15 +516,20 @@ def set_transcript_mode(kzg_settings, mode, device=0):
 def last_batch_intermediates(kzg_settings, device=0):
     """(r, proof_lincomb, rhs_g1) of the last n >= 2 batch on this device, as the oracle's trace gives them:
     r 32-byte big-endian; the two sums as affine integer pairs (or None for the identity)."""
-    ctx = kzg_settings.context(device)
+    ctx = kzg_settings.context(device) if isinstance(kzg_settings, KzgSettings) else kzg_settings
     r, part = C.create_string_buffer(32), C.create_string_buffer(PARTIAL_BYTES)
     lib = Library.get().dll
     for rc in (lib.kzgb200_last_r(ctx, r), lib.kzgb200_last_partial(ctx, part)):
         if rc:
             _raise(rc, ctx)
+    return decode_partial(part.raw, r.raw)
+
+
+def decode_partial(part, r=None):
+    """A 352-byte partial -> affine integer pairs (None = identity), sum r_i y_i and the error flags."""
     P = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
     rinv = pow(1 << 384, -1, P)
-    fe = lambda off: int.from_bytes(part.raw[off:off + 48], "little") * rinv % P
+    fe = lambda off: int.from_bytes(part[off:off + 48], "little") * rinv % P
 
     def affine(off):
         x, y, z = fe(off), fe(off + 48), fe(off + 96)
@@ -376,8 +537,8 @@ def last_batch_intermediates(kzg_settings, device=0):
             return None
         zi = pow(z, -1, P)
         return (x * zi * zi % P, y * zi * zi * zi % P)
-    s = int.from_bytes(part.raw[288:320], "little")
-    return {"r": r.raw, "A": affine(0), "B_prime": affine(144), "sum_r_y": s}
+    s = int.from_bytes(part[288:320], "little")
+    return {"r": r, "A": affine(0), "B_prime": affine(144), "sum_r_y": s, "err": int.from_bytes(part[320:324], "little")}
 
 
 def _ptr(x):

@@ -96,7 +96,12 @@ __global__ void transcript_words_kernel(const uint8_t* __restrict__ commitments,
                                         uint64_t first_entry, uint64_t entry_count, uint32_t* __restrict__ words);
 __global__ void transcript_tree_leaf_words_kernel(const uint32_t* __restrict__ words, uint64_t n, uint32_t* __restrict__ digests,
                                                   uint64_t first_group, uint64_t group_count);
-__global__ void transcript_tree_root_kernel(const uint32_t* __restrict__ digests, uint64_t n, uint32_t* __restrict__ mid, Fr* __restrict__ r_mont);
+__global__ void r_from_digest_kernel(const uint32_t* __restrict__ digest, Fr* __restrict__ r_mont);
+__global__ void z_setup_kernel(const uint8_t* __restrict__ z_be32, int n, Fr* __restrict__ z_mont, ZY* __restrict__ zy, Fr* __restrict__ zpow,
+                               uint32_t* __restrict__ status);
+__global__ void import_parsed_kernel(const uint8_t* __restrict__ c104, const uint8_t* __restrict__ p104, const uint8_t* __restrict__ z32,
+                                     const uint8_t* __restrict__ y32, int n, G1Affine* __restrict__ C, G1Affine* __restrict__ P,
+                                     uint8_t* __restrict__ c48, uint8_t* __restrict__ p48, Fr* __restrict__ z_mont, ZY* __restrict__ zy);
 __global__ void msm_scalars_kernel(const Fr* __restrict__ z_mont, const ZY* __restrict__ zy, const Fr* __restrict__ r_mont, uint64_t offset, int n,
                                    uint8_t* __restrict__ digits, Fr* __restrict__ ry);
 __global__ void msm_sort_kernel(const uint8_t* __restrict__ digits, int n, uint32_t* __restrict__ order, uint32_t* __restrict__ start);
@@ -104,11 +109,14 @@ __global__ void msm_bucket_kernel(const G1Affine* __restrict__ C, const G1Affine
                                   const uint32_t* __restrict__ start, G1* __restrict__ buckets);
 __global__ void msm_window_kernel(const G1* __restrict__ buckets, G1* __restrict__ windows);
 __global__ void msm_combine_kernel(const G1* __restrict__ windows, const Fr* __restrict__ ry, const uint32_t* __restrict__ status, int n,
-                                   Partial* __restrict__ out);
+                                   Partial* __restrict__ out, uint32_t* flag, uint32_t epoch);
+__global__ void wait_flags_kernel(const uint32_t* flags, int count, uint32_t epoch, uint32_t* __restrict__ timed_out);
 __global__ void batch_final_kernel(const Partial* __restrict__ parts, int nparts, const DeviceTables* __restrict__ T, uint32_t* __restrict__ result,
                                    long long* __restrict__ ticks);
 __global__ void single_final_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P, const ZY* __restrict__ zy,
                                     const uint32_t* __restrict__ status, const DeviceTables* __restrict__ T, uint32_t* __restrict__ result);
+__global__ void verify_parsed_each_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P, const ZY* __restrict__ zy,
+                                          const uint32_t* __restrict__ status, int n, const DeviceTables* __restrict__ T, uint8_t* __restrict__ verdicts);
 __global__ void verify_many_kernel(const uint8_t* __restrict__ c, const uint8_t* __restrict__ z, const uint8_t* __restrict__ y,
                                    const uint8_t* __restrict__ p, size_t m, const DeviceTables* __restrict__ T, uint8_t* __restrict__ verdicts);
 __global__ void export_scalars_kernel(const ZY* __restrict__ zy, int n, uint8_t* __restrict__ z_out, uint8_t* __restrict__ y_out);

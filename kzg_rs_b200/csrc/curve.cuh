@@ -153,6 +153,18 @@ KZG_NI bool g1_from_compressed(G1Affine& out, const uint8_t* b, bool check_subgr
     return true;
 }
 
+// G1Affine::to_compressed (ZCash format): 48 big-endian bytes of x with the compression / infinity / sign flags
+KZG_NI void g1_to_compressed(uint8_t* out, const G1Affine& a) {
+    if (a.inf) { for (int i = 0; i < 48; i++) out[i] = 0; out[0] = 0xc0; return; }
+    Fp x = a.x.to_raw();
+    for (int i = 0; i < 12; i++) {
+        uint8_t* p = out + 4 * (11 - i);
+        p[0] = (uint8_t)(x.l[i] >> 24); p[1] = (uint8_t)(x.l[i] >> 16); p[2] = (uint8_t)(x.l[i] >> 8); p[3] = (uint8_t)x.l[i];
+    }
+    out[0] |= 0x80;
+    if (fp_lex_largest(a.y)) out[0] |= 0x20;
+}
+
 // Fp2 square root for p = 3 mod 4 (complex method); false if not a square
 KZG_NI bool fp2_sqrt(Fp2& out, const Fp2& a) {
     if (a.is_zero()) { out = a; return true; }

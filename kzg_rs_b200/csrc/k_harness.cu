@@ -22,16 +22,6 @@ __device__ __noinline__ Fr harness_coeff(uint64_t seed, uint64_t blob, int j) {
     for (int k = 0; k < 4; k++) { uint64_t v = splitmix64(s); raw.l[2 * k] = (uint32_t)v; raw.l[2 * k + 1] = (uint32_t)(v >> 32); }
     return Fr::from_raw(raw);
 }
-__device__ __noinline__ void g1_to_compressed(uint8_t* out, const G1Affine& a) {
-    if (a.inf) { for (int i = 0; i < 48; i++) out[i] = 0; out[0] = 0xc0; return; }
-    Fp x = a.x.to_raw();
-    for (int i = 0; i < 12; i++) {
-        uint8_t* p = out + 4 * (11 - i);
-        p[0] = (uint8_t)(x.l[i] >> 24); p[1] = (uint8_t)(x.l[i] >> 16); p[2] = (uint8_t)(x.l[i] >> 8); p[3] = (uint8_t)x.l[i];
-    }
-    out[0] |= 0x80;
-    if (fp_lex_largest(a.y)) out[0] |= 0x20;
-}
 __global__ void harness_parse_points_kernel(const uint8_t* bytes, int n, G1Affine* out, uint32_t* bad) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

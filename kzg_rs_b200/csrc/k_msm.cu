@@ -111,8 +111,10 @@ __global__ void __launch_bounds__(kWinLanes) msm_window_kernel(const G1* __restr
 // window sums -> A = sum_w 256^w W[0][w], B' = sum_w 256^w (W[1][w] + W[2][w]) (Horner, 8 doublings per window):
 // warp 0 does A, warp 1 does B' with the cooperative point operations above; the other warps OR the per-blob error
 // flags and tree-sum the r_i y_i.
+// `out` may be a peer-mapped pointer into the group leader's exchange buffer (multi-GPU: the partial-sum gather is this kernel's
+// last store, over NVLink); then `flag` (same buffer) receives `epoch` after the partial, with a system-scope fence in between.
 __global__ void __launch_bounds__(256) msm_combine_kernel(const G1* __restrict__ windows, const Fr* __restrict__ ry, const uint32_t* __restrict__ status,
-                                                          int n, Partial* __restrict__ out) {
+                                                          int n, Partial* __restrict__ out, uint32_t* flag, uint32_t epoch) {
     __shared__ uint32_t s_err;
     __shared__ Fr s_ry[256];
     __shared__ CoopPoint cp[3];
@@ -150,6 +152,11 @@ __global__ void __launch_bounds__(256) msm_combine_kernel(const G1* __restrict__
     }
     if (warp < 2 && lane == 0) { G1 r = {cp[warp].v[0], cp[warp].v[1], cp[warp].v[2]}; if (warp == 1) out->b = r; else out->a = r; }
     if (t == 0) { out->ry = s_ry[0]; out->err = s_err; }
+    if (flag) {
+        __threadfence_system();
+        __syncthreads();
+        if (t == 0) { *reinterpret_cast<volatile uint32_t*>(flag) = epoch; __threadfence_system(); }
+    }
 }
 
 }  // namespace kzgb200

@@ -37,6 +37,7 @@ struct kzgb200_pipeline {
     std::set<uint64_t> live;            // submitted, not yet waited for
     uint64_t next_ticket = 1;
     size_t in_flight = 0;               // queued + running
+    size_t waiters = 0;                 // threads inside wait() / blocked in submit()
     bool stop = false;
 
     void work(size_t slot) {
@@ -92,7 +93,13 @@ extern "C" void kzgb200_pipeline_destroy(kzgb200_pipeline* p) {
         p->stop = true;
     }
     p->cv_job.notify_all();
+    p->cv_done.notify_all();                         // submitters blocked on back-pressure give up
     for (std::thread& t : p->workers) t.join();     // workers drain the queue first
+    {
+        std::unique_lock<std::mutex> lk(p->m);       // threads still inside wait() / submit() leave before the memory goes
+        p->cv_done.notify_all();
+        p->cv_done.wait(lk, [&] { return p->waiters == 0; });
+    }
     for (kzgb200_ctx* c : p->ctx) kzgb200_destroy(c);
     delete p;
 }
@@ -109,7 +116,10 @@ static int submit(kzgb200_pipeline* p, Job j, uint64_t* ticket) {
         std::unique_lock<std::mutex> lk(p->m);
         if (p->stop) return KZGB200_BAD_ARGS;
         // back-pressure: at most `depth` batches queued or running (each context holds one batch of workspace)
-        p->cv_done.wait(lk, [&] { return p->in_flight < p->ctx.size(); });
+        p->waiters++;
+        p->cv_done.wait(lk, [&] { return p->stop || p->in_flight < p->ctx.size(); });
+        p->waiters--;
+        if (p->stop) { p->cv_done.notify_all(); return KZGB200_BAD_ARGS; }      // the pipeline is being destroyed
         j.ticket = *ticket = p->next_ticket++;
         p->queue.push_back(j);
         p->live.insert(j.ticket);
@@ -133,11 +143,13 @@ extern "C" int kzgb200_pipeline_submit_device(kzgb200_pipeline* p, const uint8_t
 extern "C" int kzgb200_pipeline_wait(kzgb200_pipeline* p, uint64_t ticket, int* ok) {
     if (!p || !ok) return KZGB200_BAD_ARGS;
     std::unique_lock<std::mutex> lk(p->m);
-    if (!p->live.count(ticket)) return KZGB200_BAD_ARGS;               // unknown, or already waited for
-    p->cv_done.wait(lk, [&] { return p->done.count(ticket) != 0; });
+    if (!p->live.erase(ticket)) return KZGB200_BAD_ARGS;               // unknown, already waited for, or another thread is waiting for it
+    p->waiters++;
+    p->cv_done.wait(lk, [&] { return p->done.count(ticket) != 0; });   // every submitted job completes (destroy drains the queue)
     Done d = p->done[ticket];
     p->done.erase(ticket);
-    p->live.erase(ticket);
+    p->waiters--;
+    if (p->stop) p->cv_done.notify_all();                              // destroy waits for the last waiter to leave
     *ok = d.ok;
     return d.rc;
 }

@@ -84,12 +84,24 @@ def verify_blob_kzg_proof_batch(blobs, commitments, proofs, nthreads=1, want_tra
     return (bool(ok.value), rc, zs, ys, trace)
 
 
-def verify_batch_raw(blobs, commitments, proofs, n, nthreads=1):
-    """Contiguous-buffer variant used for timing: returns (rc, ok, z_bytes, y_bytes)."""
+def verify_batch_raw(blobs, commitments, proofs, n, nthreads=1, want_trace=False):
+    """Contiguous-buffer variant used for timing: returns (rc, ok, z_bytes, y_bytes) [+ trace dict r / proof_lincomb / rhs_g1]."""
     ok = C.c_int(0)
     z, y = C.create_string_buffer(32 * n), C.create_string_buffer(32 * n)
-    rc = lib().kzgo_verify_blob_kzg_proof_batch(blobs, n, commitments, n, proofs, n, nthreads, C.byref(ok), z, y, None)
+    tr = C.create_string_buffer(128) if want_trace else None
+    rc = lib().kzgo_verify_blob_kzg_proof_batch(blobs, n, commitments, n, proofs, n, nthreads, C.byref(ok), z, y, tr)
+    if want_trace:
+        return rc, bool(ok.value), z.raw, y.raw, {"r": tr.raw[:32], "proof_lincomb": tr.raw[32:80], "rhs_g1": tr.raw[80:128]}
     return rc, bool(ok.value), z.raw, y.raw
+
+
+def use_setup(path=None):
+    """Re-initialise the oracle with another trusted setup ("KZGS" container); None = back to the mainnet setup."""
+    with open(path or SETUP_BIN, "rb") as fh:
+        raw = fh.read()
+    rc = lib().kzgo_init(raw, len(raw))
+    if rc:
+        raise RuntimeError("oracle setup load failed rc=%d" % rc)
 
 
 def compute_challenge(blob, commitment):

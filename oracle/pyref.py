@@ -471,6 +471,19 @@ def compute_r_powers(commitments, zs, ys, proofs):  # kzg_proof.rs:291-348
     return out
 
 
+def tree_transcript_r(commitment_bytes, zs, ys, proof_bytes):
+    """NOT in the reference: the library's opt-in KZGB200_TRANSCRIPT_TREE challenge (include/kzgb200.h), restated here so that
+    the GPU value is pinned bit-exactly.  Same entries as compute_r_powers (kzg_proof.rs:314-333) hashed as a two-level tree with
+    domain separation: leaf j = SHA-256("RCKZGBATCH_LEAF_" | entries [16j, 16j+16)), r = SHA-256("RCKZGBATCH___V1_" | u64be 4096 |
+    u64be n | leaf_0 | leaf_1 | ...) mod q.  Inputs: compressed points as bytes, z / y as integers."""
+    n = len(commitment_bytes)
+    entry = lambda i: commitment_bytes[i] + zs[i].to_bytes(32, 'little') + ys[i].to_bytes(32, 'little') + proof_bytes[i]
+    root = RANDOM_CHALLENGE_KZG_BATCH_DOMAIN + (4096).to_bytes(8, 'big') + n.to_bytes(8, 'big')
+    for j in range(0, n, 16):
+        root += hashlib.sha256(b"RCKZGBATCH_LEAF_" + b"".join(entry(i) for i in range(j, min(j + 16, n)))).digest()
+    return int.from_bytes(hashlib.sha256(root).digest(), 'big') % Q
+
+
 def verify_kzg_proof_impl(C, z, y, proof, tau_g2):  # kzg_proof.rs:203-223 / :385-396
     x_minus_z = g2_add(tau_g2, g2_neg(g2_mul(G2_GEN, z)))
     p_minus_y = g1_add(C, g1_neg(g1_mul(G1_GEN, y)))

@@ -106,3 +106,19 @@ int main(int argc, char** argv) {
                            "-L", os.path.dirname(LIB), "-lkzgb200", "-Wl,-rpath," + os.path.dirname(LIB)])
     out = subprocess.run([str(exe), os.path.join(ROOT, "kzg_rs_b200", "data", "mainnet_setup.bin")], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip() in ("no-gpu", "ok-true")
+
+
+def test_host_transcript_sha256_both_code_paths(dll):
+    """The batch transcript (compute_r_powers, reference src/kzg_proof.rs:291-348) is hashed by the library's host code:
+    SHA-NI when the CPU has it, portable otherwise.  Both against hashlib, over the padding edge cases and a transcript-sized message."""
+    import hashlib
+    import random
+    dll.kzgb200_host_sha256.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_int]
+    rnd = random.Random(7)
+    out = C.create_string_buffer(32)
+    for n in list(range(0, 130)) + [32 + 160 * 64, 32 + 160 * 1000 + 0, 1 << 20]:
+        msg = rnd.randbytes(n)
+        for portable in (0, 1):
+            used = dll.kzgb200_host_sha256(msg, n, out, portable)
+            assert out.raw == hashlib.sha256(msg).digest(), (n, portable)
+            assert not (portable and used)
