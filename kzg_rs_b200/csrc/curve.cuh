@@ -14,6 +14,13 @@ struct Affine {
 };
 
 template <class FE>
+struct Jac;
+// out-of-line group law, operands by value (registers, see field.cuh)
+template <class FE> KZG_NI Jac<FE> jac_dbl(Jac<FE> p);
+template <class FE> KZG_NI Jac<FE> jac_add_mixed(Jac<FE> p, Affine<FE> q);
+template <class FE> KZG_NI Jac<FE> jac_add(Jac<FE> p, Jac<FE> q);
+
+template <class FE>
 struct Jac {
     FE x, y, z;  // z == 0 <=> identity
     KZG_HD static Jac identity() { return {FE::one(), FE::one(), FE::zero()}; }
@@ -23,40 +30,9 @@ struct Jac {
         return {a.x, a.y, FE::one()};
     }
     KZG_HD Jac neg() const { return {x, y.neg(), z}; }
-    KZG_NI Jac dbl() const {
-        if (is_identity()) return *this;
-        FE A = x.sqr(), B = y.sqr(), C = B.sqr();
-        FE D = ((x + B).sqr() - A - C).dbl();
-        FE E = A.dbl() + A, F = E.sqr();
-        FE z3 = (y * z).dbl();
-        FE x3 = F - D.dbl();
-        FE y3 = E * (D - x3) - C.dbl().dbl().dbl();
-        return {x3, y3, z3};
-    }
-    KZG_NI Jac add_mixed(const Affine<FE>& q) const {
-        if (q.inf) return *this;
-        if (is_identity()) return from_affine(q);
-        FE Z2 = z.sqr(), U2 = q.x * Z2, S2 = q.y * Z2 * z;
-        FE H = U2 - x, R = S2 - y;
-        if (H.is_zero()) return R.is_zero() ? dbl() : identity();
-        FE H2 = H.sqr(), H3 = H2 * H, XH2 = x * H2;
-        FE x3 = R.sqr() - H3 - XH2.dbl();
-        FE y3 = R * (XH2 - x3) - y * H3;
-        return {x3, y3, z * H};
-    }
-    KZG_NI Jac add(const Jac& q) const {
-        if (is_identity()) return q;
-        if (q.is_identity()) return *this;
-        FE Z1Z1 = z.sqr(), Z2Z2 = q.z.sqr();
-        FE U1 = x * Z2Z2, U2 = q.x * Z1Z1;
-        FE S1 = y * Z2Z2 * q.z, S2 = q.y * Z1Z1 * z;
-        FE H = U2 - U1, R = S2 - S1;
-        if (H.is_zero()) return R.is_zero() ? dbl() : identity();
-        FE H2 = H.sqr(), H3 = H2 * H, UH2 = U1 * H2;
-        FE x3 = R.sqr() - H3 - UH2.dbl();
-        FE y3 = R * (UH2 - x3) - S1 * H3;
-        return {x3, y3, z * q.z * H};
-    }
+    KZG_HD Jac dbl() const { return jac_dbl<FE>(*this); }
+    KZG_HD Jac add_mixed(const Affine<FE>& q) const { return jac_add_mixed<FE>(*this, q); }
+    KZG_HD Jac add(const Jac& q) const { return jac_add<FE>(*this, q); }
     // projective equality
     KZG_NI bool equals(const Jac& b) const {
         bool ia = is_identity(), ib = b.is_identity();
@@ -66,6 +42,43 @@ struct Jac {
         return y * zb * b.z == b.y * za * z;
     }
 };
+// dbl-2009-l (a = 0): 2M + 5S
+template <class FE> KZG_NI Jac<FE> jac_dbl(Jac<FE> p) {
+    if (p.is_identity()) return p;
+    FE A = p.x.sqr(), B = p.y.sqr(), C = B.sqr();
+    FE D = ((p.x + B).sqr() - A - C).dbl();
+    FE E = A.dbl() + A, F = E.sqr();
+    FE z3 = (p.y * p.z).dbl();
+    FE x3 = F - D.dbl();
+    FE y3 = E * (D - x3) - C.dbl().dbl().dbl();
+    return {x3, y3, z3};
+}
+// 8M + 3S
+template <class FE> KZG_NI Jac<FE> jac_add_mixed(Jac<FE> p, Affine<FE> q) {
+    if (q.inf) return p;
+    if (p.is_identity()) return Jac<FE>::from_affine(q);
+    FE Z2 = p.z.sqr(), U2 = q.x * Z2, S2 = q.y * Z2 * p.z;
+    FE H = U2 - p.x, R = S2 - p.y;
+    if (H.is_zero()) return R.is_zero() ? jac_dbl<FE>(p) : Jac<FE>::identity();
+    FE H2 = H.sqr(), H3 = H2 * H, XH2 = p.x * H2;
+    FE x3 = R.sqr() - H3 - XH2.dbl();
+    FE y3 = R * (XH2 - x3) - p.y * H3;
+    return {x3, y3, p.z * H};
+}
+// 12M + 4S
+template <class FE> KZG_NI Jac<FE> jac_add(Jac<FE> p, Jac<FE> q) {
+    if (p.is_identity()) return q;
+    if (q.is_identity()) return p;
+    FE Z1Z1 = p.z.sqr(), Z2Z2 = q.z.sqr();
+    FE U1 = p.x * Z2Z2, U2 = q.x * Z1Z1;
+    FE S1 = p.y * Z2Z2 * q.z, S2 = q.y * Z1Z1 * p.z;
+    FE H = U2 - U1, R = S2 - S1;
+    if (H.is_zero()) return R.is_zero() ? jac_dbl<FE>(p) : Jac<FE>::identity();
+    FE H2 = H.sqr(), H3 = H2 * H, UH2 = U1 * H2;
+    FE x3 = R.sqr() - H3 - UH2.dbl();
+    FE y3 = R * (UH2 - x3) - S1 * H3;
+    return {x3, y3, p.z * q.z * H};
+}
 
 using G1Affine = Affine<Fp>;
 using G1 = Jac<Fp>;

@@ -1,6 +1,6 @@
 """The CUDA sources are __host__ __device__ down to the carry-chain primitives, so the product's own field / curve /
 pairing / cooperative-engine code is unit-tested here on the CPU (nvcc host compile of the same headers):
-  * Montgomery products (single and fused dual), add, sub vs Python integers, edge values included;
+  * Montgomery products (single, fused dual, dedicated squaring), add, sub vs Python integers, edge values included;
   * per-proof verification logic (decompression, subgroup check, G1-side pairing equation with precomputed lines)
     and the cooperative pairing engine + binary-GCD inversion vs the reference's 114 well-formed verify_kzg_proof vectors;
   * the generated engine programs vs the Python oracle (tools/gen_vliw.py self-test).
@@ -39,7 +39,7 @@ def test_montgomery_arithmetic_matches_python(tmp_path):
             a, b, c, d = v
             w = nb // 4
             lines.append("%s %0*x %0*x %0*x %0*x" % (name, w, a, w, b, w, c, w, d))
-            exp.append((a * b * rinv % mod, (a * b + c * d) * rinv % mod, (a + b) % mod, (a - b) % mod))
+            exp.append((a * b * rinv % mod, (a * b + c * d) * rinv % mod, (a + b) % mod, (a - b) % mod, a * a * rinv % mod, c * c * rinv % mod))
     out = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True).stdout.split("\n")
     for l, e, o in zip(lines, exp, out):
         assert tuple(int(x, 16) for x in o.split()) == e, l[:40]
