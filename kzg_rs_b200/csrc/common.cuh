@@ -43,7 +43,7 @@ constexpr int kLeavesPerThread = kFieldElementsPerBlob / kEvalThreads;  // 32
 constexpr int kTreeGroup = 16;      // transcript entries (160 B each) per leaf hash: 40 compressions
 constexpr int kTreeMid = 32;        // leaf digests per middle-level hash: 17 compressions
 constexpr int kWindows = 16, kBuckets = 256, kMsmSets = 3, kDigitRows = 4 * kWindows;   // rows: (kind r|rz) x (half lo|hi) x window
-constexpr int kBucketSplit = 4;
+constexpr int kSlice = 32, kMsmRows = kMsmSets * 2 * kWindows;   // bucket accumulation: entries per thread; rows = (set, GLV half, window)
 constexpr int kWinLanes = 64, kWinPer = kBuckets / kWinLanes;     // 64 lanes x 4 buckets: 48 CTAs still fit the tail's 8 SMs in one wave
 constexpr int kFinalThreads = 64;
 constexpr int kHarnessMaxDegree = 16;
@@ -106,7 +106,9 @@ __global__ void msm_scalars_kernel(const Fr* __restrict__ z_mont, const ZY* __re
                                    uint8_t* __restrict__ digits, Fr* __restrict__ ry);
 __global__ void msm_sort_kernel(const uint8_t* __restrict__ digits, int n, uint32_t* __restrict__ order, uint32_t* __restrict__ start);
 __global__ void msm_bucket_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P, int n, const uint32_t* __restrict__ order,
-                                  const uint32_t* __restrict__ start, G1* __restrict__ buckets);
+                                  const uint32_t* __restrict__ start, G1* __restrict__ halfsum, G1* __restrict__ part);
+__global__ void msm_bucket_join_kernel(int n, const uint32_t* __restrict__ start, const G1* __restrict__ halfsum, const G1* __restrict__ part,
+                                       G1* __restrict__ buckets);
 __global__ void msm_window_kernel(const G1* __restrict__ buckets, G1* __restrict__ windows);
 __global__ void msm_combine_kernel(const G1* __restrict__ windows, const Fr* __restrict__ ry, const uint32_t* __restrict__ status, int n,
                                    Partial* __restrict__ out, uint32_t* flag, uint32_t epoch);

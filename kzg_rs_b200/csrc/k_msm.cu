@@ -54,37 +54,86 @@ __global__ void __launch_bounds__(256) msm_sort_kernel(const uint8_t* __restrict
     __syncthreads();
     for (int i = t; i < n; i += blockDim.x) ord[atomicAdd(&cursor[row[i]], 1u)] = (uint32_t)i;
 }
-// four threads per (set, window, bucket b >= 1): threads 0,1 walk the low-half list (points P_i), threads 2,3 the
-// high-half list (points -phi(P_i)), each taking every second entry; a shared-memory tree joins the four partial sums
-// (splitting the lists shortens the serial chain of point additions between "r is known" and the pairing check)
+// Bucket accumulation, balanced.  A "row" = (point set, GLV half, window): its sorted index list (n entries, grouped by digit) is
+// cut into slices of kSlice consecutive entries and every thread sums exactly one slice -- round 1 gave whole bucket lists to
+// threads (Poisson-sized: a warp ran at the pace of its longest lane, +40 %).  A slice spans one or a few digit runs: a run that
+// lies entirely inside the slice is a finished half-bucket and goes to `halfsum`; the slice's first / last run may continue in
+// the neighbouring slices and goes to `part` slot 0 / 1 (a slice that is one single run: slot 0).  msm_bucket_join_kernel adds
+// up the few partials per bucket and the two GLV halves.  The next entry's index and point are fetched one addition ahead.
+__device__ __forceinline__ G1Affine ldg_point(const G1Affine* p) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
+    G1Affine a;
+#pragma unroll
+    for (int k = 0; k < 12; k++) { a.x.l[k] = __ldg(w + k); a.y.l[k] = __ldg(w + 12 + k); }
+    a.inf = __ldg(w + 24);
+    return a;
+}
 __global__ void __launch_bounds__(128) msm_bucket_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P, int n,
                                                          const uint32_t* __restrict__ order, const uint32_t* __restrict__ start,
-                                                         G1* __restrict__ buckets /* [3][16][256] */) {
-    __shared__ G1 sm[128];
+                                                         G1* __restrict__ halfsum /* [96][256] */, G1* __restrict__ part /* [96][slices][2] */) {
+    const int slices = (n + kSlice - 1) / kSlice;
     int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    int bucket_id = tid / kBucketSplit, part = tid % kBucketSplit;
-    bool live = bucket_id < kMsmSets * kWindows * kBuckets;
+    if (tid >= kMsmRows * slices) return;
+    int row = tid / slices, s = tid % slices;                 // row = (set * 2 + half) * kWindows + w
+    int w = row % kWindows, half = (row / kWindows) & 1, set = row / (2 * kWindows);
+    const G1Affine* pts = set == 1 ? C : P;
+    int digit_row = ((set == 2 ? 1 : 0) * 2 + half) * kWindows + w;
+    const uint32_t* ord = order + (size_t)digit_row * n;
+    const uint32_t* st = start + (size_t)digit_row * (kBuckets + 1);
+    const uint32_t pos0 = (uint32_t)s * kSlice, end0 = pos0 + kSlice < (uint32_t)n ? pos0 + kSlice : (uint32_t)n;
+    // digit of the first entry: the largest b with st[b] <= pos0
+    int b = 0;
+#pragma unroll
+    for (int step = 128; step >= 1; step >>= 1) if (b + step <= 255 && __ldg(st + b + step) <= pos0) b += step;
+    uint32_t next_boundary = __ldg(st + b + 1);
     G1 acc = G1::identity();
-    if (live) {
-        int b = bucket_id % kBuckets, w = (bucket_id / kBuckets) % kWindows, set = bucket_id / (kBuckets * kWindows);
-        int kind = set == 2 ? 1 : 0, half = part >> 1;
-        const G1Affine* pts = set == 1 ? C : P;
-        int row_id = (kind * 2 + half) * kWindows + w;
-        const uint32_t* ord = order + (size_t)row_id * n;
-        const uint32_t* st = start + (size_t)row_id * (kBuckets + 1);
+    bool first = true;
+    auto flush = [&](int bb) {
+        uint32_t lo = __ldg(st + bb), hi = __ldg(st + bb + 1);
+        if (bb != 0 && hi > lo) {
+            if (lo >= pos0 && hi <= end0) halfsum[(size_t)row * kBuckets + bb] = acc;
+            else part[((size_t)row * slices + s) * 2 + (first ? 0 : 1)] = acc;
+        }
+        first = false;
+        acc = G1::identity();
+    };
+    const uint32_t beta_l[12] = KZG_FP_BETA_M;
+    const Fp beta = fp_const(beta_l);
+    G1Affine nxt = ldg_point(pts + __ldg(ord + pos0));
+    for (uint32_t k = pos0; k < end0; k++) {
+        G1Affine q = nxt;
+        if (k + 1 < end0) nxt = ldg_point(pts + __ldg(ord + k + 1));
+        while (k >= next_boundary) { flush(b); b++; next_boundary = __ldg(st + b + 1); }
         if (b != 0) {
-            uint32_t lo = st[b], hi = st[b + 1];
-            for (uint32_t k = lo + (part & 1); k < hi; k += 2) {
-                G1Affine q = pts[ord[k]];
-                acc = acc.add_mixed(half ? glv_endo_neg(q) : q);
+            if (half && !q.inf) { q.x = q.x * beta; q.y = q.y.neg(); }     // -phi(P) = (beta x, -y)
+            acc = acc.add_mixed(q);
+        }
+    }
+    flush(b);
+}
+// one thread per (set, window, bucket): the bucket's partial sums of both GLV halves -> buckets[set][window][bucket]
+__global__ void __launch_bounds__(128) msm_bucket_join_kernel(int n, const uint32_t* __restrict__ start, const G1* __restrict__ halfsum,
+                                                              const G1* __restrict__ part, G1* __restrict__ buckets /* [3][16][256] */) {
+    const int slices = (n + kSlice - 1) / kSlice;
+    int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= kMsmSets * kWindows * kBuckets) return;
+    int b = tid % kBuckets, w = (tid / kBuckets) % kWindows, set = tid / (kBuckets * kWindows);
+    G1 acc = G1::identity();
+    if (b != 0) {
+        for (int half = 0; half < 2; half++) {
+            int row = (set * 2 + half) * kWindows + w, digit_row = ((set == 2 ? 1 : 0) * 2 + half) * kWindows + w;
+            const uint32_t* st = start + (size_t)digit_row * (kBuckets + 1);
+            uint32_t lo = __ldg(st + b), hi = __ldg(st + b + 1);
+            if (hi <= lo) continue;
+            uint32_t s0 = lo / kSlice, s1 = (hi - 1) / kSlice;
+            if (s0 == s1) { acc = acc.add(halfsum[(size_t)row * kBuckets + b]); continue; }
+            for (uint32_t s = s0; s <= s1; s++) {
+                int slot = (s == s0 && lo != s0 * kSlice) ? 1 : 0;     // the bucket opens inside slice s0: that slice's last run
+                acc = acc.add(part[((size_t)row * slices + s) * 2 + slot]);
             }
         }
     }
-    sm[threadIdx.x] = acc;
-    __syncthreads();
-    if (part < 2) sm[threadIdx.x] = sm[threadIdx.x].add(sm[threadIdx.x + 2]);
-    __syncthreads();
-    if (part == 0 && live) buckets[bucket_id] = sm[threadIdx.x].add(sm[threadIdx.x + 1]);
+    buckets[tid] = acc;
 }
 // two warps per (set, window): W = sum_b b * bucket[b].  Lane l owns buckets 4l .. 4l+3 (running-sum trick inside
 // the segment, then the segment's offset 8l by a short double-and-add), then a shared-memory tree over the lanes.

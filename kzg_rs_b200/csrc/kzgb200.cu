@@ -75,6 +75,7 @@ int ensure_capacity(kzgb200_ctx* ctx, size_t n, bool need_blob_staging) {
         CK(regrow(ctx->d_status, c)); CK(regrow(ctx->d_ry, c));
         CK(regrow(ctx->d_digits, c * kDigitRows)); CK(regrow(ctx->d_order, c * kDigitRows));
         CK(regrow(ctx->d_zout, c * 32)); CK(regrow(ctx->d_yout, c * 32));
+        CK(regrow(ctx->d_part, (size_t)kMsmRows * ((c + kSlice - 1) / kSlice) * 2));
         ctx->cap = c;
     }
     if (n > ctx->host_cap) {
@@ -363,7 +364,11 @@ int launch_lincomb(kzgb200_ctx* ctx, size_t offset, Partial* d_out, bool wait_su
     phase_begin(ctx, kPhLincomb, ctx->stream);
     msm_scalars_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_z_mont, ctx->d_zy, ctx->d_r, (uint64_t)offset, n, ctx->d_digits, ctx->d_ry);
     msm_sort_kernel<<<kDigitRows, 256, 0, ctx->stream>>>(ctx->d_digits, n, ctx->d_order, ctx->d_start);
-    msm_bucket_kernel<<<(kMsmSets * kWindows * kBuckets * kBucketSplit + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_C, ctx->d_P, n, ctx->d_order, ctx->d_start, ctx->d_buckets);
+    {
+        const int slices = (n + kSlice - 1) / kSlice;
+        msm_bucket_kernel<<<(kMsmRows * slices + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_C, ctx->d_P, n, ctx->d_order, ctx->d_start, ctx->d_halfsum, ctx->d_part);
+        msm_bucket_join_kernel<<<(kMsmSets * kWindows * kBuckets + 127) / 128, 128, 0, ctx->stream>>>(n, ctx->d_start, ctx->d_halfsum, ctx->d_part, ctx->d_buckets);
+    }
     phase_end(ctx, kPhLincomb, ctx->stream);
     if (ctx->subgroup_pending) {
         // Deferred subgroup checks: from here on the batch is latency-bound (window sums, Horner combination, one pairing: a
@@ -442,6 +447,7 @@ extern "C" int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_p
         CK(cudaMalloc(&ctx->d_result, 16));
         CK(cudaMalloc(&ctx->d_start, kDigitRows * (kBuckets + 1) * sizeof(uint32_t)));
         CK(cudaMalloc(&ctx->d_buckets, kMsmSets * kWindows * kBuckets * sizeof(G1)));
+        CK(cudaMalloc(&ctx->d_halfsum, kMsmRows * kBuckets * sizeof(G1)));
         CK(cudaMalloc(&ctx->d_windows, kMsmSets * kWindows * sizeof(G1)));
         CK(cudaMallocHost(&ctx->h_result, 16));
         CK(cudaMallocHost(&ctx->h_digest, 32));
@@ -477,7 +483,7 @@ extern "C" void kzgb200_destroy(kzgb200_ctx* ctx) {
     for (auto e : ctx->ev_stage) if (e) cudaEventDestroy(e);
     void* ptrs[] = {ctx->tables, ctx->d_blobs, ctx->d_c, ctx->d_p, ctx->d_z_mont, ctx->d_zy, ctx->d_C, ctx->d_P, ctx->d_status,
                     ctx->d_ry, ctx->d_r, ctx->d_partial, ctx->d_result, ctx->d_zout, ctx->d_yout, ctx->d_many, ctx->d_wk,
-                    ctx->d_digits, ctx->d_order, ctx->d_start, ctx->d_buckets, ctx->d_windows, ctx->d_lag_table, ctx->d_scalars, ctx->d_zpow,
+                    ctx->d_digits, ctx->d_order, ctx->d_start, ctx->d_buckets, ctx->d_halfsum, ctx->d_part, ctx->d_windows, ctx->d_lag_table, ctx->d_scalars, ctx->d_zpow,
                     ctx->d_chain_state, ctx->d_scratch, ctx->d_digest};
     for (void* p : ptrs) if (p) cudaFree(p);
     void* hptrs[] = {ctx->h_result, ctx->h_digest, ctx->h_partial, ctx->h_zy, ctx->h_c, ctx->h_p, ctx->h_stage[0], ctx->h_stage[1], ctx->h_stage[2], ctx->h_stage[3]};

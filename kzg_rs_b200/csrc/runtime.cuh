@@ -62,6 +62,7 @@ struct kzgb200_ctx {
     uint8_t* d_digits = nullptr;            // [4*16][cap]
     uint32_t *d_order = nullptr, *d_start = nullptr;
     kzgb200::G1 *d_buckets = nullptr, *d_windows = nullptr;
+    kzgb200::G1 *d_halfsum = nullptr, *d_part = nullptr;   // bucket accumulation: finished half-buckets [96][256], slice partials [96][slices][2]
     kzgb200::Partial* d_partial = nullptr;
     uint32_t* d_result = nullptr;
     uint8_t *d_zout = nullptr, *d_yout = nullptr;
