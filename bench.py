@@ -255,6 +255,7 @@ def run_tuples(args, rank, world, local_rank):
     hc, hz, hy, hp = pin(cs), pin(zs), pin(ys), pin(ps)
     out = torch.empty(m, dtype=torch.uint8).pin_memory()
     stream = torch.cuda.ExternalStream(lib.kzgb200_stream(ctx), device=torch.device("cuda", local_rank))
+    lib.kzgb200_set_profiling(ctx, 1)
     sampler = ClockSampler(local_rank)
     sampler.start()
 
@@ -292,6 +293,7 @@ def run_tuples(args, rank, world, local_rank):
                                                "tuples_per_gpu": m, "negatives": "1 % wrong y, 0.1 % non-canonical z"},
                "e2e": {"value": val, "unit": "checks/s", "ms_per_step": ms, "h2d_bytes_per_step": 160 * m * world, "d2h_bytes_per_step": m * world},
                "verdicts_match_construction": ok, "clocks": sampler.summary(),
+               "phases_ms_last_chunk": {"g1_parse": kernel_ms[0], "lhs_points": kernel_ms[4], "pairings": kernel_ms[6]},
                "roofline": {"bound": "integer (FMA-heavy pipe)", "achieved": val / world * 25000, "peak": fp_mul_peak, "unit": "Fp mul/s", "frac": val / world * 25000 / fp_mul_peak,
                             "note": "~25 k Fp multiplications per check (SURVEY.md 8d) against the measured 2.9e10 Fp mul/s (profiles/intpipe_r01.txt)"}}
         print(json.dumps(res))

@@ -46,6 +46,8 @@ constexpr int kWindows = 16, kBuckets = 256, kMsmSets = 3, kDigitRows = 4 * kWin
 constexpr int kSlice = 32, kMsmRows = kMsmSets * 2 * kWindows;   // bucket accumulation: entries per thread; rows = (set, GLV half, window)
 constexpr int kWinLanes = 64, kWinPer = kBuckets / kWinLanes;     // 64 lanes x 4 buckets: 48 CTAs still fit the tail's 8 SMs in one wave
 constexpr int kFinalThreads = 64;
+constexpr int kManyThreads = 384, kManyGroups = 21;   // many_pairing_kernel: checks run in lockstep by one CTA
+constexpr int kManyWarps = 4;         // many_pairing_warp_kernel (identity inputs): one check per warp
 constexpr int kHarnessMaxDegree = 16;
 constexpr int kLagWindows = 32, kLagEntries = 255;
 
@@ -79,10 +81,11 @@ struct FinalSmem {
     vliw::SharedTables stab;
 };
 
+constexpr int kManyStride = vliw::kTotalRegsThr * 12 + 1;     // words between the register files of consecutive groups (odd: bank skew)
+constexpr int kManySmemBytes = kManyGroups * kManyStride * 4 + (int)sizeof(vliw::SharedTables) + kManyGroups * (2 * (int)sizeof(G1Affine) + 2) + 64;
 // ---- kernels (k_*.cu) ----------------------------------------------------------------------------------------
 __global__ void setup_tables_kernel(DeviceTables* T, const uint8_t* g2_points);
-__global__ void challenge_kernel(const uint8_t* __restrict__ blobs, const uint8_t* __restrict__ commitments, int n, Fr* __restrict__ z_mont,
-                                 ZY* __restrict__ zy, Fr* __restrict__ zpow, uint32_t one);
+void launch_challenge(int stages, cudaStream_t st, const uint8_t* blobs, const uint8_t* commitments, int n, Fr* z_mont, ZY* zy, Fr* zpow);   // K2
 __global__ void eval_kernel(const uint8_t* __restrict__ blobs, int n, const Fr* __restrict__ zpow, const DeviceTables* __restrict__ T,
                             ZY* __restrict__ zy, uint32_t* __restrict__ status);
 __global__ void g1_decompress_kernel(const uint8_t* __restrict__ commitments, const uint8_t* __restrict__ proofs, int n, G1Affine* __restrict__ C,
@@ -117,10 +120,15 @@ __global__ void batch_final_kernel(const Partial* __restrict__ parts, int nparts
                                    long long* __restrict__ ticks);
 __global__ void single_final_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P, const ZY* __restrict__ zy,
                                     const uint32_t* __restrict__ status, const DeviceTables* __restrict__ T, uint32_t* __restrict__ result);
-__global__ void verify_parsed_each_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P, const ZY* __restrict__ zy,
-                                          const uint32_t* __restrict__ status, int n, const DeviceTables* __restrict__ T, uint8_t* __restrict__ verdicts);
-__global__ void verify_many_kernel(const uint8_t* __restrict__ c, const uint8_t* __restrict__ z, const uint8_t* __restrict__ y,
-                                   const uint8_t* __restrict__ p, size_t m, const DeviceTables* __restrict__ T, uint8_t* __restrict__ verdicts);
+__global__ void many_lhs_kernel(const uint8_t* __restrict__ z32, const uint8_t* __restrict__ y32, const G1Affine* __restrict__ C,
+                                const G1Affine* __restrict__ P, size_t m, const DeviceTables* __restrict__ T, G1Affine* __restrict__ X,
+                                uint32_t* __restrict__ status);
+__global__ void many_lhs_zy_kernel(const ZY* __restrict__ zy, const G1Affine* __restrict__ C, const G1Affine* __restrict__ P, size_t m,
+                                   const DeviceTables* __restrict__ T, G1Affine* __restrict__ X, const uint32_t* __restrict__ status);
+__global__ void many_pairing_kernel(const G1Affine* __restrict__ X, const G1Affine* __restrict__ P, const uint32_t* __restrict__ status, size_t m,
+                                    const DeviceTables* __restrict__ T, uint8_t* __restrict__ verdicts);
+__global__ void many_pairing_warp_kernel(const G1Affine* __restrict__ X, const G1Affine* __restrict__ P, size_t m, const DeviceTables* __restrict__ T,
+                                         uint8_t* __restrict__ verdicts);
 __global__ void export_scalars_kernel(const ZY* __restrict__ zy, int n, uint8_t* __restrict__ z_out, uint8_t* __restrict__ y_out);
 __global__ void r_to_raw_kernel(const Fr* __restrict__ r_mont, ZY* __restrict__ out);
 __global__ void status_or_kernel(const uint32_t* __restrict__ status, int n, uint32_t* __restrict__ out);

@@ -17,10 +17,10 @@ namespace kzgb200 {
 // whatever ptxas does with the loop: with register prefetching the same source ran at 3.3 ms per chain when the loads were
 // scheduled at the top of the body and at 4.3 ms when ptxas sank them to the bottom (tools/microbench/shachain.cu).  Each
 // thread reads back only what it copied itself, so no barrier is needed, only cp.async.wait_group.
-constexpr int kShaStages = 4;
 __device__ __forceinline__ void sha_cp_async16(uint4* smem_dst, const uint4* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
+template <int kShaStages>
 __device__ __forceinline__ void sha256_blob_body(uint32_t st[8], const uint4* __restrict__ bp, uint4 (*ring)[4][kShaThreads] /* [stage][quarter][thread] */,
                                                  uint32_t one) {
     const int t = threadIdx.x;
@@ -49,6 +49,7 @@ __device__ __forceinline__ void sha256_blob_body(uint32_t st[8], const uint4* __
         sha256_compress_bal(st, w, one);
     }
 }
+template <int kShaStages>
 __global__ void __launch_bounds__(kShaThreads) challenge_kernel(const uint8_t* __restrict__ blobs, const uint8_t* __restrict__ commitments,
                                                        int n, Fr* __restrict__ z_mont, ZY* __restrict__ zy, Fr* __restrict__ zpow,
                                                        uint32_t one /* == 1, opaque to the compiler: see sha256_compress_bal */) {
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(kShaThreads) challenge_kernel(const uint8_t* _
     }
     sha256_compress(st, w);
     // blocks 1..2047: blob[64k-32 .. 64k+32)
-    sha256_blob_body(st, bp, ring, one);
+    sha256_blob_body<kShaStages>(st, bp, ring, one);
     // block 2048: blob[131040..131072) | commitment[0..32)
     {
         uint4 a = __ldg(bp + 8190), b = __ldg(bp + 8191);
@@ -93,6 +94,13 @@ __global__ void __launch_bounds__(kShaThreads) challenge_kernel(const uint8_t* _
     Fr s = zm;
 #pragma unroll 1
     for (int k = 0; k <= 12; k++) { zpow[(size_t)i * 13 + k] = s; s = s.mul_inl(s); }
+}
+
+// ring depth: 4 stages (three 64-byte blocks, ~5 us, in flight per thread) or 8 (seven blocks); see kzgb200_ctx::sha_stages
+void launch_challenge(int stages, cudaStream_t st, const uint8_t* blobs, const uint8_t* commitments, int n, Fr* z_mont, ZY* zy, Fr* zpow) {
+    unsigned grid = (unsigned)((n + kShaThreads - 1) / kShaThreads);
+    if (stages >= 8) challenge_kernel<8><<<grid, kShaThreads, 0, st>>>(blobs, commitments, n, z_mont, zy, zpow, 1u);
+    else challenge_kernel<4><<<grid, kShaThreads, 0, st>>>(blobs, commitments, n, z_mont, zy, zpow, 1u);
 }
 
 }  // namespace kzgb200

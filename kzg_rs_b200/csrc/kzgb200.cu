@@ -310,7 +310,7 @@ int launch_phase1(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t* h_blo
         cudaStream_t s0 = ctx->s_work[0];
         CK(cudaStreamWaitEvent(s0, ctx->ev_begin, 0));
         phase_begin(ctx, kPhChallenge, s0);
-        challenge_kernel<<<((int)n + kShaThreads - 1) / kShaThreads, kShaThreads, 0, s0>>>(d_blobs, d_c, (int)n, ctx->d_z_mont, ctx->d_zy, ctx->d_zpow, 1u);
+        launch_challenge(ctx->sha_stages, s0, d_blobs, d_c, (int)n, ctx->d_z_mont, ctx->d_zy, ctx->d_zpow);
         phase_end(ctx, kPhChallenge, s0);
         CK(cudaEventRecord(ctx->ev_sha_all, s0));
         if (!ctx->parse_first) { int rc = launch_parse(); if (rc) return rc; }   // G1 decompression queued behind the hash launch
@@ -336,8 +336,8 @@ int launch_phase1(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t* h_blo
             CK(cudaStreamWaitEvent(sw, ctx->ev_h2d[c], 0));
             CK(cudaStreamWaitEvent(sw, ctx->ev_begin, 0));
             phase_begin(ctx, kPhChallenge, sw);
-            challenge_kernel<<<((int)cnt + kShaThreads - 1) / kShaThreads, kShaThreads, 0, sw>>>(d_blobs + lo * kBytesPerBlob, d_c + lo * 48, (int)cnt, ctx->d_z_mont + lo,
-                                                                                                   ctx->d_zy + lo, ctx->d_zpow + lo * 13, 1u);
+            launch_challenge(ctx->sha_stages, sw, d_blobs + lo * kBytesPerBlob, d_c + lo * 48, (int)cnt, ctx->d_z_mont + lo,
+                                                                                                   ctx->d_zy + lo, ctx->d_zpow + lo * 13);
             phase_end(ctx, kPhChallenge, sw);
             phase_begin(ctx, kPhEval, sw);
             eval_kernel<<<(int)cnt, kEvalThreads, 0, sw>>>(d_blobs + lo * kBytesPerBlob, (int)cnt, ctx->d_zpow + lo * 13, ctx->tables, ctx->d_zy + lo, ctx->d_status + lo);
@@ -425,6 +425,7 @@ extern "C" int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_p
         if (const char* v = getenv("KZGB200_PARSE_FIRST")) ctx->parse_first = atoi(v);
         if (const char* v = getenv("KZGB200_PARSE_FUSED")) ctx->parse_fused = atoi(v);
         if (const char* v = getenv("KZGB200_DEFER_SUBGROUP")) ctx->defer_subgroup = atoi(v);
+        if (const char* v = getenv("KZGB200_SHA_STAGES")) ctx->sha_stages = atoi(v);
         if (const char* v = getenv("KZGB200_PAGEABLE")) ctx->pageable_mode = !strcmp(v, "direct") ? 1 : (!strcmp(v, "register") ? 2 : 0);
         if (const char* v = getenv("KZGB200_TRANSCRIPT")) ctx->transcript_mode = !strcmp(v, "tree") ? KZGB200_TRANSCRIPT_TREE : (!strcmp(v, "device") ? KZGB200_TRANSCRIPT_EXACT_DEVICE : KZGB200_TRANSCRIPT_EXACT);
         CK(cudaFuncSetAttribute(g1_subgroup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailHogSmem));
@@ -441,6 +442,8 @@ extern "C" int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_p
         CK(cudaMalloc(&ctx->d_digest, 32));
         CK(cudaFuncSetAttribute(batch_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinalSmem)));
         CK(cudaFuncSetAttribute(single_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinalSmem)));
+        CK(cudaFuncSetAttribute(many_pairing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kManySmemBytes));
+        CK(cudaFuncSetAttribute(many_pairing_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kManySmemBytes));
         CK(cudaMalloc(&ctx->tables, sizeof(DeviceTables)));
         CK(cudaMalloc(&ctx->d_r, sizeof(Fr)));
         CK(cudaMalloc(&ctx->d_partial, sizeof(Partial)));
@@ -494,6 +497,18 @@ extern "C" void kzgb200_destroy(kzgb200_ctx* ctx) {
 
 extern "C" const char* kzgb200_last_error(const kzgb200_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 
+// per tuple of the many-tuple path: 3 affine points, a status word, 160 input bytes, a verdict byte (rounded up)
+constexpr size_t kManyBytesPerTuple = 3 * sizeof(G1Affine) + 4 + 160 + 4;
+// the pairing checks of m parsed tuples: kManyGroups per CTA in lockstep (one persistent CTA per SM), then the rare identity inputs
+static int launch_many_pairings(kzgb200_ctx* ctx, const G1Affine* X, const G1Affine* P, const uint32_t* status, size_t m, uint8_t* dv) {
+    size_t nbatch = (m + kManyGroups - 1) / kManyGroups;
+    unsigned grid = (unsigned)(nbatch < (size_t)ctx->num_sms ? nbatch : (size_t)ctx->num_sms);
+    many_pairing_kernel<<<grid, kManyThreads, kManySmemBytes, ctx->stream>>>(X, P, status, m, ctx->tables, dv);
+    size_t nw = (m + kManyWarps - 1) / kManyWarps;
+    many_pairing_warp_kernel<<<(unsigned)(nw < (size_t)ctx->num_sms ? nw : (size_t)ctx->num_sms), 32 * kManyWarps, kManySmemBytes, ctx->stream>>>(X, P, m, ctx->tables, dv);
+    CK(cudaGetLastError());
+    return KZGB200_OK;
+}
 // whole batch on one GPU, n >= 1; blobs either resident (h_blobs == nullptr) or streamed from the host (then hc / hp = the
 // caller's host commitments / proofs, which the transcript reads in place)
 static int batch_locked(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t* h_blobs, const uint8_t* d_c, const uint8_t* d_p, size_t n, int* ok,
@@ -596,10 +611,12 @@ extern "C" int kzgb200_verify_blob_kzg_proof_batch_each(kzgb200_ctx* ctx, const 
     if (all_true) memset(verdicts, 1, n);
     else {
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_parse, 0));
-        if (n > ctx->many_cap) { CK(regrow(ctx->d_many, n * 304)); ctx->many_cap = n; }
-        verify_parsed_each_kernel<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(ctx->d_C, ctx->d_P, ctx->d_zy, ctx->d_status, (int)n, ctx->tables, ctx->d_many);
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(verdicts, ctx->d_many, n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (n > ctx->many_cap) { CK(regrow(ctx->d_many, n * kManyBytesPerTuple)); ctx->many_cap = n; }
+        G1Affine* X = reinterpret_cast<G1Affine*>(ctx->d_many);
+        uint8_t* dv = ctx->d_many + n * sizeof(G1Affine);
+        many_lhs_zy_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_zy, ctx->d_C, ctx->d_P, n, ctx->tables, X, ctx->d_status);
+        if ((rc = launch_many_pairings(ctx, X, ctx->d_P, ctx->d_status, n, dv))) return rc;
+        CK(cudaMemcpyAsync(verdicts, dv, n, cudaMemcpyDeviceToHost, ctx->stream));
     }
     if (z_out) CK(cudaMemcpyAsync(z_out, ctx->d_zout, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
     if (y_out) CK(cudaMemcpyAsync(y_out, ctx->d_yout, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
@@ -617,7 +634,7 @@ extern "C" int kzgb200_verify_kzg_proof_batch(kzgb200_ctx* ctx, const uint8_t* c
     CK(cudaSetDevice(ctx->device));
     int rc = ensure_capacity(ctx, n, false);
     if (rc) return rc;
-    if (n > ctx->many_cap) { CK(regrow(ctx->d_many, n * 304)); ctx->many_cap = n; }
+    if (n > ctx->many_cap) { CK(regrow(ctx->d_many, n * kManyBytesPerTuple)); ctx->many_cap = n; }
     uint8_t *dc = ctx->d_many, *dp = dc + n * 104, *dz = dp + n * 104, *dy = dz + n * 32;
     for (int i = 0; i < 8; i++) ctx->ph_started[i] = false;
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_parse, 0));
@@ -653,7 +670,7 @@ extern "C" int kzgb200_compute_challenge(kzgb200_ctx* ctx, const uint8_t* blob, 
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_parse, 0));
     CK(cudaMemcpyAsync(ctx->d_blobs, blob, kBytesPerBlob, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_c, commitment48, 48, cudaMemcpyHostToDevice, ctx->stream));
-    challenge_kernel<<<1, kShaThreads, 0, ctx->stream>>>(ctx->d_blobs, ctx->d_c, 1, ctx->d_z_mont, ctx->d_zy, ctx->d_zpow, 1u);
+    launch_challenge(ctx->sha_stages, ctx->stream, ctx->d_blobs, ctx->d_c, 1, ctx->d_z_mont, ctx->d_zy, ctx->d_zpow);
     export_scalars_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_zy, 1, ctx->d_zout, nullptr);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(z_out32, ctx->d_zout, 32, cudaMemcpyDeviceToHost, ctx->stream));
@@ -682,22 +699,42 @@ extern "C" int kzgb200_evaluate_polynomial_in_evaluation_form(kzgb200_ctx* ctx, 
     return ctx->h_result[0] ? KZGB200_BAD_ARGS : KZGB200_OK;
 }
 
+// m independent verify_kzg_proof tuples (BASELINE config 5): parse kernels (one thread per point), X_i = C_i - [y_i]G + [z_i]pi_i (one
+// thread per tuple), then one warp per pairing check on the cooperative engine (k_many.cu); chunks of 2^20 tuples.
 extern "C" int kzgb200_verify_kzg_proof_many(kzgb200_ctx* ctx, const uint8_t* commitments, const uint8_t* zs, const uint8_t* ys,
                                              const uint8_t* proofs, size_t m, uint8_t* verdicts) {
     if (!ctx || (m && (!commitments || !zs || !ys || !proofs || !verdicts))) return KZGB200_BAD_ARGS;
     if (m == 0) return KZGB200_OK;
     std::lock_guard<std::mutex> g(ctx->lock);
     CK(cudaSetDevice(ctx->device));
-    if (m > ctx->many_cap) { CK(regrow(ctx->d_many, m * 304)); ctx->many_cap = m; }
-    uint8_t *dc = ctx->d_many, *dz = dc + m * 48, *dy = dz + m * 32, *dp = dy + m * 32, *dv = dp + m * 48;
-    CK(cudaMemcpyAsync(dc, commitments, m * 48, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(dz, zs, m * 32, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(dy, ys, m * 32, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(dp, proofs, m * 48, cudaMemcpyHostToDevice, ctx->stream));
-    verify_many_kernel<<<(unsigned)((m + 63) / 64), 64, 0, ctx->stream>>>(dc, dz, dy, dp, m, ctx->tables, dv);
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(verdicts, dv, m, cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t kChunk = (size_t)1 << 20, c = m < kChunk ? m : kChunk;
+    if (c > ctx->many_cap) { CK(regrow(ctx->d_many, c * kManyBytesPerTuple)); ctx->many_cap = c; }
+    G1Affine *dC = reinterpret_cast<G1Affine*>(ctx->d_many), *dP = dC + c, *dX = dP + c;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(dX + c);
+    uint8_t *dc = reinterpret_cast<uint8_t*>(dst + c), *dp = dc + c * 48, *dz = dp + c * 48, *dy = dz + c * 32, *dv = dy + c * 32;
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_parse, 0));
+    for (int i = 0; i < 8; i++) ctx->ph_started[i] = false;
+    for (size_t lo = 0; lo < m; lo += c) {
+        size_t cnt = m - lo < c ? m - lo : c;
+        CK(cudaMemcpyAsync(dc, commitments + lo * 48, cnt * 48, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(dz, zs + lo * 32, cnt * 32, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(dy, ys + lo * 32, cnt * 32, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(dp, proofs + lo * 48, cnt * 48, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(dst, 0, cnt * 4, ctx->stream));
+        phase_begin(ctx, kPhParse, ctx->stream);
+        g1_decompress_kernel<<<(unsigned)((2 * cnt + 127) / 128), 128, 0, ctx->stream>>>(dc, dp, (int)cnt, dC, dP, dst, false);
+        g1_subgroup_kernel<<<(unsigned)((2 * cnt + 255) / 256), 256, 0, ctx->stream>>>(dC, dP, (int)cnt, dst);
+        phase_end(ctx, kPhParse, ctx->stream);
+        phase_begin(ctx, kPhLincomb, ctx->stream);
+        many_lhs_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, ctx->stream>>>(dz, dy, dC, dP, cnt, ctx->tables, dX, dst);
+        phase_end(ctx, kPhLincomb, ctx->stream);
+        phase_begin(ctx, kPhFinal, ctx->stream);
+        { int rc = launch_many_pairings(ctx, dX, dP, dst, cnt, dv); if (rc) return rc; }
+        phase_end(ctx, kPhFinal, ctx->stream);
+        CK(cudaMemcpyAsync(verdicts + lo, dv, cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CK(cudaStreamSynchronize(ctx->stream));
+    collect_phase_times(ctx);
     return KZGB200_OK;
 }
 
@@ -740,7 +777,7 @@ extern "C" int kzgb200_harness_generate(kzgb200_ctx* ctx, uint64_t seed, size_t 
     int ni = (int)n;
     harness_blob_kernel<<<ni, 128, 0, ctx->stream>>>(seed, ni, degree, ctx->tables, d_blobs);
     harness_commit_kernel<<<(ni + 63) / 64, 64, 0, ctx->stream>>>(seed, ni, degree, d_M, nullptr, d_commitments, 0);
-    challenge_kernel<<<(ni + kShaThreads - 1) / kShaThreads, kShaThreads, 0, ctx->stream>>>(d_blobs, d_commitments, ni, ctx->d_z_mont, ctx->d_zy, ctx->d_zpow, 1u);
+    launch_challenge(ctx->sha_stages, ctx->stream, d_blobs, d_commitments, ni, ctx->d_z_mont, ctx->d_zy, ctx->d_zpow);
     harness_commit_kernel<<<(ni + 63) / 64, 64, 0, ctx->stream>>>(seed, ni, degree, d_M, ctx->d_z_mont, d_proofs, 1);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -827,7 +864,7 @@ static int commit_or_prove(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8
         if (!want_proof) {
             blob_scalars_kernel<<<(unsigned)(((size_t)cnt * kFieldElementsPerBlob + 127) / 128), 128, 0, ctx->stream>>>(blobs, cnt, ctx->d_scalars, ctx->d_status);
         } else {
-            challenge_kernel<<<(cnt + kShaThreads - 1) / kShaThreads, kShaThreads, 0, ctx->stream>>>(blobs, d_commitments + lo * 48, cnt, ctx->d_z_mont, ctx->d_zy, ctx->d_zpow, 1u);
+            launch_challenge(ctx->sha_stages, ctx->stream, blobs, d_commitments + lo * 48, cnt, ctx->d_z_mont, ctx->d_zy, ctx->d_zpow);
             eval_kernel<<<cnt, kEvalThreads, 0, ctx->stream>>>(blobs, cnt, ctx->d_zpow, ctx->tables, ctx->d_zy, ctx->d_status);
             quotient_kernel<<<cnt, kEvalThreads, 0, ctx->stream>>>(blobs, cnt, ctx->d_z_mont, ctx->d_zy, ctx->tables, ctx->d_scalars);
         }

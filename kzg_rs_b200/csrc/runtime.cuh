@@ -93,6 +93,7 @@ struct kzgb200_ctx {
     int num_sms = 148;
     int parse_fused = 0;            // tuning: decompression + subgroup check in one kernel (env KZGB200_PARSE_FUSED; measured slower)
     int defer_subgroup = 1;         // subgroup checks run beside the latency-bound tail on their own SMs (env KZGB200_DEFER_SUBGROUP)
+    int sha_stages = 8;             // cp.async ring depth of the challenge hash (env KZGB200_SHA_STAGES: 4 or 8)
     int pageable_mode = 0;          // 0 = pinned staging ring, 1 = plain cudaMemcpyAsync (driver staging), 2 = cudaHostRegister in place
     bool subgroup_pending = false;
     int parse_first = 0;            // tuning: launch G1 parsing before the first hash launch (env KZGB200_PARSE_FIRST)

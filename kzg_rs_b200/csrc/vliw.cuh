@@ -13,16 +13,24 @@ namespace vliw {
 
 // program tables (global memory, or a shared-memory copy made by load_tables)
 struct Tables {
-    const uint16_t (*mul)[6];
+    const uint16_t (*mul)[19];
     const uint32_t (*lin)[3];
     const uint16_t* term;
     const Level* level;
     const Program* prog;
+    bool plain;               // every multiplication operand is a single register (the `lat` programs)
 };
 struct Lanes {
     int tid, n;   // this thread's lane and the number of cooperating threads (host: 0, 1)
     Tables tab;
     long long* ticks = nullptr;   // optional: per-section clock64() stamps (profiling aid)
+    bool warp = false;            // the cooperating threads are the 32 lanes of ONE warp (many independent checks per CTA)
+    int groups = 1;               // independent register files run in lockstep through the same program: a level of k instructions
+    int stride = 0;               // becomes groups * k independent ones spread over the threads.  Group g's file starts `stride` 32-bit
+                                  // WORDS after group g-1's; an odd stride puts the same register of 32 groups on 32 different banks
+                                  // (consecutive threads run the SAME instruction for consecutive groups: uniform control flow,
+                                  // broadcast table reads, conflict-free register-file accesses)
+    KZG_HD Fp* file(Fp* regs, int g) const { return reinterpret_cast<Fp*>(reinterpret_cast<uint32_t*>(regs) + (size_t)g * stride); }
     KZG_HD void tick(int i) const {
 #ifdef __CUDA_ARCH__
         if (ticks && tid == 0) ticks[i] = clock64();
@@ -30,44 +38,92 @@ struct Lanes {
     }
     KZG_HD void sync() const {
 #ifdef __CUDA_ARCH__
-        __syncthreads();
+        if (warp) __syncwarp(); else __syncthreads();
 #endif
     }
 };
+// two program sets (tools/gen_vliw.py): `lat` for ONE check on one CTA, `thr` for many checks in lockstep
 KZG_HD Tables default_tables() {
 #ifdef __CUDA_ARCH__
-    return Tables{d_mul, d_lin, d_term, d_level, d_prog};
+    return Tables{lat::d_mul, lat::d_lin, lat::d_term, lat::d_level, lat::d_prog, true};
 #else
-    return Tables{h_mul, h_lin, h_term, h_level, h_prog};
+    return Tables{lat::h_mul, lat::h_lin, lat::h_term, lat::h_level, lat::h_prog, true};
+#endif
+}
+KZG_HD Tables throughput_tables() {
+#ifdef __CUDA_ARCH__
+    return Tables{thr::d_mul, thr::d_lin, thr::d_term, thr::d_level, thr::d_prog, false};
+#else
+    return Tables{thr::h_mul, thr::h_lin, thr::h_term, thr::h_level, thr::h_prog, false};
 #endif
 }
 // shared-memory image of the tables (instruction fetch becomes an LDS instead of a dependent global load)
 struct SharedTables {
-    uint16_t mul[kNumMul][6];
-    uint32_t lin[kNumLin][3];
-    uint16_t term[kNumTerm];
-    Level level[kNumLevel];
+    uint16_t mul[kNumMulMax][19];
+    uint32_t lin[kNumLinMax][3];
+    uint16_t term[kNumTermMax];
+    Level level[kNumLevelMax];
     Program prog[kNumPrograms];
 };
 #ifdef __CUDACC__
-__device__ __forceinline__ Tables load_tables(SharedTables* st, int tid, int n) {
-    for (int i = tid; i < kNumMul * 6; i += n) (&st->mul[0][0])[i] = (&d_mul[0][0])[i];
-    for (int i = tid; i < kNumLin * 3; i += n) (&st->lin[0][0])[i] = (&d_lin[0][0])[i];
-    for (int i = tid; i < kNumTerm; i += n) st->term[i] = d_term[i];
-    for (int i = tid; i < kNumLevel; i += n) st->level[i] = d_level[i];
-    for (int i = tid; i < kNumPrograms; i += n) st->prog[i] = d_prog[i];
+__device__ __forceinline__ Tables load_tables(SharedTables* st, int tid, int n, bool throughput = false) {
+    const Tables src = throughput ? throughput_tables() : default_tables();
+    const int nmul = throughput ? thr::kNumMul : lat::kNumMul, nlin = throughput ? thr::kNumLin : lat::kNumLin;
+    const int nterm = throughput ? thr::kNumTerm : lat::kNumTerm, nlevel = throughput ? thr::kNumLevel : lat::kNumLevel;
+    for (int i = tid; i < nmul * 19; i += n) (&st->mul[0][0])[i] = (&src.mul[0][0])[i];
+    for (int i = tid; i < nlin * 3; i += n) (&st->lin[0][0])[i] = (&src.lin[0][0])[i];
+    for (int i = tid; i < nterm; i += n) st->term[i] = src.term[i];
+    for (int i = tid; i < nlevel; i += n) st->level[i] = src.level[i];
+    for (int i = tid; i < kNumPrograms; i += n) st->prog[i] = src.prog[i];
     __syncthreads();
-    return Tables{st->mul, st->lin, st->term, st->level, st->prog};
+    return Tables{st->mul, st->lin, st->term, st->level, st->prog, !throughput};
 }
 #endif
 
-KZG_HD void exec_mul(Fp* regs, const uint16_t* ins) {
-    Fp a = regs[ins[1]], b = regs[ins[2]];
-    if (ins[3] == 0xffff) {
+// One multiplication operand = up to four registers with signs, summed by the multiplying thread itself (no LIN level, no
+// barrier): lazily, sum(pos) + #neg * p - sum(neg) < 4p, then one conditional subtraction of 2p for three or four terms, so the
+// operand is < 2p -- the Montgomery products tolerate that: a b + c d < 8 p^2 < R p (R = 2^384 = 9.8 p), result < p as usual.
+KZG_HD Fp mul_operand(const Fp* regs, const uint16_t* slot, uint32_t signs) {
+    Fp x = regs[slot[0]];                                   // the first term is always positive
+    if (slot[1] == 0xffff) return x;
+    const Fp p = Fp::modulus();
+    int n = 1;
+#pragma unroll 1
+    for (int j = 1; j < 4 && slot[j] != 0xffff; j++, n++) {
+        Fp y = regs[slot[j]];
+        if ((signs >> j) & 1u) { add_n<12>(x.l, x.l, p.l); sub_n<12>(x.l, x.l, y.l); }
+        else add_n<12>(x.l, x.l, y.l);
+    }
+    if (n > 2) {
+        Fp p2, t;
+        add_n<12>(p2.l, p.l, p.l);
+        uint32_t borrow = sub_n<12>(t.l, x.l, p2.l);
+#pragma unroll
+        for (int i = 0; i < 12; i++) x.l[i] = borrow ? x.l[i] : t.l[i];
+    }
+    return x;
+}
+// ins: dst, 4 operands x 4 slots, sign bits (4 per operand), negate-second-product flag
+KZG_HD void exec_mul(Fp* regs, const uint16_t* ins, bool plain) {
+    if (plain) {            // latency programs: every operand is one register
+        Fp a = regs[ins[1]], b = regs[ins[5]];
+        if (ins[9] == 0xffff) { regs[ins[0]] = a.mul_inl(b); return; }
+        Fp c = regs[ins[9]], d = regs[ins[13]];
+        if (ins[18] & 1) c = Fp::zero().sub_inl(c);
+        regs[ins[0]] = Fp::mul_dual_inl(a, b, c, d);
+        return;
+    }
+    const uint32_t signs = ins[17];
+    Fp a = mul_operand(regs, ins + 1, signs), b = mul_operand(regs, ins + 5, signs >> 4);
+    if (ins[9] == 0xffff) {
         regs[ins[0]] = a.mul_inl(b);
     } else {
-        Fp c = regs[ins[3]], d = regs[ins[4]];
-        if (ins[5] & 1) c = Fp::zero().sub_inl(c);
+        Fp c = mul_operand(regs, ins + 9, signs >> 8), d = mul_operand(regs, ins + 13, signs >> 12);
+        if (ins[18] & 1) {                                  // - c d = (2p - c) d with 2p - c in (0, 2p]
+            Fp p2, p = Fp::modulus();
+            add_n<12>(p2.l, p.l, p.l);
+            sub_n<12>(c.l, p2.l, c.l);
+        }
         regs[ins[0]] = Fp::mul_dual_inl(a, b, c, d);
     }
 }
@@ -141,8 +197,14 @@ KZG_HD void run(int prog, Fp* regs, const Lanes& L) {
 #ifdef __CUDA_ARCH__
         long long c0 = L.ticks ? clock64() : 0;
 #endif
-        if (lev.kind == 1) { for (int k = L.tid; k < lev.count; k += L.n) exec_mul(regs, L.tab.mul[lev.first + k]); }
-        else { for (int k = L.tid; k < lev.count; k += L.n) exec_lin(regs, L.tab.lin[lev.first + k], L.tab.term); }
+        if (L.groups == 1) {
+            if (lev.kind == 1) { for (int k = L.tid; k < lev.count; k += L.n) exec_mul(regs, L.tab.mul[lev.first + k], L.tab.plain); }
+            else { for (int k = L.tid; k < lev.count; k += L.n) exec_lin(regs, L.tab.lin[lev.first + k], L.tab.term); }
+        } else {
+            const int total = lev.count * L.groups;
+            if (lev.kind == 1) { for (int j = L.tid; j < total; j += L.n) { int k = j / L.groups, g = j - k * L.groups; exec_mul(L.file(regs, g), L.tab.mul[lev.first + k], L.tab.plain); } }
+            else { for (int j = L.tid; j < total; j += L.n) { int k = j / L.groups, g = j - k * L.groups; exec_lin(L.file(regs, g), L.tab.lin[lev.first + k], L.tab.term); } }
+        }
 #ifdef __CUDA_ARCH__
         long long c1 = L.ticks ? clock64() : 0;
 #endif
@@ -158,7 +220,12 @@ KZG_HD void run(int prog, Fp* regs, const Lanes& L) {
 }
 // regs[dst .. dst+count) = regs[src ..)
 KZG_HD void copy_regs(Fp* regs, int dst, int src, int count, const Lanes& L) {
-    for (int k = L.tid; k < count * 12; k += L.n) regs[dst + k / 12].l[k % 12] = regs[src + k / 12].l[k % 12];
+    const int per = count * 12;
+    for (int j = L.tid; j < per * L.groups; j += L.n) {
+        int k = j / L.groups, g = j - k * L.groups;
+        Fp* r = L.file(regs, g);
+        r[dst + k / 12].l[k % 12] = r[src + k / 12].l[k % 12];
+    }
     L.sync();
 }
 
@@ -197,18 +264,21 @@ KZG_NI Fp fp_inv_bingcd(const Fp& a_mont) {
 }
 
 // Shared-memory register file: program registers [0, kMaxRegs) then saved Fp12 values.
+constexpr int kMaxRegs = lat::kMaxRegs;
 constexpr int kSave0 = kMaxRegs;            // each save slot = 12 registers
 constexpr int kNumSaves = 5;
 constexpr int kTotalRegs = kMaxRegs + 12 * kNumSaves;
+constexpr int kSave0Thr = thr::kMaxRegs, kTotalRegsThr = thr::kMaxRegs + 12 * kNumSaves;   // register file of the lockstep form (throughput programs)
 
 KZG_HD void load_lines(Fp* regs, const LineCoeffs* c1, const LineCoeffs* c2, int k, const Lanes& L) {
     // 6 Fp per line (A, B, C as Fp2) into regs[kRegLines + 6 j ..]
-    for (int i = L.tid; i < 12 * 12; i += L.n) {
+    for (int q = L.tid; q < 12 * 12 * L.groups; q += L.n) {
+        int i = q / L.groups, g = q - i * L.groups;
         int fe = i / 12, limb = i % 12, j = fe / 6, e = fe % 6;
         const LineCoeffs* src = j == 0 ? c1 : c2;
         if (!src) continue;
         const Fp2& f2 = e < 2 ? src[k].A : (e < 4 ? src[k].B : src[k].C);
-        regs[kRegLines + fe].l[limb] = (e & 1) ? f2.c1.l[limb] : f2.c0.l[limb];
+        L.file(regs, g)[kRegLines + fe].l[limb] = (e & 1) ? f2.c1.l[limb] : f2.c0.l[limb];
     }
     L.sync();
 }
@@ -314,6 +384,77 @@ KZG_HD bool coop_pairing_product_is_one(Fp* regs, const G1Affine& P1, const Line
     for (int i = 1; i < 12; i++) ok = ok && regs[kRegF + i].is_zero();
     L.sync();
     return ok;
+}
+
+// L.groups independent checks e(P1[g], Q1) e(P2[g], Q2) == 1 in lockstep (both points of every group must be finite: the program
+// path then is the same for all groups; the caller routes the rare identity inputs to the single-group form).  ok[g] (memory
+// all cooperating threads see) receives the verdicts.  regs: L.groups register files, L.stride words apart.
+KZG_HD void coop_pairing_multi(Fp* regs, const G1Affine* P1, const LineCoeffs* c1, const G1Affine* P2, const LineCoeffs* c2, const Lanes& L,
+                               uint8_t* ok) {
+    for (int gi = L.tid; gi < L.groups; gi += L.n) {
+        Fp* r = L.file(regs, gi);
+        const uint32_t g[10][12] = {KZG_FP_FROB6_1_C0_M, KZG_FP_FROB6_1_C1_M, KZG_FP_FROB6_2_C0_M, KZG_FP_FROB6_2_C1_M, KZG_FP_FROB6_3_C0_M,
+                                    KZG_FP_FROB6_3_C1_M, KZG_FP_FROB6_4_C0_M, KZG_FP_FROB6_4_C1_M, KZG_FP_FROB6_5_C0_M, KZG_FP_FROB6_5_C1_M};
+        for (int i = 0; i < 10; i++) r[kRegConst + i] = fp_const(g[i]);
+        r[kRegP] = P1[gi].x; r[kRegP + 1] = P1[gi].y; r[kRegP + 2] = P2[gi].x; r[kRegP + 3] = P2[gi].y;
+        for (int i = 0; i < 12; i++) r[kRegF + i] = Fp::zero();
+        r[kRegF] = Fp::one();
+    }
+    L.sync();
+    int k = 0;
+    for (int bit = 62; bit >= 0; bit--) {
+        load_lines(regs, c1, c2, k++, L);
+        run(kProg_sqr_lines, regs, L);
+        run(kProg_f12_mul, regs, L);
+        if ((KZG_BLS_X_ABS >> bit) & 1) {
+            load_lines(regs, c1, c2, k++, L);
+            run(kProg_lines, regs, L);
+            run(kProg_f12_mul, regs, L);
+        }
+    }
+    run(kProg_conj, regs, L);
+    const int S0 = kSave0Thr, S1 = kSave0Thr + 12, S2 = kSave0Thr + 24, S3 = kSave0Thr + 36, S4 = kSave0Thr + 48;
+    copy_regs(regs, S0, kRegF, 12, L);
+    run(kProg_inv_prep, regs, L);
+    for (int gi = L.tid; gi < L.groups; gi += L.n) { Fp* r = L.file(regs, gi); r[kRegH + 8] = fp_inv_bingcd(r[kRegH + 8]); }
+    L.sync();
+    run(kProg_inv_finish, regs, L);
+    copy_regs(regs, kRegG, kRegF, 12, L);
+    copy_regs(regs, kRegF, S0, 12, L);
+    run(kProg_conj, regs, L);
+    run(kProg_f12_mul, regs, L);
+    run(kProg_frob2, regs, L);
+    run(kProg_f12_mul, regs, L);
+    copy_regs(regs, S0, kRegF, 12, L);
+    exp_by_x_slot(regs, S0, L);
+    copy_regs(regs, kRegG, S0, 12, L); run(kProg_conj_g, regs, L); run(kProg_f12_mul, regs, L);
+    copy_regs(regs, S1, kRegF, 12, L);
+    exp_by_x_slot(regs, S1, L);
+    copy_regs(regs, kRegG, S1, 12, L); run(kProg_conj_g, regs, L); run(kProg_f12_mul, regs, L);
+    copy_regs(regs, S1, kRegF, 12, L);
+    exp_by_x_slot(regs, S1, L);
+    copy_regs(regs, S2, kRegF, 12, L);
+    copy_regs(regs, kRegF, S1, 12, L); run(kProg_frob, regs, L);
+    copy_regs(regs, kRegF, S2, 12, L); run(kProg_f12_mul, regs, L);
+    copy_regs(regs, S2, kRegF, 12, L);
+    exp_by_x_slot(regs, S2, L);
+    copy_regs(regs, S3, kRegF, 12, L);
+    exp_by_x_slot(regs, S3, L);
+    copy_regs(regs, S4, kRegF, 12, L);
+    copy_regs(regs, kRegF, S2, 12, L); run(kProg_frob2, regs, L);
+    copy_regs(regs, kRegF, S4, 12, L); run(kProg_f12_mul, regs, L);
+    copy_regs(regs, kRegG, S2, 12, L); run(kProg_conj_g, regs, L); run(kProg_f12_mul, regs, L);
+    copy_regs(regs, S4, kRegF, 12, L);
+    copy_regs(regs, kRegF, S0, 12, L); run(kProg_f12_sqr, regs, L);
+    copy_regs(regs, kRegG, S0, 12, L); run(kProg_f12_mul, regs, L);
+    copy_regs(regs, kRegG, S4, 12, L); run(kProg_f12_mul, regs, L);
+    for (int gi = L.tid; gi < L.groups; gi += L.n) {
+        const Fp* r = L.file(regs, gi);
+        bool one = r[kRegF] == Fp::one();
+        for (int i = 1; i < 12; i++) one = one && r[kRegF + i].is_zero();
+        ok[gi] = one ? 1 : 0;
+    }
+    L.sync();
 }
 
 }  // namespace vliw

@@ -24,6 +24,7 @@ import pyref as R
 
 P = R.P
 MAX_LIN_TERMS = 24
+MAX_OPERAND_TERMS = 4
 
 
 class Val:
@@ -97,15 +98,27 @@ class Builder:
         self.cache[key] = dst
         return dst
 
+    def operand(self, v):
+        """A multiplication operand = up to MAX_OPERAND_TERMS registers with signs (small coefficients expand into repeated terms):
+        the multiplying thread forms the sum itself, lazily: sum(pos) + #neg * p - sum(neg) < 4p, one conditional subtraction of
+        2p brings it below 2p, which the Montgomery products tolerate (4 operands < 2p: ab + cd < 8 p^2 < R p).  Longer sums are
+        materialised by a LIN instruction.  Returns [(reg, minus), ...]."""
+        terms = []
+        for r, c in sorted(v.t.items()):
+            terms += [(r, c < 0)] * abs(c)
+        if 1 <= len(terms) <= MAX_OPERAND_TERMS and any(not minus for _, minus in terms):
+            terms.sort(key=lambda t: t[1])          # a positive term first
+            return terms
+        return [(self.materialize(v), False)]
+
     def mul(self, a, b, c=None, d=None, neg=False):
         """a*b (+|-) c*d"""
-        ra, rb = self.materialize(a), self.materialize(b)
-        srcs = [ra, rb]
+        ops = [self.operand(a), self.operand(b)]
         if c is not None:
-            srcs += [self.materialize(c), self.materialize(d)]
-        level = 1 + max(self.level_of[r] for r in srcs)
+            ops += [self.operand(c), self.operand(d)]
+        level = 1 + max(self.level_of[r] for o in ops for r, _ in o)
         dst = self._new(level)
-        self.instrs.append((level, "MUL", dst, (srcs, neg)))
+        self.instrs.append((level, "MUL", dst, (ops, neg)))
         return Val({dst: 1})
 
     def output(self, v, reg):
@@ -133,7 +146,7 @@ class Builder:
         last = max([i[0] for i in body] + [0])
         by_dst = {i[2]: i for i in body}
         def srcs_of(i):
-            return i[3][0] if i[1] == "MUL" else [r for r, _, _ in i[3]]
+            return mul_srcs(i[3][0]) if i[1] == "MUL" else [r for r, _, _ in i[3]]
         changed = True
         while changed:
             changed = False
@@ -153,13 +166,20 @@ class Builder:
         for lv, k, dst, pay in body:
             levels.setdefault((lv, k), []).append((k, dst, pay))
         prog = []
+        # LIN instructions of a level sorted by length: the threads of a warp then run sums of similar length (a warp runs as
+        # many term iterations as its longest sum)
+        by_len = lambda ins: sorted(ins, key=lambda i: -len(i[2]))
         for lv in range(1, last + 1):
             for kind in ("LIN", "MUL"):
                 if (lv, kind) in levels:
-                    prog.append((kind, levels[(lv, kind)]))
+                    prog.append((kind, by_len(levels[(lv, kind)]) if kind == "LIN" else levels[(lv, kind)]))
         if outs:
-            prog.append(("LIN", [("LIN", dst, pay) for _, _, dst, pay in outs]))
+            prog.append(("LIN", by_len([("LIN", dst, pay) for _, _, dst, pay in outs])))
         return prog
+
+
+def mul_srcs(ops):
+    return [r for o in ops for r, _ in o]
 
 
 def check_hazards(prog, n_inputs):
@@ -168,7 +188,7 @@ def check_hazards(prog, n_inputs):
         written = set(d for _, d, _ in ins)
         assert len(written) == len(ins), "two instructions of a level write the same register"
         for _, d, pay in ins:
-            srcs = pay[0] if kind == "MUL" else [r for r, _, _ in pay]
+            srcs = mul_srcs(pay[0]) if kind == "MUL" else [r for r, _, _ in pay]
             assert not ((set(srcs) - {d}) & written), "read/write hazard inside a level"
 
 
@@ -484,10 +504,11 @@ def run(prog, regs):
         new = {}
         for _, dst, pay in ins:
             if kind == "MUL":
-                (s, neg) = pay
-                v = regs[s[0]] * regs[s[1]]
-                if len(s) == 4:
-                    w = regs[s[2]] * regs[s[3]]
+                (ops, neg) = pay
+                val = lambda o: sum(-regs[r] if minus else regs[r] for r, minus in o)
+                v = val(ops[0]) * val(ops[1])
+                if len(ops) == 4:
+                    w = val(ops[2]) * val(ops[3])
                     v = v - w if neg else v + w
             else:
                 v = 0
@@ -576,16 +597,8 @@ def selftest(progs):
     print("python self-test of all programs: ok")
 
 
-def emit(progs, path):
-    out = ["// GENERATED by tools/gen_vliw.py -- do not edit.  Level-scheduled Fp programs for vliw.cuh.",
-           "#pragma once", "#include <stdint.h>", "namespace kzgb200 { namespace vliw {",
-           "constexpr int kRegF = 0, kRegG = %d, kRegH = %d, kRegLines = %d, kRegConst = %d, kRegP = %d, kNumInputRegs = %d;" % (RG, RH, RL, RC, RP, N_IN),
-           "// MUL instruction: dst, s0, s1, s2, s3 (s2 = 0xffff: single product), flag bit0 = subtract the second product",
-           "// LIN instruction: dst, first term index, term count; a term = reg | neg << 14 | dbl << 15",
-           "struct Level { uint16_t kind /*0 LIN, 1 MUL*/, count; uint32_t first; };",
-           "struct Program { uint16_t first_level, n_levels, n_regs; };"]
-    mul_tab, lin_tab, term_tab, level_tab, prog_tab, names = [], [], [], [], [], []
-    stats = []
+def tables_of(progs):
+    mul_tab, lin_tab, term_tab, level_tab, prog_tab, names, stats = [], [], [], [], [], [], []
     for name, prog in progs.items():
         first_level = len(level_tab)
         n_regs = N_IN
@@ -593,9 +606,16 @@ def emit(progs, path):
         for kind, ins in prog:
             if kind == "MUL":
                 level_tab.append((1, len(ins), len(mul_tab)))
-                for _, dst, (s, neg) in ins:
-                    s = list(s) + [0xffff, 0xffff] if len(s) == 2 else list(s)
-                    mul_tab.append((dst, s[0], s[1], s[2], s[3], 1 if neg else 0))
+                for _, dst, (ops, neg) in ins:
+                    ops = list(ops) + [[]] * (4 - len(ops))
+                    signs = 0
+                    row = [dst]
+                    for i, terms in enumerate(ops):
+                        slots = [r for r, _ in terms] + [0xffff] * (4 - len(terms))
+                        row += slots
+                        for j, (_, minus) in enumerate(terms):
+                            signs |= (1 << (4 * i + j)) if minus else 0
+                    mul_tab.append(tuple(row + [signs, 1 if neg else 0]))
                     n_regs = max(n_regs, dst + 1)
                 nmul += len(ins)
             else:
@@ -609,29 +629,56 @@ def emit(progs, path):
         prog_tab.append((first_level, len(level_tab) - first_level, n_regs))
         names.append(name)
         stats.append((name, len(level_tab) - first_level, nmul, nlin, n_regs))
-    out.append("enum ProgramId { " + ", ".join("kProg_%s = %d" % (n, i) for i, n in enumerate(names)) + ", kNumPrograms = %d };" % len(names))
-    out.append("constexpr int kMaxRegs = %d;" % max(p[2] for p in prog_tab))
-    out.append("constexpr int kNumMul = %d, kNumLin = %d, kNumTerm = %d, kNumLevel = %d;" % (len(mul_tab), len(lin_tab), len(term_tab), len(level_tab)))
-    out.append("static __device__ const uint16_t d_mul[%d][6] = {%s};" % (len(mul_tab), ",".join("{%d,%d,%d,%d,%d,%d}" % m for m in mul_tab)))
-    out.append("static __device__ const uint32_t d_lin[%d][3] = {%s};" % (len(lin_tab), ",".join("{%d,%d,%d}" % m for m in lin_tab)))
-    out.append("static __device__ const uint16_t d_term[%d] = {%s};" % (len(term_tab), ",".join(str(t) for t in term_tab)))
-    out.append("static __device__ const Level d_level[%d] = {%s};" % (len(level_tab), ",".join("{%d,%d,%d}" % l for l in level_tab)))
-    out.append("static __device__ const Program d_prog[%d] = {%s};" % (len(prog_tab), ",".join("{%d,%d,%d}" % p for p in prog_tab)))
-    # host copies for the CPU unit test of the interpreter
-    out.append("#ifndef __CUDA_ARCH__")
-    out.append("static const uint16_t h_mul[%d][6] = {%s};" % (len(mul_tab), ",".join("{%d,%d,%d,%d,%d,%d}" % m for m in mul_tab)))
-    out.append("static const uint32_t h_lin[%d][3] = {%s};" % (len(lin_tab), ",".join("{%d,%d,%d}" % m for m in lin_tab)))
-    out.append("static const uint16_t h_term[%d] = {%s};" % (len(term_tab), ",".join(str(t) for t in term_tab)))
-    out.append("static const Level h_level[%d] = {%s};" % (len(level_tab), ",".join("{%d,%d,%d}" % l for l in level_tab)))
-    out.append("static const Program h_prog[%d] = {%s};" % (len(prog_tab), ",".join("{%d,%d,%d}" % p for p in prog_tab)))
-    out.append("#endif")
+    return mul_tab, lin_tab, term_tab, level_tab, prog_tab, names, stats
+
+
+def emit(sets, path):
+    """sets: {"lat": programs for ONE check on one CTA (latency: sums are formed once, by LIN levels, in parallel),
+              "thr": programs for many checks in lockstep (throughput: multiplication operands of up to 4 terms are summed by
+                     the multiplying thread, which removes the operand LIN levels and their barriers)}"""
+    out = ["// GENERATED by tools/gen_vliw.py -- do not edit.  Level-scheduled Fp programs for vliw.cuh.",
+           "#pragma once", "#include <stdint.h>", "namespace kzgb200 { namespace vliw {",
+           "constexpr int kRegF = 0, kRegG = %d, kRegH = %d, kRegLines = %d, kRegConst = %d, kRegP = %d, kNumInputRegs = %d;" % (RG, RH, RL, RC, RP, N_IN),
+           "// MUL instruction (19 x u16): dst, then four operands of four register slots each (0xffff = unused; the first slot of an",
+           "// operand is always a positive term; the third operand unused: single product), then the sign bits: bit 4i+j = slot j of",
+           "// operand i is subtracted; last word: 1 = the second product as a whole is subtracted",
+           "// LIN instruction: dst, first term index, term count; a term = reg | neg << 14 | dbl << 15",
+           "struct Level { uint16_t kind /*0 LIN, 1 MUL*/, count; uint32_t first; };",
+           "struct Program { uint16_t first_level, n_levels, n_regs; };"]
+    first = True
+    maxes = [0, 0, 0, 0]
+    for tag, progs in sets.items():
+        mul_tab, lin_tab, term_tab, level_tab, prog_tab, names, stats = tables_of(progs)
+        if first:
+            out.append("enum ProgramId { " + ", ".join("kProg_%s = %d" % (n, i) for i, n in enumerate(names)) + ", kNumPrograms = %d };" % len(names))
+            first = False
+        maxes = [max(a, b) for a, b in zip(maxes, [len(mul_tab), len(lin_tab), len(term_tab), len(level_tab)])]
+        out.append("namespace %s {" % tag)
+        out.append("constexpr int kMaxRegs = %d;" % max(p[2] for p in prog_tab))
+        out.append("constexpr int kNumMul = %d, kNumLin = %d, kNumTerm = %d, kNumLevel = %d;" % (len(mul_tab), len(lin_tab), len(term_tab), len(level_tab)))
+        row = lambda m: "{" + ",".join(str(x) for x in m) + "}"
+        for qual, pre in (("static __device__ const", "d"), ("static const", "h")):
+            if pre == "h":
+                out.append("#ifndef __CUDA_ARCH__")
+            out.append("%s uint16_t %s_mul[%d][19] = {%s};" % (qual, pre, len(mul_tab), ",".join(row(m) for m in mul_tab)))
+            out.append("%s uint32_t %s_lin[%d][3] = {%s};" % (qual, pre, len(lin_tab), ",".join(row(m) for m in lin_tab)))
+            out.append("%s uint16_t %s_term[%d] = {%s};" % (qual, pre, len(term_tab), ",".join(str(t) for t in term_tab)))
+            out.append("%s Level %s_level[%d] = {%s};" % (qual, pre, len(level_tab), ",".join(row(l) for l in level_tab)))
+            out.append("%s Program %s_prog[%d] = {%s};" % (qual, pre, len(prog_tab), ",".join(row(p) for p in prog_tab)))
+            if pre == "h":
+                out.append("#endif")
+        out.append("}  // namespace %s" % tag)
+        print("-- %s" % tag)
+        for st in stats:
+            print("%-14s levels %2d  MUL %3d  LIN %3d  regs %3d" % st)
+    out.append("constexpr int kNumMulMax = %d, kNumLinMax = %d, kNumTermMax = %d, kNumLevelMax = %d;" % tuple(maxes))
     out.append("}}  // namespace kzgb200::vliw")
     open(path, "w").write("\n".join(out) + "\n")
-    for s in stats:
-        print("%-14s levels %2d  MUL %3d  LIN %3d  regs %3d" % s)
 
 
-if __name__ == "__main__":
+def build_all(max_operand_terms):
+    global MAX_OPERAND_TERMS
+    MAX_OPERAND_TERMS = max_operand_terms
     progs = {}
     for mk in PROGRAMS:
         B = mk()
@@ -639,5 +686,10 @@ if __name__ == "__main__":
         check_hazards(prog, N_IN)
         progs[B.name] = prog
     selftest(progs)
+    return progs
+
+
+if __name__ == "__main__":
+    sets = {"lat": build_all(1), "thr": build_all(4)}
     if "--check" not in sys.argv:
-        emit(progs, os.path.join(ROOT, "kzg_rs_b200", "csrc", "vliw_programs.cuh"))
+        emit(sets, os.path.join(ROOT, "kzg_rs_b200", "csrc", "vliw_programs.cuh"))

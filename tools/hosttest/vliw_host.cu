@@ -14,17 +14,34 @@ int main(int argc, char** argv) {
   // inversion self-check
   Fp x = Fp::from_u32(123456789u);
   for (int i = 0; i < 50; i++) { x = x * x + Fp::from_u32(i + 3); Fp a = vliw::fp_inv_bingcd(x), b = fp_inv(x); if (!(a == b)) { puts("bingcd mismatch"); return 4; } }
+  static G1Affine gen_table[64][15];
+  for (int w = 0; w < 64; w++) for (int d = 1; d <= 15; d++) { uint32_t k[8] = {0,0,0,0,0,0,0,0}; k[w / 8] = (uint32_t)d << (4 * (w % 8)); gen_table[w][d - 1] = g1_to_affine(scalar_mul_affine(g1_generator(), k, 256)); }
   std::vector<Fp> regs(vliw::kTotalRegs);
   vliw::Lanes L{0, 1, vliw::default_tables()};
   uint8_t rec[160];
+  std::vector<G1Affine> mx, mp; std::vector<uint8_t> mv;
   while (fread(rec, 1, 160, stdin) == 160) {
     Fr z, y; G1Affine C, pi; int v;
     if (!scalar_from_be32_checked(z, rec + 48) || !scalar_from_be32_checked(y, rec + 80) || !g1_from_compressed(C, rec, true) || !g1_from_compressed(pi, rec + 112, true)) v = 2;
     else {
       G1Affine X = kzg_lhs_point(C, z, y, pi), npi = pi; if (!npi.inf) npi.y = npi.y.neg();
+      // the table / GLV form of the same point (per-tuple batched path)
+      G1Affine Xf = g1_to_affine(kzg_lhs_point_fast(C, z, y, pi, gen_table));
+      if (Xf.inf != X.inf || (!X.inf && (!(Xf.x == X.x) || !(Xf.y == X.y)))) { puts("lhs mismatch"); return 5; }
       v = vliw::coop_pairing_product_is_one(regs.data(), X, T.g2_gen, npi, T.tau_g2, L) ? 1 : 0;
+      if (!X.inf && !npi.inf) { mx.push_back(X); mp.push_back(npi); mv.push_back((uint8_t)v); }
     }
     putchar('0' + v);
+  }
+  // the same checks three at a time in lockstep (multi-group form used by the many-tuple kernel)
+  const int G = 3;
+  std::vector<Fp> mregs(G * (vliw::kTotalRegs + 1));
+  vliw::Lanes LM{0, 1, vliw::throughput_tables()};
+  LM.groups = G; LM.stride = vliw::kTotalRegsThr * 12 + 1;
+  for (size_t i = 0; i + G <= mx.size() && i < 12; i += G) {
+    uint8_t ok[G];
+    vliw::coop_pairing_multi(mregs.data(), &mx[i], T.g2_gen, &mp[i], T.tau_g2, LM, ok);
+    for (int g = 0; g < G; g++) if (ok[g] != mv[i + g]) { puts("multi mismatch"); return 6; }
   }
   putchar('\n');
 }
