@@ -345,6 +345,7 @@ int alloc_leader_buffers(kzgb200_group* g) {
 
 extern "C" int kzgb200_group_create(kzgb200_group** out, const int* device_ids, int n_devices, const uint8_t* g2_points, size_t g2_points_len,
                                     size_t max_blobs_per_device) {
+    DeviceGuard dev;
     if (!out) return KZGB200_BAD_ARGS;
     *out = nullptr;
     if (!device_ids || n_devices < 1 || n_devices > kMaxRanks || max_blobs_per_device == 0) return KZGB200_BAD_ARGS;
@@ -390,6 +391,7 @@ extern "C" int kzgb200_group_create(kzgb200_group** out, const int* device_ids, 
 
 extern "C" int kzgb200_group_join(kzgb200_group** out, const char* session, int rank, int world, int device, const uint8_t* g2_points,
                                   size_t g2_points_len, size_t max_blobs_per_rank) {
+    DeviceGuard dev;
     if (!out) return KZGB200_BAD_ARGS;
     *out = nullptr;
     if (!session || !*session || world < 1 || world > kMaxRanks || rank < 0 || rank >= world || max_blobs_per_rank == 0) return KZGB200_BAD_ARGS;
@@ -459,6 +461,7 @@ extern "C" int kzgb200_group_join(kzgb200_group** out, const char* session, int 
 }
 
 extern "C" void kzgb200_group_destroy(kzgb200_group* g) {
+    DeviceGuard dev;
     if (!g) return;
     for (Member& m : g->local) {
         if (m.ctx) { cudaSetDevice(m.ctx->device); cudaDeviceSynchronize(); }
@@ -485,6 +488,7 @@ extern "C" int kzgb200_group_uses_peer_stores(const kzgb200_group* g, int local_
 extern "C" int kzgb200_group_verify_shards(kzgb200_group* g, const uint8_t* const* blobs, const uint8_t* const* commitments,
                                            const uint8_t* const* proofs, const size_t* n_local, int device_pointers, int* ok,
                                            uint8_t* const* z_out, uint8_t* const* y_out) {
+    DeviceGuard dev;
     if (!g || !blobs || !commitments || !proofs || !n_local || !ok) return KZGB200_BAD_ARGS;
     std::lock_guard<std::mutex> lk(g->lock);
     ShardArgs a[kMaxRanks];
@@ -497,6 +501,7 @@ extern "C" int kzgb200_group_verify_shards(kzgb200_group* g, const uint8_t* cons
 extern "C" int kzgb200_group_verify_blob_kzg_proof_batch(kzgb200_group* g, const uint8_t* blobs, size_t n_blobs, const uint8_t* commitments,
                                                          size_t n_commitments, const uint8_t* proofs, size_t n_proofs, int* ok, uint8_t* z_out,
                                                          uint8_t* y_out) {
+    DeviceGuard dev;
     if (!g || !ok || g->shm) return KZGB200_BAD_ARGS;
     if (n_blobs == 0) { *ok = 1; return KZGB200_OK; }                 // reference src/kzg_proof.rs:478-480
     if (n_blobs < 32 || g->world == 1)                                  // too small to shard (and the n = 1 dispatch of :482-489)
@@ -518,6 +523,7 @@ extern "C" int kzgb200_group_verify_blob_kzg_proof_batch(kzgb200_group* g, const
 
 // the gathered partials of the last collective call (leader only): world x KZGB200_PARTIAL_BYTES, for parity tests
 extern "C" int kzgb200_group_last_partials(kzgb200_group* g, uint8_t* out, size_t n_ranks) {
+    DeviceGuard dev;
     if (!g || !out || !g->d_x || n_ranks > (size_t)kMaxRanks) return KZGB200_BAD_ARGS;
     std::lock_guard<std::mutex> lk(g->lock);
     cudaSetDevice(g->local[0].ctx->device);

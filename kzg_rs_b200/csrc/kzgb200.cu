@@ -413,9 +413,10 @@ extern "C" int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_p
     kzgb200_ctx* ctx = new (std::nothrow) kzgb200_ctx();
     if (!ctx) return KZGB200_INTERNAL_ERROR;
     ctx->device = device;
+    DeviceGuard dev;
     auto fail = [&](int rc) { fprintf(stderr, "kzgb200_create: %s\n", ctx->err); kzgb200_destroy(ctx); return rc; };
     int rc = [&]() -> int {
-        CK(cudaSetDevice(device));
+        CK(cudaSetDevice(device));      // (restored by the guard below)
         CK(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device));
         int prio_lo = 0, prio_hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -473,7 +474,7 @@ extern "C" int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_p
 
 extern "C" void kzgb200_destroy(kzgb200_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    DeviceGuard dev(ctx->device);
     cudaDeviceSynchronize();
     delete ctx->pool;
     for (cudaStream_t st : {ctx->s_aux, ctx->s_copy, ctx->s_d2h, ctx->s_work[0], ctx->s_work[1], ctx->s_work[2], ctx->s_work[3]}) if (st) cudaStreamDestroy(st);
@@ -542,7 +543,7 @@ extern "C" int kzgb200_verify_blob_kzg_proof_batch_device(kzgb200_ctx* ctx, cons
                                                           const uint8_t* d_proofs, size_t n, int* ok, uint8_t* d_z_out, uint8_t* d_y_out) {
     if (!ctx || !ok || n == 0 || n > 0x7fffffff / 2) return KZGB200_BAD_ARGS;
     std::lock_guard<std::mutex> g(ctx->lock);
-    CK(cudaSetDevice(ctx->device));
+    DeviceGuard dev(ctx->device);
     int rc = ensure_capacity(ctx, n, false);
     if (rc) return rc;
     return batch_locked(ctx, d_blobs, nullptr, d_commitments, d_proofs, n, ok, d_z_out, d_y_out, nullptr, nullptr);
@@ -561,7 +562,7 @@ extern "C" int kzgb200_verify_blob_kzg_proof_batch(kzgb200_ctx* ctx, const uint8
     }
     if (n_blobs > 0x7fffffff / 2) return KZGB200_BAD_ARGS;
     std::lock_guard<std::mutex> g(ctx->lock);
-    CK(cudaSetDevice(ctx->device));
+    DeviceGuard dev(ctx->device);
     size_t n = n_blobs;
     int rc = ensure_capacity(ctx, n, true);
     if (rc) return rc;
@@ -588,7 +589,7 @@ extern "C" int kzgb200_verify_blob_kzg_proof_batch_each(kzgb200_ctx* ctx, const 
     if (!ctx || (n && (!blobs || !commitments || !proofs || !verdicts)) || n > 0x7fffffff / 2) return KZGB200_BAD_ARGS;
     if (n == 0) return KZGB200_OK;
     std::lock_guard<std::mutex> g(ctx->lock);
-    CK(cudaSetDevice(ctx->device));
+    DeviceGuard dev(ctx->device);
     int rc = ensure_capacity(ctx, n, true);
     if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->d_c, commitments, n * 48, cudaMemcpyHostToDevice, ctx->stream));
@@ -631,7 +632,7 @@ extern "C" int kzgb200_verify_kzg_proof_batch(kzgb200_ctx* ctx, const uint8_t* c
     if (!ctx || !ok || (n && (!commitments104 || !zs32 || !ys32 || !proofs104)) || n > 0x7fffffff / 2) return KZGB200_BAD_ARGS;
     if (n == 0) { *ok = 1; return KZGB200_OK; }     // empty sums: both pairing arguments are the identity
     std::lock_guard<std::mutex> g(ctx->lock);
-    CK(cudaSetDevice(ctx->device));
+    DeviceGuard dev(ctx->device);
     int rc = ensure_capacity(ctx, n, false);
     if (rc) return rc;
     if (n > ctx->many_cap) { CK(regrow(ctx->d_many, n * kManyBytesPerTuple)); ctx->many_cap = n; }
@@ -664,7 +665,7 @@ extern "C" int kzgb200_verify_kzg_proof_batch(kzgb200_ctx* ctx, const uint8_t* c
 extern "C" int kzgb200_compute_challenge(kzgb200_ctx* ctx, const uint8_t* blob, const uint8_t* commitment48, uint8_t* z_out32) {
     if (!ctx || !blob || !commitment48 || !z_out32) return KZGB200_BAD_ARGS;
     std::lock_guard<std::mutex> g(ctx->lock);
-    CK(cudaSetDevice(ctx->device));
+    DeviceGuard dev(ctx->device);
     int rc = ensure_capacity(ctx, 1, true);
     if (rc) return rc;
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_parse, 0));
@@ -682,7 +683,7 @@ extern "C" int kzgb200_compute_challenge(kzgb200_ctx* ctx, const uint8_t* blob, 
 extern "C" int kzgb200_evaluate_polynomial_in_evaluation_form(kzgb200_ctx* ctx, const uint8_t* blob, const uint8_t* z32, uint8_t* y_out32) {
     if (!ctx || !blob || !z32 || !y_out32) return KZGB200_BAD_ARGS;
     std::lock_guard<std::mutex> g(ctx->lock);
-    CK(cudaSetDevice(ctx->device));
+    DeviceGuard dev(ctx->device);
     int rc = ensure_capacity(ctx, 1, true);
     if (rc) return rc;
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_parse, 0));
@@ -706,7 +707,7 @@ extern "C" int kzgb200_verify_kzg_proof_many(kzgb200_ctx* ctx, const uint8_t* co
     if (!ctx || (m && (!commitments || !zs || !ys || !proofs || !verdicts))) return KZGB200_BAD_ARGS;
     if (m == 0) return KZGB200_OK;
     std::lock_guard<std::mutex> g(ctx->lock);
-    CK(cudaSetDevice(ctx->device));
+    DeviceGuard dev(ctx->device);
     const size_t kChunk = (size_t)1 << 20, c = m < kChunk ? m : kChunk;
     if (c > ctx->many_cap) { CK(regrow(ctx->d_many, c * kManyBytesPerTuple)); ctx->many_cap = c; }
     G1Affine *dC = reinterpret_cast<G1Affine*>(ctx->d_many), *dP = dC + c, *dX = dP + c;
@@ -766,7 +767,7 @@ extern "C" int kzgb200_harness_generate(kzgb200_ctx* ctx, uint64_t seed, size_t 
                                         uint8_t* d_blobs, uint8_t* d_commitments, uint8_t* d_proofs) {
     if (!ctx || n == 0 || degree < 2 || degree > kHarnessMaxDegree || !tau_powers48) return KZGB200_BAD_ARGS;
     std::lock_guard<std::mutex> g(ctx->lock);
-    CK(cudaSetDevice(ctx->device));
+    DeviceGuard dev(ctx->device);
     int rc = ensure_capacity(ctx, n, false);
     if (rc) return rc;
     uint8_t* d_bytes = nullptr; G1Affine* d_M = nullptr; uint32_t* d_bad = nullptr; uint32_t bad = 0;
@@ -795,7 +796,7 @@ extern "C" int kzgb200_set_transcript_mode(kzgb200_ctx* ctx, int mode) {
 extern "C" int kzgb200_last_r(kzgb200_ctx* ctx, uint8_t* r_out32) {
     if (!ctx || !r_out32) return KZGB200_BAD_ARGS;
     std::lock_guard<std::mutex> g(ctx->lock);
-    CK(cudaSetDevice(ctx->device));
+    DeviceGuard dev(ctx->device);
     // scratch: the first ZY slot of the (idle) z/y export buffers
     ZY* tmp = reinterpret_cast<ZY*>(ctx->d_scratch);
     uint8_t* d_out = ctx->d_scratch + sizeof(ZY);
@@ -810,7 +811,7 @@ extern "C" int kzgb200_last_r(kzgb200_ctx* ctx, uint8_t* r_out32) {
 extern "C" int kzgb200_last_partial(kzgb200_ctx* ctx, uint8_t* out352) {
     if (!ctx || !out352) return KZGB200_BAD_ARGS;
     std::lock_guard<std::mutex> g(ctx->lock);
-    CK(cudaSetDevice(ctx->device));
+    DeviceGuard dev(ctx->device);
     CK(cudaMemcpyAsync(out352, ctx->d_partial, sizeof(Partial), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return KZGB200_OK;
@@ -819,7 +820,7 @@ extern "C" int kzgb200_last_partial(kzgb200_ctx* ctx, uint8_t* out352) {
 extern "C" int kzgb200_set_profiling(kzgb200_ctx* ctx, int on) {
     if (!ctx) return KZGB200_BAD_ARGS;
     std::lock_guard<std::mutex> g(ctx->lock);
-    CK(cudaSetDevice(ctx->device));
+    DeviceGuard dev(ctx->device);
     if (on) { for (auto& e : ctx->ev_s) if (!e) CK(cudaEventCreate(&e)); for (auto& e : ctx->ev_e) if (!e) CK(cudaEventCreate(&e)); }
     ctx->profile = on != 0;
     return KZGB200_OK;
@@ -833,7 +834,7 @@ extern "C" int kzgb200_get_phase_ms(kzgb200_ctx* ctx, float* out7) {
 extern "C" int kzgb200_load_g1_lagrange(kzgb200_ctx* ctx, const uint8_t* g1_lagrange, size_t n_points) {
     if (!ctx || !g1_lagrange || n_points != (size_t)kFieldElementsPerBlob) return KZGB200_INVALID_SETUP;
     std::lock_guard<std::mutex> g(ctx->lock);
-    CK(cudaSetDevice(ctx->device));
+    DeviceGuard dev(ctx->device);
     if (ctx->d_lag_table) return KZGB200_OK;
     uint8_t* d_bytes = nullptr; G1Affine* d_L = nullptr; uint32_t* d_bad = nullptr; uint32_t bad = 0;
     CK(cudaMalloc(&d_bytes, n_points * 48)); CK(cudaMalloc(&d_L, n_points * sizeof(G1Affine))); CK(cudaMalloc(&d_bad, 4));
@@ -880,21 +881,21 @@ static int commit_or_prove(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8
 extern "C" int kzgb200_blob_to_kzg_commitment_batch(kzgb200_ctx* ctx, const uint8_t* d_blobs, size_t n, uint8_t* d_commitments_out) {
     if (!ctx || !d_blobs || !d_commitments_out || n == 0) return KZGB200_BAD_ARGS;
     std::lock_guard<std::mutex> g(ctx->lock);
-    CK(cudaSetDevice(ctx->device));
+    DeviceGuard dev(ctx->device);
     return commit_or_prove(ctx, d_blobs, nullptr, n, d_commitments_out, 0);
 }
 extern "C" int kzgb200_compute_blob_kzg_proof_batch(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t* d_commitments, size_t n,
                                                     uint8_t* d_proofs_out) {
     if (!ctx || !d_blobs || !d_commitments || !d_proofs_out || n == 0) return KZGB200_BAD_ARGS;
     std::lock_guard<std::mutex> g(ctx->lock);
-    CK(cudaSetDevice(ctx->device));
+    DeviceGuard dev(ctx->device);
     return commit_or_prove(ctx, d_blobs, d_commitments, n, d_proofs_out, 1);
 }
 // clock64() stamps of the last single-GPU batch_final_kernel: start, prelude end, Miller loop end, easy part end, hard part end, done
 extern "C" int kzgb200_debug_final_ticks(kzgb200_ctx* ctx, long long* out14) {
     if (!ctx || !out14) return KZGB200_BAD_ARGS;
     std::lock_guard<std::mutex> g(ctx->lock);
-    CK(cudaSetDevice(ctx->device));
+    DeviceGuard dev(ctx->device);
     CK(cudaMemcpy(out14, ctx->d_scratch + 128, 112, cudaMemcpyDeviceToHost));
     return KZGB200_OK;
 }

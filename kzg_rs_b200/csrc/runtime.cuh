@@ -129,6 +129,15 @@ struct kzgb200_ctx {
 
 namespace kzgb200 {
 
+// Every entry point runs on its context's GPU and leaves the calling thread's current CUDA device as it found it (callers
+// such as PyTorch cache the current device and would otherwise allocate on the wrong GPU afterwards).
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int device) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; cudaSetDevice(device); }
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 template <class T>
 inline cudaError_t regrow(T*& p, size_t count) {
     if (p) cudaFree(p);

@@ -318,6 +318,33 @@ def _sum_partials(api, parts):
     return {"A": A, "B_prime": Bp, "sum_r_y": s}
 
 
+def test_group_across_all_visible_gpus(K, settings, oracle):
+    """One process driving every visible GPU (kzgb200_group_create with device ids 0..N-1): the partial sums travel by peer
+    stores over NVLink into the leader GPU.  Skipped on a single-GPU box (the two-contexts-on-one-GPU tests cover the protocol)."""
+    import torch
+    from kzg_rs_b200 import api
+    ng = torch.cuda.device_count()
+    if ng < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = 64 * ng + 24
+    _, (hb, hc, hp) = harness(K, settings, n, 0x9d0 + ng)
+    rc, ok_ref, z_ref, y_ref, tr = oracle.verify_batch_raw(hb, hc, hp, n, nthreads=os.cpu_count(), want_trace=True)
+    with K.DeviceGroup.create(settings, list(range(ng)), 4096) as g:
+        assert [g.uses_peer_stores(i) for i in range(ng)] == [True] * ng
+        ok, z, y = g.verify_blob_kzg_proof_batch_raw(hb, n, hc, n, hp, n, want_zy=True)
+        assert ok is True and z == z_ref and y == y_ref
+        lib = K.Library.get().dll
+        for i in range(ng):
+            r = C.create_string_buffer(32)
+            assert lib.kzgb200_last_r(g.context(i), r) == 0 and r.raw == tr["r"]
+        check_sums(_sum_partials(api, g.last_partials(ng)), tr)
+        bad = bytearray(hp); bad[48 * (n - 1):48 * n] = hp[:48]
+        assert g.verify_blob_kzg_proof_batch_raw(hb, n, hc, n, bytes(bad), n) is False
+        badb = bytearray(hb); badb[(n - 1) * 131072 + 64:(n - 1) * 131072 + 96] = Q.to_bytes(32, "big")
+        assert tri(lambda: g.verify_blob_kzg_proof_batch_raw(bytes(badb), n, hc, n, hp, n)) is None
+        assert g.verify_blob_kzg_proof_batch_raw(hb, n, hc, n, hp, n) is True
+
+
 @pytest.mark.parametrize("no_p2p", [0, 1])
 def test_group_of_two_contexts_on_one_gpu(K, settings, oracle, no_p2p):
     """The multi-GPU path behind the ABI with world = 2 on cuda:0 (one process, two contexts): shards, transcript exchange, r,
