@@ -334,10 +334,12 @@ def test_group_across_all_visible_gpus(K, settings, oracle):
         ok, z, y = g.verify_blob_kzg_proof_batch_raw(hb, n, hc, n, hp, n, want_zy=True)
         assert ok is True and z == z_ref and y == y_ref
         lib = K.Library.get().dll
-        for i in range(ng):
+        from kzg_rs_b200.sharded import shard_ranges
+        active = sum(1 for lo, hi in shard_ranges(n, ng) if hi > lo)      # shards are multiples of 16 blobs: the last GPUs may stay idle
+        for i in range(active):
             r = C.create_string_buffer(32)
             assert lib.kzgb200_last_r(g.context(i), r) == 0 and r.raw == tr["r"]
-        check_sums(_sum_partials(api, g.last_partials(ng)), tr)
+        check_sums(_sum_partials(api, g.last_partials(active)), tr)
         bad = bytearray(hp); bad[48 * (n - 1):48 * n] = hp[:48]
         assert g.verify_blob_kzg_proof_batch_raw(hb, n, hc, n, bytes(bad), n) is False
         badb = bytearray(hb); badb[(n - 1) * 131072 + 64:(n - 1) * 131072 + 96] = Q.to_bytes(32, "big")
