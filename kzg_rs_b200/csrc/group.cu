@@ -55,7 +55,9 @@ struct XShared {
     std::atomic<uint32_t> path[kMaxRanks];          // how rank k delivers its partial: 1 = peer store into the leader GPU, 2 = through this block
     std::atomic<uint32_t> ipc_ready;                // 1: handle valid, 2: the leader could not export one
     unsigned char ipc_handle[64];
-    // then: c[world][cap][48], zy[world][cap][64], p[world][cap][48]
+    // then: entries[world][cap][160] -- each rank's transcript entries already in the byte order compute_r_powers hashes
+    // (C_i | z_i LE | y_i LE | pi_i), so that the leader hashes them in place (tree mode: 32-byte leaf digests at the start
+    // of the rank's region)
 };
 static_assert(sizeof(cudaIpcMemHandle_t) <= 64, "IPC handle size");
 size_t shared_bytes(int world, size_t cap) { return ((sizeof(XShared) + 63) & ~(size_t)63) + (size_t)world * cap * 160; }
@@ -108,11 +110,8 @@ struct kzgb200_group {
     size_t hashed[kMaxRanks] = {0};
     std::mutex lock;
     char err[256] = {0};
-    uint8_t* arr(int which, int rank) const {   // 0: c, 1: zy, 2: p
-        uint8_t* base = reinterpret_cast<uint8_t*>(sh) + ((sizeof(XShared) + 63) & ~(size_t)63);
-        size_t cap = sh->cap, w = (size_t)world;
-        size_t off = which == 0 ? 0 : (which == 1 ? w * cap * 48 : w * cap * 112);
-        return base + off + (size_t)rank * cap * (which == 1 ? 64 : 48);
+    uint8_t* entries(int rank) const {          // rank's region of the shared block: cap x 160 bytes
+        return reinterpret_cast<uint8_t*>(sh) + ((sizeof(XShared) + 63) & ~(size_t)63) + (size_t)rank * sh->cap * 160;
     }
     bool leader_here() const { return !local.empty() && local[0].rank == 0; }
 };
@@ -135,11 +134,14 @@ void publish_chunk(void* arg, int c) {
     if (ctx->transcript_mode == KZGB200_TRANSCRIPT_TREE) {
         size_t ngroups = (m->n + kTreeGroup - 1) / kTreeGroup;
         size_t g0 = lo / kTreeGroup, g1 = end >= m->n ? ngroups : end / kTreeGroup;
-        memcpy(g->arr(1, m->rank) + g0 * 32, ctx->h_zy + g0 * 32, (g1 - g0) * 32);     // leaf digests
+        memcpy(g->entries(m->rank) + g0 * 32, ctx->h_zy + g0 * 32, (g1 - g0) * 32);     // leaf digests
     } else {
-        memcpy(g->arr(0, m->rank) + lo * 48, ctx->tr_c + lo * 48, cnt * 48);
-        memcpy(g->arr(1, m->rank) + lo * 64, ctx->h_zy + lo * 64, cnt * 64);
-        memcpy(g->arr(2, m->rank) + lo * 48, ctx->tr_p + lo * 48, cnt * 48);
+        uint8_t* e = g->entries(m->rank) + lo * 160;       // interleaved by the publishing rank: the leader's hash stays one pass
+        for (size_t i = lo; i < end; i++, e += 160) {
+            memcpy(e, ctx->tr_c + 48 * i, 48);
+            memcpy(e + 48, ctx->h_zy + 64 * i, 64);
+            memcpy(e + 112, ctx->tr_p + 48 * i, 48);
+        }
     }
     g->sh->ready[m->rank].store(((uint64_t)g->epoch << 32) | (uint64_t)end, std::memory_order_release);
 }
@@ -155,9 +157,9 @@ bool leader_hash_available(kzgb200_group* g, int aw, const size_t* n_of, bool tr
                 if (tree) {
                     size_t ng = (n_of[k] + kTreeGroup - 1) / kTreeGroup;
                     size_t g0 = g->hashed[k] / kTreeGroup, g1 = avail >= n_of[k] ? ng : avail / kTreeGroup;
-                    host_sha256_update(&g->sha, g->arr(1, k) + g0 * 32, (g1 - g0) * 32);
+                    host_sha256_update(&g->sha, g->entries(k) + g0 * 32, (g1 - g0) * 32);
                 } else {
-                    hash_entries(&g->sha, g->arr(0, k), g->arr(1, k), g->arr(2, k), g->hashed[k], avail - g->hashed[k]);
+                    host_sha256_update(&g->sha, g->entries(k) + g->hashed[k] * 160, (avail - g->hashed[k]) * 160);
                 }
                 g->hashed[k] = avail;
             }
@@ -582,9 +584,12 @@ extern "C" int kzgb200_group_host_protocol_test(const char* session, int rank, i
         if (!rc && !wait_until([&] {
                 if (pub < n_local) {     // publish the next chunk
                     size_t cnt = n_local - pub < chunk ? n_local - pub : chunk;
-                    memcpy(g->arr(0, rank) + pub * 48, commitments + pub * 48, cnt * 48);
-                    memcpy(g->arr(1, rank) + pub * 64, zy + pub * 64, cnt * 64);
-                    memcpy(g->arr(2, rank) + pub * 48, proofs + pub * 48, cnt * 48);
+                    uint8_t* e = g->entries(rank) + pub * 160;
+                    for (size_t i = pub; i < pub + cnt; i++, e += 160) {
+                        memcpy(e, commitments + 48 * i, 48);
+                        memcpy(e + 48, zy + 64 * i, 64);
+                        memcpy(e + 112, proofs + 48 * i, 48);
+                    }
                     pub += cnt;
                     sh->ready[rank].store(((uint64_t)epoch << 32) | pub, std::memory_order_release);
                 }
