@@ -6,6 +6,7 @@
 #include "sha256.cuh"
 #include "verify.cuh"
 #include "vliw.cuh"
+#include "vliw29.cuh"
 #include "glv.cuh"
 
 namespace kzgb200 {
@@ -28,6 +29,8 @@ struct DeviceTables {
     // thread + 1 pad, so the stream is sequential and the next one can be fetched while the current merge runs
     Fr twiddle_po[128][32];
     PairingTables pairing;
+    // the same line triples in the representation of the cooperative pairing engine (vliw29.cuh): [0] = G2 generator, [1] = [tau]G2
+    vliw29::LineCoeffs29 lines29[2][kMillerSteps];
     // fixed-base table of the G1 generator: gen_table[w][d-1] = [d * 16^w] G, d = 1..15, w < 64
     G1Affine gen_table[64][15];
     uint32_t setup_ok;
@@ -76,15 +79,16 @@ struct Partial {
 
 // dynamic shared memory of the final kernels: engine register file, program tables, G1 tree scratch (> 48 KB: opt-in)
 struct FinalSmem {
-    Fp regs[vliw::kTotalRegs];
+    f29::F29 regs[vliw29::kTotalRegs];
     G1 sm[kFinalThreads];
-    vliw::SharedTables stab;
+    vliw29::SharedTables stab;
 };
 
 constexpr int kManyStride = vliw::kTotalRegsThr * 12 + 1;     // words between the register files of consecutive groups (odd: bank skew)
 constexpr int kManySmemBytes = kManyGroups * kManyStride * 4 + (int)sizeof(vliw::SharedTables) + kManyGroups * (2 * (int)sizeof(G1Affine) + 2) + 64;
 // ---- kernels (k_*.cu) ----------------------------------------------------------------------------------------
 __global__ void setup_tables_kernel(DeviceTables* T, const uint8_t* g2_points);
+__global__ void setup_lines29_kernel(DeviceTables* T);
 void launch_challenge(int stages, cudaStream_t st, const uint8_t* blobs, const uint8_t* commitments, int n, Fr* z_mont, ZY* zy, Fr* zpow);   // K2
 __global__ void eval_kernel(const uint8_t* __restrict__ blobs, int n, const Fr* __restrict__ zpow, const DeviceTables* __restrict__ T,
                             ZY* __restrict__ zy, uint32_t* __restrict__ status);

@@ -43,7 +43,9 @@ __device__ __forceinline__ void coop_dbl(CoopPoint* s, int lane) {
 __device__ __forceinline__ void coop_add(CoopPoint* s, const G1& q, int lane) {
     Fp* v = s->v;
     if (q.is_identity()) return;
-    if (v[2].is_zero()) { if (lane == 0) { v[0] = q.x; v[1] = q.y; v[2] = q.z; } __syncwarp(); return; }
+    const bool acc_is_identity = v[2].is_zero();                  // uniform; every lane has read Z before lane 0 may overwrite it
+    __syncwarp();
+    if (acc_is_identity) { if (lane == 0) { v[0] = q.x; v[1] = q.y; v[2] = q.z; } __syncwarp(); return; }
     int k = lane & 3;
     Fp X1 = v[0], Y1 = v[1], Z1 = v[2];
     // level 1: Z1*Z1, Z2*Z2, Z1*Z2

@@ -12,7 +12,7 @@ __global__ void __launch_bounds__(kFinalThreads) batch_final_kernel(const Partia
                                                                     uint32_t* __restrict__ result, long long* __restrict__ ticks) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     FinalSmem& S = *reinterpret_cast<FinalSmem*>(dyn_smem);
-    Fp* regs = S.regs;
+    f29::F29* regs = S.regs;
     G1* sm = S.sm;
     __shared__ G1Affine pts[2];
     __shared__ Fr s_sum;
@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(kFinalThreads) batch_final_kernel(const Partia
     int t = threadIdx.x;
     if (t == 0) result[2] = 0;
     if (ticks && t == 0) { ticks[0] = clock64(); for (int i = 8; i < 14; i++) ticks[i] = 0; }
-    vliw::Tables tab = vliw::load_tables(&S.stab, t, kFinalThreads);
+    vliw29::Tables tab = vliw29::load_tables(&S.stab, t, kFinalThreads);
     if (t == 0) {
         Fr s = Fr::zero(); uint32_t err = 0;
         for (int k = 0; k < nparts; k++) { s = s.add_inl(parts[k].ry); err |= parts[k].err; }
@@ -40,8 +40,8 @@ __global__ void __launch_bounds__(kFinalThreads) batch_final_kernel(const Partia
         pts[w] = a;
     }
     __syncthreads();
-    vliw::Lanes L{t, kFinalThreads, tab, ticks};
-    bool ok = vliw::coop_pairing_product_is_one(regs, pts[1], T->pairing.g2_gen, pts[0], T->pairing.tau_g2, L);
+    vliw29::Lanes L{t, kFinalThreads, tab, ticks};
+    bool ok = vliw29::coop_pairing_product_is_one(regs, pts[1], T->lines29[0], pts[0], T->lines29[1], L);
     L.tick(5);
     if (t == 0) { result[0] = ok ? kTrue : kFalse; result[1] = 0; }
 }

@@ -11,12 +11,12 @@ __global__ void __launch_bounds__(kFinalThreads) single_final_kernel(const G1Aff
                                                                      uint32_t* __restrict__ result) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     FinalSmem& S = *reinterpret_cast<FinalSmem*>(dyn_smem);
-    Fp* regs = S.regs;
+    f29::F29* regs = S.regs;
     G1* sm = S.sm;
     __shared__ G1Affine pts[2];
     int t = threadIdx.x;
     if (t == 0) result[2] = 0;
-    vliw::Tables tab = vliw::load_tables(&S.stab, t, kFinalThreads);
+    vliw29::Tables tab = vliw29::load_tables(&S.stab, t, kFinalThreads);
     if (status[0]) { if (t == 0) { result[0] = kBadArgs; result[1] = status[0]; } return; }
     G1 yg = coop_fixed_base_mul(zy[0].y, T, sm);
     __shared__ CoopPoint ladder;
@@ -41,8 +41,8 @@ __global__ void __launch_bounds__(kFinalThreads) single_final_kernel(const G1Aff
         pts[1] = np;
     }
     __syncthreads();
-    vliw::Lanes L{t, kFinalThreads, tab};
-    bool ok = vliw::coop_pairing_product_is_one(regs, pts[0], T->pairing.g2_gen, pts[1], T->pairing.tau_g2, L);
+    vliw29::Lanes L{t, kFinalThreads, tab};
+    bool ok = vliw29::coop_pairing_product_is_one(regs, pts[0], T->lines29[0], pts[1], T->lines29[1], L);
     if (t == 0) { result[0] = ok ? kTrue : kFalse; result[1] = 0; }
 }
 

@@ -44,4 +44,14 @@ __global__ void setup_tables_kernel(DeviceTables* T, const uint8_t* g2_points /*
     }
 }
 
+// line tables of the two fixed G2 points in the pairing engine's 29-bit-limb representation (one value per thread)
+__global__ void setup_lines29_kernel(DeviceTables* T) {
+    int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= 2 * kMillerSteps * 6) return;
+    int q = tid / (kMillerSteps * 6), k = (tid / 6) % kMillerSteps, e = tid % 6;
+    const LineCoeffs& l = q == 0 ? T->pairing.g2_gen[k] : T->pairing.tau_g2[k];
+    const Fp2& f2 = e < 2 ? l.A : (e < 4 ? l.B : l.C);
+    T->lines29[q][k].v[e] = f29::from_fp((e & 1) ? f2.c1 : f2.c0);
+}
+
 }  // namespace kzgb200

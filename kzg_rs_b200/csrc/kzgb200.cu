@@ -460,6 +460,7 @@ extern "C" int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_p
         CK(cudaMalloc(&d_g2, 192));
         CK(cudaMemcpyAsync(d_g2, g2_points, 192, cudaMemcpyHostToDevice, ctx->stream));
         setup_tables_kernel<<<(8192 + 4096) / 128, 128, 0, ctx->stream>>>(ctx->tables, d_g2);
+        setup_lines29_kernel<<<(2 * kMillerSteps * 6 + 127) / 128, 128, 0, ctx->stream>>>(ctx->tables);
         CK(cudaGetLastError());
         uint32_t ok = 0;
         CK(cudaMemcpyAsync(&ok, &ctx->tables->setup_ok, 4, cudaMemcpyDeviceToHost, ctx->stream));

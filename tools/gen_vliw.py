@@ -54,6 +54,8 @@ class Val:
 
 
 class Builder:
+    headroom = False            # Builder29: values carry slack (multiples of p) instead of being reduced after every sum
+
     def __init__(self, name, n_inputs):
         self.name = name
         self.n_inputs = n_inputs
@@ -178,6 +180,182 @@ class Builder:
         return prog
 
 
+BUILDER = Builder
+
+# ------------------------------------------------------------------------------------------ headroom programs (vliw29.cuh)
+# Second engine representation: Fp values as 14 limbs of 29 bits (406 bits, Montgomery radix 2^406 = 2^25.3 p), products as
+# carry-free 64-bit column sums (IMAD.WIDE without the carry chain: twice the issue rate of IMAD.WIDE.X, and independent
+# columns instead of one long chain).  The 25 spare bits replace the modular reduction after every sum: a register holds ANY
+# representative below bound * p, the bounds are tracked HERE, statically:
+#   MUL  d = (a b + c d') / 2^406 : needs A B + C D <= 2^23 (bounds in units of p) and yields a value below 1.25 p;
+#   LIN  d = K p + sum +-(1|2) src : K = ceil(sum of the bounds of the subtracted terms) keeps the sum non-negative; no
+#        reduction unless the bound leaves LIN_LIMIT (program outputs: IO_BOUND), in which case the instruction carries a
+#        `reduce` flag: the executing thread subtracts floor-estimate(v / p) * p (float estimate from the two top columns,
+#        error < 4), leaving a value below RED_BOUND * p.
+# A product subtracted as a whole, a b - c d, runs as signed column sums plus Kx p^2, Kx = ceil(C D).
+import math
+from fractions import Fraction
+
+W29, N29 = 29, 14
+R29 = 1 << (W29 * N29)
+IO_BOUND = 8
+RED_BOUND = 6
+LIN_LIMIT = 1024
+MUL_BOUND = Fraction(5, 4)
+MULSUM_LIMIT = 1 << 23
+
+
+class Terms(list):
+    """LIN payload of the headroom programs: the term list, the multiple of p added, the reduce flag"""
+    K = 0
+    reduce = False
+
+
+class Builder29(Builder):
+    headroom = True
+
+    def __init__(self, name, n_inputs):
+        super().__init__(name, n_inputs)
+        self.bound = {r: Fraction(IO_BOUND) for r in range(n_inputs)}
+        self.out_bounds = []
+
+    @staticmethod
+    def _terms(v):
+        terms = []
+        for r, c in sorted(v.t.items()):
+            neg, c = c < 0, abs(c)
+            while c >= 2:
+                terms.append((r, neg, True))
+                c -= 2
+            if c:
+                terms.append((r, neg, False))
+        return terms
+
+    def _meta(self, terms, limit):
+        w = lambda t: (2 if t[2] else 1) * self.bound[t[0]]
+        pos = sum((w(t) for t in terms if not t[1]), Fraction(0))
+        neg = sum((w(t) for t in terms if t[1]), Fraction(0))
+        K = int(math.ceil(neg))
+        b = pos + K
+        assert b < (1 << 20), "sum too large for the float quotient estimate"
+        t = Terms(terms)
+        t.K, t.reduce = K, b > limit
+        return t, (Fraction(RED_BOUND) if t.reduce else b)
+
+    def materialize(self, v):
+        if len(v.t) == 1 and list(v.t.values())[0] == 1:
+            return list(v.t.keys())[0]
+        key = tuple(sorted(v.t.items()))
+        if key in self.cache:
+            return self.cache[key]
+        terms = self._terms(v)
+        if len(terms) > MAX_LIN_TERMS:
+            items = sorted(v.t.items())
+            half = len(items) // 2
+            a = self.materialize(Val(dict(items[:half])))
+            b = self.materialize(Val(dict(items[half:])))
+            return self.materialize(Val({a: 1}) + Val({b: 1}))
+        level = 1 + max((self.level_of[r] for r, _, _ in terms), default=0)
+        dst = self._new(level)
+        pay, self.bound[dst] = self._meta(terms, LIN_LIMIT)
+        self.instrs.append((level, "LIN", dst, pay))
+        self.cache[key] = dst
+        return dst
+
+    def operand(self, v):
+        return [(self.materialize(v), False)]
+
+    def mul(self, a, b, c=None, d=None, neg=False):
+        """a b (+|-) c d.  A subtracted product is executed natively: signed column sums plus Kx p^2 with
+        Kx = ceil(C D) >= c d / p^2, so that the total stays non-negative for the Montgomery reduction."""
+        ops = [self.operand(a), self.operand(b)]
+        if c is not None:
+            ops += [self.operand(c), self.operand(d)]
+        bs = [self.bound[o[0][0]] for o in ops]
+        total = bs[0] * bs[1] + (bs[2] * bs[3] if c is not None else 0)
+        kx = int(math.ceil(bs[2] * bs[3])) if (c is not None and neg) else 0
+        assert total + 1 <= MULSUM_LIMIT, "operand bounds too large"
+        level = 1 + max(self.level_of[r] for o in ops for r, _ in o)
+        dst = self._new(level)
+        self.bound[dst] = MUL_BOUND
+        self.instrs.append((level, "MUL", dst, (ops, ("neg", kx) if neg else False)))
+        return Val({dst: 1})
+
+    def output(self, v, reg):
+        terms = self._terms(v)
+        if len(terms) > MAX_LIN_TERMS:
+            terms = [(self.materialize(v), False, False)]
+        level = 1 + max((self.level_of[r] for r, _, _ in terms), default=0)
+        pay, b = self._meta(terms, IO_BOUND)
+        assert b <= IO_BOUND
+        self.instrs.append((level, "OUT", reg, pay))
+
+
+def limbs29(v):
+    assert 0 <= v < R29
+    return [(v >> (W29 * i)) & ((1 << W29) - 1) for i in range(N29)]
+
+
+def lin29_exact(values, pay):
+    """the LIN instruction exactly as vliw29.cuh executes it: 64-bit column sums, K p added, the float32 quotient estimate"""
+    import numpy as np
+    f32 = np.float32
+    pl = limbs29(P)
+    t = [0] * N29
+    for r, ng, db in pay:
+        c = (2 if db else 1) * (-1 if ng else 1)
+        for i, x in enumerate(limbs29(values[r])):
+            t[i] += c * x
+    for i in range(N29):
+        t[i] += pay.K * pl[i]
+        assert -(1 << 63) <= t[i] < (1 << 63)
+    if pay.reduce:
+        vf = f32(f32(t[13]) * f32(536870912.0)) + f32(t[12])
+        pinv = f32(1.0) / f32(f32(f32(pl[13]) * f32(536870912.0)) + f32(pl[12]) + f32(1.0))
+        q = int(f32(vf * pinv)) - 2
+        if q < 0:
+            q = 0
+        for i in range(N29):
+            t[i] -= q * pl[i]
+    v = sum(x << (W29 * i) for i, x in enumerate(t))
+    return v
+
+
+def run29_exact(prog, regs):
+    """registers hold the actual integers (Montgomery residues to the radix 2^406 with slack); bounds are asserted"""
+    pinv = (-pow(P, -1, R29)) % R29
+    for kind, ins in prog:
+        new = {}
+        for _, dst, pay in ins:
+            if kind == "MUL":
+                ops, neg = pay
+                assert all(len(o) == 1 and not o[0][1] for o in ops)
+                x = [regs[o[0][0]] for o in ops]
+                t = x[0] * x[1] + (x[2] * x[3] if len(x) == 4 else 0)
+                if neg:
+                    t = x[0] * x[1] - x[2] * x[3] + neg[1] * P * P
+                    assert t >= 0
+                m = (t * pinv) % R29
+                v = (t + m * P) >> (W29 * N29)
+                assert v < MUL_BOUND * P
+            else:
+                v = lin29_exact(regs, pay)
+                assert 0 <= v < (RED_BOUND if pay.reduce else 1 << 20) * P, (v // P, pay.K, pay.reduce)
+            assert 0 <= v < R29 and (dst >= N_IN or v < IO_BOUND * P)
+            new[dst] = v
+        regs.update(new)
+
+
+def run29(prog, regs):
+    """selftest adapter: canonical values in, canonical values out; inside, random representatives below IO_BOUND p"""
+    rnd = random.Random(len(prog) * 7919 + 1)
+    enc = {k: v * R29 % P + rnd.randrange(IO_BOUND) * P if rnd.random() < 0.7 else v * R29 % P + (IO_BOUND - 1) * P for k, v in regs.items()}
+    run29_exact(prog, enc)
+    rinv = pow(R29, -1, P)
+    for k, v in enc.items():
+        regs[k] = v * rinv % P
+
+
 def mul_srcs(ops):
     return [r for o in ops for r, _ in o]
 
@@ -263,20 +441,20 @@ N_IN = 64
 
 
 def prog_f12_mul():        # F <- F * G
-    B = Builder("f12_mul", N_IN)
+    B = BUILDER("f12_mul", N_IN)
     out12(B, f12_in(B, 0).mul(f12_in(B, RG), B), 0)
     return B
 
 
 def prog_f12_sqr():        # F <- F^2
-    B = Builder("f12_sqr", N_IN)
+    B = BUILDER("f12_sqr", N_IN)
     out12(B, f12_in(B, 0).sqr(B), 0)
     return B
 
 
 def prog_f12_sqr_k(k):     # F <- F^(2^k): k squarings in one program; the lazy additions fuse each output level with the next
     def mk():              # squaring's operand level, so a squaring costs 2 levels instead of 3
-        B = Builder("f12_sqr%d" % k, N_IN)
+        B = BUILDER("f12_sqr%d" % k, N_IN)
         x = f12_in(B, 0)
         for _ in range(k):
             x = x.sqr(B)
@@ -286,7 +464,7 @@ def prog_f12_sqr_k(k):     # F <- F^(2^k): k squarings in one program; the lazy 
 
 
 def prog_miller_step():    # F <- F^2 * line1(P1) * line2(P2)   (one doubling step of the Miller loop, both pairs live)
-    B = Builder("miller_step", N_IN)
+    B = BUILDER("miller_step", N_IN)
     f2 = f12_in(B, 0).sqr(B)
     L = sparse_mul(line_in(B, 0), line_in(B, 1), B)
     out12(B, f2.mul(L, B), 0)
@@ -294,7 +472,7 @@ def prog_miller_step():    # F <- F^2 * line1(P1) * line2(P2)   (one doubling st
 
 
 def prog_miller_add():     # F <- F * line1(P1) * line2(P2)     (an addition step)
-    B = Builder("miller_add", N_IN)
+    B = BUILDER("miller_add", N_IN)
     L = sparse_mul(line_in(B, 0), line_in(B, 1), B)
     out12(B, f12_in(B, 0).mul(L, B), 0)
     return B
@@ -334,7 +512,7 @@ def materialize12(B, x):
 
 def prog_cyc_sqr_k(k):     # F <- F^(2^k) for F in the cyclotomic subgroup (hard part of the final exponentiation)
     def mk():
-        B = Builder("cyc_sqr%d" % k, N_IN)
+        B = BUILDER("cyc_sqr%d" % k, N_IN)
         x = xr = f12_in(B, 0)
         for i in range(k):
             x = cyclotomic_sqr(x, xr, B)
@@ -358,7 +536,7 @@ def line_in(B, j):
 
 
 def prog_sqr_lines():      # F <- F^2 ; G <- line1(P1) * line2(P2)
-    B = Builder("sqr_lines", N_IN)
+    B = BUILDER("sqr_lines", N_IN)
     f2 = f12_in(B, 0).sqr(B)
     out12(B, f2, 0)
     out12(B, sparse_mul(line_in(B, 0), line_in(B, 1), B), RG)
@@ -366,19 +544,19 @@ def prog_sqr_lines():      # F <- F^2 ; G <- line1(P1) * line2(P2)
 
 
 def prog_lines():          # G <- line1(P1) * line2(P2)
-    B = Builder("lines", N_IN)
+    B = BUILDER("lines", N_IN)
     out12(B, sparse_mul(line_in(B, 0), line_in(B, 1), B), RG)
     return B
 
 
 def prog_line1():          # G <- line1(P1) as a full Fp12 element (the other pair is skipped)
-    B = Builder("line1", N_IN)
+    B = BUILDER("line1", N_IN)
     out12(B, line_in(B, 0), RG)
     return B
 
 
 def prog_conj_g():         # G <- conj(G)
-    B = Builder("conj_g", N_IN)
+    B = BUILDER("conj_g", N_IN)
     out12(B, f12_in(B, RG).conj(), RG)
     return B
 
@@ -397,7 +575,7 @@ def sparse_mul(a, b, B):
 
 
 def prog_conj():           # F <- conj(F)
-    B = Builder("conj", N_IN)
+    B = BUILDER("conj", N_IN)
     out12(B, f12_in(B, 0).conj(), 0)
     return B
 
@@ -410,13 +588,13 @@ def frob(B, a):
 
 
 def prog_frob():           # G <- frob(F)
-    B = Builder("frob", N_IN)
+    B = BUILDER("frob", N_IN)
     out12(B, frob(B, f12_in(B, 0)), RG)
     return B
 
 
 def prog_frob2():          # G <- frob(frob(F))
-    B = Builder("frob2", N_IN)
+    B = BUILDER("frob2", N_IN)
     out12(B, frob(B, frob(B, f12_in(B, 0))), RG)
     return B
 
@@ -425,7 +603,7 @@ def prog_inv_prep():
     """Fp12 inversion, part 1: F = a0 + a1 w.  t = a0^2 - v a1^2 (Fp6); its Fp6 inverse needs the Fp2 norm
     n2 = t0*c0 + xi(t2*c1 + t1*c2) and then the Fp norm n = n2.c0^2 + n2.c1^2.  Outputs: H[0..5] = (c0,c1,c2)
     cofactors, H[6..7] = n2, H[8] = n (to be inverted by the caller), G = copy of F."""
-    B = Builder("inv_prep", N_IN)
+    B = BUILDER("inv_prep", N_IN)
     a = f12_in(B, 0)
     t = a.c0.mul(a.c0, B) - a.c1.mul(a.c1, B).mul_v()
     c0 = t.c0.sqr(B) - t.c1.mul(t.c2, B).mul_xi()
@@ -442,7 +620,7 @@ def prog_inv_prep():
 def prog_inv_finish():
     """part 2: H[8] now holds 1/n.  n2^-1 = conj(n2)/n ; t^-1 = (c0,c1,c2) * n2^-1 ; F <- (a0 t^-1, -a1 t^-1)
     with a = G."""
-    B = Builder("inv_finish", N_IN)
+    B = BUILDER("inv_finish", N_IN)
     a = f12_in(B, RG)
     c = [f2_in(B, RH), f2_in(B, RH + 2), f2_in(B, RH + 4)]
     n2, ninv = f2_in(B, RH + 6), B.input(RH + 8)
@@ -453,7 +631,7 @@ def prog_inv_finish():
 
 
 def prog_copy(src, dst, name):
-    B = Builder(name, N_IN)
+    B = BUILDER(name, N_IN)
     for i in range(12):
         B.output(B.input(src + i), dst + i)
     return B
@@ -461,7 +639,7 @@ def prog_copy(src, dst, name):
 
 # G1 Jacobian programs for the MSM recombination: point X,Y,Z = regs 0,1,2 ; second point 3,4,5
 def prog_g1_dbl():
-    B = Builder("g1_dbl", N_IN)
+    B = BUILDER("g1_dbl", N_IN)
     X, Y, Z = B.input(0), B.input(1), B.input(2)
     A, Bq = B.mul(X, X), B.mul(Y, Y)
     C = B.mul(Bq, Bq)
@@ -479,7 +657,7 @@ def prog_g1_dbl():
 def prog_g1_add():
     """generic Jacobian addition (0,1,2) += (3,4,5); the caller handles identities / equal points.
     Also leaves H = U2-U1 in reg 6 and R = S2-S1 in reg 7 for the caller's special-case test."""
-    B = Builder("g1_add", N_IN)
+    B = BUILDER("g1_add", N_IN)
     X1, Y1, Z1, X2, Y2, Z2 = (B.input(i) for i in range(6))
     Z1Z1, Z2Z2 = B.mul(Z1, Z1), B.mul(Z2, Z2)
     U1, U2 = B.mul(X1, Z2Z2), B.mul(X2, Z1Z1)
@@ -519,7 +697,8 @@ def run(prog, regs):
         regs.update(new)
 
 
-def selftest(progs):
+def selftest(progs, run=None):
+    run = run or globals()['run']
     rnd = random.Random(11)
     def rnd12():
         return tuple(tuple((rnd.randrange(P), rnd.randrange(P)) for _ in range(3)) for _ in range(2))
@@ -676,20 +855,76 @@ def emit(sets, path):
     open(path, "w").write("\n".join(out) + "\n")
 
 
-def build_all(max_operand_terms):
-    global MAX_OPERAND_TERMS
+def emit29(progs, path):
+    """tables of the headroom programs (vliw29.cuh): MUL row = {dst | a << 16, b | c << 16, d | flags << 16, Kx} with flags bit 0 =
+    dual product, bit 1 = the second product is subtracted; LIN row = {dst, first term, term count, K | reduce << 31}"""
+    mul_tab, lin_tab, term_tab, level_tab, prog_tab, names = [], [], [], [], [], []
+    print("-- lat29")
+    for name, prog in progs.items():
+        first_level, n_regs, nmul, nlin = len(level_tab), N_IN, 0, 0
+        for kind, ins in prog:
+            if kind == "MUL":
+                level_tab.append((1, len(ins), len(mul_tab)))
+                for _, dst, (ops, neg) in ins:
+                    r = [o[0][0] for o in ops] + [0xffff] * (4 - len(ops))
+                    flags = (1 if len(ops) == 4 else 0) | (2 if neg else 0)
+                    mul_tab.append((dst | r[0] << 16, r[1] | r[2] << 16, r[3] | flags << 16, neg[1] if neg else 0))
+                    n_regs = max(n_regs, dst + 1)
+                nmul += len(ins)
+            else:
+                level_tab.append((0, len(ins), len(lin_tab)))
+                for _, dst, terms in ins:
+                    lin_tab.append((dst, len(term_tab), len(terms), terms.K | (1 << 31 if terms.reduce else 0)))
+                    for r, ng, db in terms:
+                        term_tab.append(r | (1 << 14 if ng else 0) | (1 << 15 if db else 0))
+                    n_regs = max(n_regs, dst + 1)
+                nlin += len(ins)
+        prog_tab.append((first_level, len(level_tab) - first_level, n_regs))
+        names.append(name)
+        print("%-14s levels %2d  MUL %3d  LIN %3d  regs %3d" % (name, len(level_tab) - first_level, nmul, nlin, n_regs))
+    row = lambda m: "{" + ",".join("%du" % x if x > 0x7fffffff else str(x) for x in m) + "}"
+    out = ["// GENERATED by tools/gen_vliw.py -- do not edit.  Level-scheduled Fp programs for vliw29.cuh (29-bit limbs, headroom instead of",
+           "// reductions; the bounds that make this sound are tracked and asserted by the generator).",
+           "#pragma once", "#include <stdint.h>", "namespace kzgb200 { namespace vliw29 {",
+           "constexpr int kRegF = 0, kRegG = %d, kRegH = %d, kRegLines = %d, kRegConst = %d, kRegP = %d, kNumInputRegs = %d;" % (RG, RH, RL, RC, RP, N_IN),
+           "constexpr int kIoBound = %d;   // every register at a program boundary holds a value below kIoBound * p" % IO_BOUND,
+           "struct Level { uint16_t kind /*0 LIN, 1 MUL*/, count; uint32_t first; };",
+           "struct Program { uint16_t first_level, n_levels, n_regs; };",
+           "enum ProgramId { " + ", ".join("kProg_%s = %d" % (n, i) for i, n in enumerate(names)) + ", kNumPrograms = %d };" % len(names),
+           "constexpr int kMaxRegs = %d;" % max(p[2] for p in prog_tab),
+           "constexpr int kNumMul = %d, kNumLin = %d, kNumTerm = %d, kNumLevel = %d;" % (len(mul_tab), len(lin_tab), len(term_tab), len(level_tab))]
+    for qual, pre in (("static __device__ const", "d"), ("static const", "h")):
+        if pre == "h":
+            out.append("#ifndef __CUDA_ARCH__")
+        out.append("%s uint32_t %s_mul[%d][4] = {%s};" % (qual, pre, len(mul_tab), ",".join(row(m) for m in mul_tab)))
+        out.append("%s uint32_t %s_lin[%d][4] = {%s};" % (qual, pre, len(lin_tab), ",".join(row(m) for m in lin_tab)))
+        out.append("%s uint16_t %s_term[%d] = {%s};" % (qual, pre, len(term_tab), ",".join(str(t) for t in term_tab)))
+        out.append("%s Level %s_level[%d] = {%s};" % (qual, pre, len(level_tab), ",".join(row(l) for l in level_tab)))
+        out.append("%s Program %s_prog[%d] = {%s};" % (qual, pre, len(prog_tab), ",".join(row(p) for p in prog_tab)))
+        if pre == "h":
+            out.append("#endif")
+    out.append("}}  // namespace kzgb200::vliw29")
+    open(path, "w").write("\n".join(out) + "\n")
+
+
+def build_all(max_operand_terms, builder=Builder):
+    global MAX_OPERAND_TERMS, BUILDER
     MAX_OPERAND_TERMS = max_operand_terms
+    BUILDER = builder
     progs = {}
     for mk in PROGRAMS:
         B = mk()
         prog = B.finish()
         check_hazards(prog, N_IN)
         progs[B.name] = prog
-    selftest(progs)
+    selftest(progs, run29 if builder is Builder29 else None)
+    BUILDER = Builder
     return progs
 
 
 if __name__ == "__main__":
     sets = {"lat": build_all(1), "thr": build_all(4)}
+    lat29 = build_all(1, Builder29)
     if "--check" not in sys.argv:
         emit(sets, os.path.join(ROOT, "kzg_rs_b200", "csrc", "vliw_programs.cuh"))
+        emit29(lat29, os.path.join(ROOT, "kzg_rs_b200", "csrc", "vliw29_programs.cuh"))
