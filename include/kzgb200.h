@@ -187,6 +187,10 @@ int kzgb200_set_profiling(kzgb200_ctx* ctx, int on);
 int kzgb200_get_phase_ms(kzgb200_ctx* ctx, float* out8);
 /* profiling aid: SM clock stamps of the sections of the last single-GPU final pairing kernel */
 int kzgb200_debug_final_ticks(kzgb200_ctx* ctx, long long* out14);
+/* Self-test of the pairing engine's 16-lane instructions (csrc/vliw29.cuh): every engine program is run `rounds` times on the
+ * cooperative executors and on the sequential reference executors from the same seeded register files; mismatches[i] receives
+ * the number of registers of program i whose canonical values differ (all zero = pass).  n_programs receives their count. */
+int kzgb200_debug_engine_selftest(kzgb200_ctx* ctx, uint32_t seed, int rounds, uint32_t* mismatches32, int* n_programs);
 /* the cudaStream_t all work of this context is issued on (for CUDA-event timing by the caller) */
 void* kzgb200_stream(kzgb200_ctx* ctx);
 

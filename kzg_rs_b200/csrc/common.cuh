@@ -48,7 +48,8 @@ constexpr int kTreeMid = 32;        // leaf digests per middle-level hash: 17 co
 constexpr int kWindows = 16, kBuckets = 256, kMsmSets = 3, kDigitRows = 4 * kWindows;   // rows: (kind r|rz) x (half lo|hi) x window
 constexpr int kSlice = 32, kMsmRows = kMsmSets * 2 * kWindows;   // bucket accumulation: entries per thread; rows = (set, GLV half, window)
 constexpr int kWinLanes = 64, kWinPer = kBuckets / kWinLanes;     // 64 lanes x 4 buckets: 48 CTAs still fit the tail's 8 SMs in one wave
-constexpr int kFinalThreads = 64;
+constexpr int kFinalThreads = 64;       // G1 prelude of the final check (sums, [s]G, affine conversion)
+constexpr int kPairThreads = 768;       // pairing engine: 48 groups of 16 lanes, one engine instruction per group
 constexpr int kManyThreads = 384, kManyGroups = 21;   // many_pairing_kernel: checks run in lockstep by one CTA
 constexpr int kManyWarps = 4;         // many_pairing_warp_kernel (identity inputs): one check per warp
 constexpr int kHarnessMaxDegree = 16;
@@ -78,11 +79,17 @@ struct Partial {
 };
 
 // dynamic shared memory of the final kernels: engine register file, program tables, G1 tree scratch (> 48 KB: opt-in)
-struct FinalSmem {
-    f29::F29 regs[vliw29::kTotalRegs];
+struct FinalSmem {                       // prelude kernels (padded: see kTailPadSmem in runtime.cuh)
     G1 sm[kFinalThreads];
-    vliw29::SharedTables stab;
+    unsigned char pad[20 * 1024];
 };
+struct PairSmem {                        // pairing_check_kernel
+    f29::F29 regs[vliw29::kTotalRegs];
+    vliw29::SharedTables stab;
+    long long scratch[(kPairThreads / vliw29::kGroupLanes) * vliw29::kScratchWords];
+};
+// hand-over from the prelude kernel to the pairing kernel (device memory, 256 bytes into the context's 512-byte scratch)
+struct FinalPts { G1Affine pts[2]; uint32_t go; };
 
 constexpr int kManyStride = vliw::kTotalRegsThr * 12 + 1;     // words between the register files of consecutive groups (odd: bank skew)
 constexpr int kManySmemBytes = kManyGroups * kManyStride * 4 + (int)sizeof(vliw::SharedTables) + kManyGroups * (2 * (int)sizeof(G1Affine) + 2) + 64;
@@ -121,9 +128,21 @@ __global__ void msm_combine_kernel(const G1* __restrict__ windows, const Fr* __r
                                    Partial* __restrict__ out, uint32_t* flag, uint32_t epoch);
 __global__ void wait_flags_kernel(const uint32_t* flags, int count, uint32_t epoch, uint32_t* __restrict__ timed_out);
 __global__ void batch_final_kernel(const Partial* __restrict__ parts, int nparts, const DeviceTables* __restrict__ T, uint32_t* __restrict__ result,
-                                   long long* __restrict__ ticks);
+                                   FinalPts* __restrict__ out);
 __global__ void single_final_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P, const ZY* __restrict__ zy,
-                                    const uint32_t* __restrict__ status, const DeviceTables* __restrict__ T, uint32_t* __restrict__ result);
+                                    const uint32_t* __restrict__ status, const DeviceTables* __restrict__ T, uint32_t* __restrict__ result,
+                                    FinalPts* __restrict__ out);
+__global__ void pairing_check_kernel(const FinalPts* __restrict__ in, const DeviceTables* __restrict__ T, uint32_t* __restrict__ result,
+                                     long long* __restrict__ ticks);
+__global__ void engine_selftest_kernel(uint32_t seed, int rounds, f29::F29* __restrict__ ref, uint32_t* __restrict__ mismatches);
+// final check of a batch = G1 prelude + pairing engine, back to back on `st`; scratch512 = the context's 512-byte device scratch
+// (ticks at +128 when profiling, the hand-over points at +256)
+inline void launch_batch_final(cudaStream_t st, const Partial* parts, int nparts, const DeviceTables* T, uint32_t* result, unsigned char* scratch512,
+                               bool ticks) {
+    FinalPts* fp = reinterpret_cast<FinalPts*>(scratch512 + 256);
+    batch_final_kernel<<<1, kFinalThreads, sizeof(FinalSmem), st>>>(parts, nparts, T, result, fp);
+    pairing_check_kernel<<<1, kPairThreads, sizeof(PairSmem), st>>>(fp, T, result, ticks ? reinterpret_cast<long long*>(scratch512 + 128) : nullptr);
+}
 __global__ void many_lhs_kernel(const uint8_t* __restrict__ z32, const uint8_t* __restrict__ y32, const G1Affine* __restrict__ C,
                                 const G1Affine* __restrict__ P, size_t m, const DeviceTables* __restrict__ T, G1Affine* __restrict__ X,
                                 uint32_t* __restrict__ status);

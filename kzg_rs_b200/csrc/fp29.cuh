@@ -19,23 +19,27 @@ constexpr uint32_t kMask = 0x1fffffffu;
 struct alignas(16) F29 { uint32_t l[16]; };   // l[14], l[15]: padding (registers are moved as four 16-byte words)
 
 KZG_HD constexpr uint32_t p29(int i) { constexpr uint32_t m[14] = KZG29_P; return m[i]; }
+KZG_HD uint32_t p29_rt(int i) { constexpr uint32_t m[14] = KZG29_P; return m[i]; }   // run-time index
 KZG_HD constexpr uint32_t p2_29(int i) { constexpr uint32_t m[28] = KZG29_P2; return m[i]; }
 KZG_HD F29 f29_const(const uint32_t (&v)[14]) { F29 r; for (int i = 0; i < 14; i++) r.l[i] = v[i]; r.l[14] = r.l[15] = 0; return r; }
 KZG_HD F29 f29_zero() { F29 r; for (int i = 0; i < 16; i++) r.l[i] = 0; return r; }
 KZG_HD F29 f29_one() { const uint32_t v[14] = KZG29_ONE; return f29_const(v); }
 
-// acc += a * b as ONE IMAD.WIDE (inline PTX: nvcc otherwise reassociates the column sums into separate product chains joined by
-// 64-bit additions, roughly doubling the instruction count)
+// acc += a * b as ONE IMAD.WIDE with the accumulator as its addend.  Written as the (mad.lo.cc, madc.hi) pair: ptxas fuses the
+// pair into IMAD.WIDE Rd, Ra, Rb, Rd; given `acc += (uint64_t)a * b` or mad.wide it instead emits IMAD.WIDE Rt, Ra, Rb, RZ plus a
+// three-input IADD3 / IADD3.X pair per two products -- twice the instructions, and a lone warp pays per instruction.
 KZG_HD void madw(uint64_t& acc, uint32_t a, uint32_t b) {
 #ifdef __CUDA_ARCH__
-    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a), "r"(b));
+    asm("{\n\t.reg .u32 lo, hi;\n\tmov.b64 {lo, hi}, %0;\n\tmad.lo.cc.u32 lo, %1, %2, lo;\n\tmadc.hi.u32 hi, %1, %2, hi;\n\tmov.b64 %0, {lo, hi};\n\t}"
+        : "+l"(acc) : "r"(a), "r"(b));
 #else
     acc += (uint64_t)a * b;
 #endif
 }
 KZG_HD void madw_s(uint64_t& acc, int32_t a, int32_t b) {
 #ifdef __CUDA_ARCH__
-    asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a), "r"(b));
+    asm("{\n\t.reg .u32 lo, hi;\n\tmov.b64 {lo, hi}, %0;\n\tmad.lo.cc.s32 lo, %1, %2, lo;\n\tmadc.hi.s32 hi, %1, %2, hi;\n\tmov.b64 %0, {lo, hi};\n\t}"
+        : "+l"(acc) : "r"(a), "r"(b));
 #else
     acc += (uint64_t)((int64_t)a * b);
 #endif

@@ -290,7 +290,7 @@ int group_run(kzgb200_group* g, const ShardArgs* args, int aw, int* ok) {
         }
         wait_flags_kernel<<<1, 32, 0, ctx->stream>>>(g->d_x->flags, aw, epoch, &g->d_x->timed_out);
         phase_begin(ctx, kPhFinal, ctx->stream);
-        batch_final_kernel<<<1, kFinalThreads, sizeof(FinalSmem), ctx->stream>>>(g->d_x->partials, aw, ctx->tables, ctx->d_result, nullptr);
+        launch_batch_final(ctx->stream, g->d_x->partials, aw, ctx->tables, ctx->d_result, ctx->d_scratch, false);
         phase_end(ctx, kPhFinal, ctx->stream);
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_parse, 0));
         status_or_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_status, (int)L.n, ctx->d_result + 2);

@@ -443,6 +443,7 @@ extern "C" int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_p
         CK(cudaMalloc(&ctx->d_digest, 32));
         CK(cudaFuncSetAttribute(batch_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinalSmem)));
         CK(cudaFuncSetAttribute(single_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinalSmem)));
+        CK(cudaFuncSetAttribute(pairing_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairSmem)));
         CK(cudaFuncSetAttribute(many_pairing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kManySmemBytes));
         CK(cudaFuncSetAttribute(many_pairing_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kManySmemBytes));
         CK(cudaMalloc(&ctx->tables, sizeof(DeviceTables)));
@@ -522,13 +523,15 @@ static int batch_locked(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t*
     if (n == 1) {   // single path (reference src/kzg_proof.rs:482-489)
         phase_begin(ctx, kPhFinal, ctx->stream);
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_parse, 0));
-        single_final_kernel<<<1, kFinalThreads, sizeof(FinalSmem), ctx->stream>>>(ctx->d_C, ctx->d_P, ctx->d_zy, ctx->d_status, ctx->tables, ctx->d_result);
+        FinalPts* fp = reinterpret_cast<FinalPts*>(ctx->d_scratch + 256);
+        single_final_kernel<<<1, kFinalThreads, sizeof(FinalSmem), ctx->stream>>>(ctx->d_C, ctx->d_P, ctx->d_zy, ctx->d_status, ctx->tables, ctx->d_result, fp);
+        pairing_check_kernel<<<1, kPairThreads, sizeof(PairSmem), ctx->stream>>>(fp, ctx->tables, ctx->d_result, nullptr);
     } else {
         if ((rc = transcript_progress(ctx, true))) return rc;     // the host hashes the transcript behind the evaluation chunks
         if ((rc = transcript_finish(ctx))) return rc;
         if ((rc = launch_lincomb(ctx, 0, ctx->d_partial, !defer))) return rc;   // deferred: the flags are merged by status_or below
         phase_begin(ctx, kPhFinal, ctx->stream);
-        batch_final_kernel<<<1, kFinalThreads, sizeof(FinalSmem), ctx->stream>>>(ctx->d_partial, 1, ctx->tables, ctx->d_result, reinterpret_cast<long long*>(ctx->d_scratch + 128));
+        launch_batch_final(ctx->stream, ctx->d_partial, 1, ctx->tables, ctx->d_result, ctx->d_scratch, true);
     }
     phase_end(ctx, kPhFinal, ctx->stream);
     // the deferred subgroup checks may still be running beside the pairing: their flags are merged last
@@ -603,7 +606,7 @@ extern "C" int kzgb200_verify_blob_kzg_proof_batch_each(kzgb200_ctx* ctx, const 
         if ((rc = transcript_progress(ctx, true))) return rc;
         if ((rc = transcript_finish(ctx))) return rc;
         if ((rc = launch_lincomb(ctx, 0, ctx->d_partial, true))) return rc;
-        batch_final_kernel<<<1, kFinalThreads, sizeof(FinalSmem), ctx->stream>>>(ctx->d_partial, 1, ctx->tables, ctx->d_result, nullptr);
+        launch_batch_final(ctx->stream, ctx->d_partial, 1, ctx->tables, ctx->d_result, ctx->d_scratch, false);
         status_or_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_status, (int)n, ctx->d_result + 2);
         CK(cudaGetLastError());
         rc = read_result(ctx, &ok);
@@ -656,7 +659,7 @@ extern "C" int kzgb200_verify_kzg_proof_batch(kzgb200_ctx* ctx, const uint8_t* c
     if ((rc = transcript_progress(ctx, true))) return rc;
     if ((rc = transcript_finish(ctx))) return rc;
     if ((rc = launch_lincomb(ctx, 0, ctx->d_partial, false))) return rc;
-    batch_final_kernel<<<1, kFinalThreads, sizeof(FinalSmem), ctx->stream>>>(ctx->d_partial, 1, ctx->tables, ctx->d_result, nullptr);
+    launch_batch_final(ctx->stream, ctx->d_partial, 1, ctx->tables, ctx->d_result, ctx->d_scratch, false);
     CK(cudaMemsetAsync(ctx->d_result + 2, 0, 4, ctx->stream));
     CK(cudaGetLastError());
     return read_result(ctx, ok);
@@ -898,6 +901,24 @@ extern "C" int kzgb200_debug_final_ticks(kzgb200_ctx* ctx, long long* out14) {
     std::lock_guard<std::mutex> g(ctx->lock);
     DeviceGuard dev(ctx->device);
     CK(cudaMemcpy(out14, ctx->d_scratch + 128, 112, cudaMemcpyDeviceToHost));
+    return KZGB200_OK;
+}
+extern "C" int kzgb200_debug_engine_selftest(kzgb200_ctx* ctx, uint32_t seed, int rounds, uint32_t* mismatches32, int* n_programs) {
+    if (!ctx || !mismatches32 || !n_programs || rounds < 1) return KZGB200_BAD_ARGS;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    DeviceGuard dev(ctx->device);
+    f29::F29* d_ref = nullptr; uint32_t* d_mis = nullptr;
+    CK(cudaMalloc(&d_ref, sizeof(f29::F29) * vliw29::kTotalRegs));
+    CK(cudaMalloc(&d_mis, 32 * sizeof(uint32_t)));
+    CK(cudaMemsetAsync(d_mis, 0, 32 * sizeof(uint32_t), ctx->stream));
+    CK(cudaFuncSetAttribute(engine_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairSmem)));
+    engine_selftest_kernel<<<1, kPairThreads, sizeof(PairSmem), ctx->stream>>>(seed, rounds, d_ref, d_mis);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(mismatches32, d_mis, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_ref); cudaFree(d_mis);
+    *n_programs = vliw29::kNumPrograms;
+    static_assert(vliw29::kNumPrograms <= 32, "mismatch array");
     return KZGB200_OK;
 }
 // the stream every call of this context is issued on (cudaStream_t), for event timing by the caller

@@ -1,12 +1,25 @@
 // Cooperative pairing engine, second generation: the level-scheduled programs of vliw29_programs.cuh over a shared-memory
-// register file of 29-bit-limb values (fp29.cuh).  Same idea as vliw.cuh (instruction k of a level on thread k, a barrier per
-// level; reference src/pairings.rs:5-9 via src/kzg_proof.rs:436-441), different arithmetic:
-//   MUL  dst = (a b +- c d) / 2^406     392 carry-free IMAD.WIDE + 196 for the reduction (was 432 chained IMAD.WIDE.X)
-//   LIN  dst = K p + sum +-(1|2) src    14 IMAD.WIDE per term into signed 64-bit columns, one carry pass; NO modular reduction
-//                                       (headroom: 2^406 = 2^25.3 p) unless the generator flagged the sum, in which case
-//                                       floor-estimate(v / p) p is subtracted first (value then below 6 p)
-// Measured on a lone 64-thread CTA (round 2): a MUL level 1.96 -> ~0.8 us, a LIN level 1.42 -> ~0.3 us.
-// Host build: the same code runs the lanes one after the other (tools/hosttest/vliw29_host.cu).
+// register file of 29-bit-limb values (fp29.cuh).  Same idea as vliw.cuh (a level = independent instructions, a barrier per
+// level; reference src/pairings.rs:5-9 via src/kzg_proof.rs:436-441), different arithmetic and a different execution shape:
+//
+//   * values are SIGNED 14-limb numbers (limbs 0..12 in [-1, 2^29 + 1], limb 13 signed, |v| < 2^405) and ANY representative of
+//     their residue: 2^406 = 2^25.3 p of headroom replaces the modular reduction after every sum; the bounds that make this
+//     sound are tracked statically by tools/gen_vliw.py;
+//   * ONE INSTRUCTION RUNS ON 16 LANES (one limb per lane), not on one thread.  Measured on B200 (tools/microbench/lonewarp.cu): a
+//     lone warp issues an IMAD.WIDE only every ~7 clocks however many lanes are active, so a one-thread Montgomery product (620
+//     wide multiplications) costs ~4200 clocks and a level of 36 of them leaves 32 lanes busy on two sub-partitions.  Per lane
+//     the 16-lane form needs 56 wide multiplications per dual product:
+//       MUL  dst = (a b +- c d) / 2^406 : lane j forms the row a_j * b[0..13] (+- c_j * d[0..13]); the rows are summed by columns
+//            through a per-group shared-memory scratch; two carry rounds; m = T_lo * (-p^-1) mod 2^406 and m * p the same way
+//            (constant operands as immediates); the low half of T + m p is an exact multiple of 2^406, so its carry into the
+//            high half is read off its top limb without a ripple loop;
+//       LIN  dst = sum +-(1|2) src      : lane j adds limb j of every term (32-bit multiply-adds on 16-bit halves: no wide
+//            multiplication), two carry rounds; with the `reduce` flag round(v / p) p is subtracted first (float estimate from
+//            the two top columns), leaving |v| < 4 p.
+//   A 768-thread CTA runs 48 instructions at a time.
+//
+// The sequential executors (exec_*_ref, host + device) are the specification of the two instructions: the CPU unit test runs the
+// pairing with them (tools/hosttest/vliw29_host.cu), the GPU unit test compares the 16-lane forms with them limb for limb.
 #pragma once
 #include "vliw.cuh"
 #include "fp29.cuh"
@@ -15,6 +28,7 @@
 namespace kzgb200 {
 namespace vliw29 {
 using f29::F29;
+constexpr int32_t kM = (int32_t)f29::kMask;
 
 struct Tables {
     const uint32_t (*mul)[4];
@@ -23,10 +37,14 @@ struct Tables {
     const Level* level;
     const Program* prog;
 };
+constexpr int kGroupLanes = 16;
+constexpr int kScratchWords = 14 * 28 + 4;        // 64-bit words per group: rows[14][28] (+ pad for the idle lanes' reads)
 struct Lanes {
-    int tid, n;                   // this thread's lane and the number of cooperating threads (host: 0, 1)
+    int tid, n;                   // this thread's index and the number of cooperating threads (host: 0, 1)
     Tables tab;
     long long* ticks = nullptr;   // optional: per-section clock64() stamps (profiling aid)
+    long long* scratch = nullptr; // device: kScratchWords 64-bit words per 16-lane group, zero-initialised
+    const int32_t* p29s = nullptr;   // device: limbs of p, one per lane, in shared memory
     KZG_HD void tick(int i) const {
 #ifdef __CUDA_ARCH__
         if (ticks && tid == 0) ticks[i] = clock64();
@@ -51,6 +69,7 @@ struct SharedTables {
     uint16_t term[kNumTerm];
     Level level[kNumLevel];
     Program prog[kNumPrograms];
+    int32_t p29[16];              // limbs of p, one per lane (lanes 14, 15: 0)
 };
 #ifdef __CUDACC__
 __device__ __forceinline__ Tables load_tables(SharedTables* st, int tid, int n) {
@@ -60,6 +79,7 @@ __device__ __forceinline__ Tables load_tables(SharedTables* st, int tid, int n) 
     for (int i = tid; i < kNumTerm; i += n) st->term[i] = src.term[i];
     for (int i = tid; i < kNumLevel; i += n) st->level[i] = src.level[i];
     for (int i = tid; i < kNumPrograms; i += n) st->prog[i] = src.prog[i];
+    if (tid < 16) st->p29[tid] = tid < 14 ? (int32_t)f29::p29_rt(tid) : 0;
     __syncthreads();
     return Tables{st->mul, st->lin, st->term, st->level, st->prog};
 }
@@ -83,71 +103,224 @@ KZG_HD F29 frob_const(int i) {
     return r;
 }
 
-// MUL row: {dst | a << 16, b | c << 16, d | flags << 16, kx}; flags bit 0 = dual product, bit 1 = the second product is subtracted
-KZG_HD void exec_mul(F29* regs, const uint32_t* ins) {
+// ------------------------------------------------------------------------------------------ sequential reference executors
+// t[] = signed 64-bit column sums of a 14-limb number -> limbs 0..12 in [0, 2^29), limb 13 = the (signed) rest
+KZG_HD void normalize_ref(F29& r, int64_t* t) {
+    for (int i = 0; i < 13; i++) { r.l[i] = (uint32_t)t[i] & f29::kMask; t[i + 1] += t[i] >> 29; }
+    r.l[13] = (uint32_t)t[13]; r.l[14] = 0; r.l[15] = 0;
+}
+KZG_HD int32_t limb(const F29& v, int i) { return (int32_t)v.l[i]; }
+// MUL row: {dst | a << 16, b | c << 16, d | flags << 16, 0}; flags bit 0 = dual product, bit 1 = the second product is subtracted
+KZG_NI void exec_mul_ref(F29* regs, const uint32_t* ins) {
     const uint32_t w0 = ins[0], w1 = ins[1], w2 = ins[2];
     const bool dual = (w2 >> 16) & 1u, neg = (w2 >> 17) & 1u;
     const F29 a = regs[w0 >> 16], b = regs[w1 & 0xffffu];
-    const F29 c = regs[dual ? (w1 >> 16) : (w0 >> 16)], d = regs[dual ? (w2 & 0xffffu) : (w1 & 0xffffu)];
+    int64_t t[29];
+    for (int k = 0; k < 29; k++) t[k] = 0;
+    for (int i = 0; i < 14; i++) for (int j = 0; j < 14; j++) t[i + j] += (int64_t)limb(a, i) * limb(b, j);
+    if (dual) {
+        const F29 c = regs[w1 >> 16], d = regs[w2 & 0xffffu];
+        for (int i = 0; i < 14; i++) for (int j = 0; j < 14; j++) t[i + j] += (int64_t)(neg ? -limb(c, i) : limb(c, i)) * limb(d, j);
+    }
+    for (int k = 0; k < 28; k++) { int64_t c = t[k] >> 29; t[k] &= f29::kMask; t[k + 1] += c; }    // exact 29-limb form (t[28] = signed rest)
+    for (int i = 0; i < 14; i++) {
+        int64_t m = (int64_t)(((uint32_t)t[i] * KZG29_PINV) & f29::kMask);
+        for (int j = 0; j < 14; j++) t[i + j] += m * (int64_t)f29::p29_rt(j);
+        t[i + 1] += t[i] >> 29;            // t[i] is now a multiple of 2^29
+    }
+    t[27] += t[28] << 29;
     F29 r;
-    f29::mont_mul29(r.l, a.l, b.l, c.l, d.l, dual, neg, ins[3]);
-    r.l[14] = 0; r.l[15] = 0;
+    normalize_ref(r, t + 14);
     regs[w0 & 0xffffu] = r;
 }
-// LIN row: {dst, first term, term count, K | reduce << 31}; a term = reg | neg << 14 | dbl << 15
-KZG_HD void exec_lin(F29* regs, const uint32_t* ins, const uint16_t* terms) {
-    uint64_t t[f29::kN];   // signed column sums (two's complement)
-#pragma unroll
-    for (int i = 0; i < f29::kN; i++) t[i] = 0;
-    const uint16_t* tt = terms + ins[1];
-    const uint32_t count = ins[2];
-#pragma unroll 1
-    for (uint32_t k = 0; k < count; k++) {
-        const uint32_t e = tt[k];
-        const F29 v = regs[e & 0x3fffu];
+// LIN row: {dst, first term, term count, reduce}; a term = reg | neg << 14 | dbl << 15
+KZG_NI void exec_lin_ref(F29* regs, const uint32_t* ins, const uint16_t* terms) {
+    int64_t t[14];
+    for (int i = 0; i < 14; i++) t[i] = 0;
+    for (uint32_t k = 0; k < ins[2]; k++) {
+        const uint32_t e = terms[ins[1] + k];
+        const F29& v = regs[e & 0x3fffu];
         int32_t coef = (int32_t)((e >> 15) & 1u) + 1;
         if (e & 0x4000u) coef = -coef;
-#pragma unroll
-        for (int i = 0; i < f29::kN; i++) f29::madw_s(t[i], (int32_t)v.l[i], coef);
+        for (int i = 0; i < 14; i++) t[i] += (int64_t)limb(v, i) * coef;
     }
-    const int32_t K = (int32_t)(ins[3] & 0x7fffffffu);
-#pragma unroll
-    for (int i = 0; i < f29::kN; i++) f29::madw_s(t[i], (int32_t)f29::p29(i), K);
-    if (ins[3] >> 31) {
-        // v < 2^20 p: quotient estimate from the two top columns in float (relative error 2^-21 -> off by less than 1), minus 2
-        const float vf = (float)(int64_t)t[13] * 536870912.0f + (float)(int64_t)t[12];
-        const float pinv = 1.0f / ((float)f29::p29(13) * 536870912.0f + (float)f29::p29(12) + 1.0f);
-        int32_t q = (int32_t)(vf * pinv) - 2;
-        if (q < 0) q = 0;
-#pragma unroll
-        for (int i = 0; i < f29::kN; i++) f29::madw_s(t[i], (int32_t)f29::p29(i), -q);
+    if (ins[3] & 1u) {
+        // |v| < 2^20 p: quotient estimate from the two top columns in float (relative error ~2^-22: off by less than 1)
+        const float vf = (float)t[13] * 536870912.0f + (float)t[12];
+        const float pinv = 1.0f / ((float)f29::p29_rt(13) * 536870912.0f + (float)f29::p29_rt(12));
+        const int32_t q = (int32_t)rintf(vf * pinv);
+        for (int i = 0; i < 14; i++) t[i] -= (int64_t)f29::p29_rt(i) * q;
     }
     F29 r;
-#pragma unroll
-    for (int i = 0; i < f29::kN - 1; i++) {
-        r.l[i] = (uint32_t)t[i] & f29::kMask;
-        t[i + 1] += (uint64_t)((int64_t)t[i] >> f29::kW);
-    }
-    r.l[13] = (uint32_t)t[13];
-    r.l[14] = 0; r.l[15] = 0;
+    normalize_ref(r, t);
     regs[ins[0]] = r;
 }
-// run one program; every cooperating thread must call it (barriers inside)
-KZG_NI void run(int prog, F29* regs, const Lanes& L) {
+
+// ------------------------------------------------------------------------------------------ 16-lane executors (device)
+#ifdef __CUDACC__
+constexpr unsigned kFull = 0xffffffffu;
+__device__ __forceinline__ int32_t up(int32_t v, int d, int lane) { int32_t r = __shfl_up_sync(kFull, v, d, kGroupLanes); return lane < d ? 0 : r; }
+__device__ __forceinline__ int32_t from(int32_t v, int src) { return __shfl_sync(kFull, v, src, kGroupLanes); }
+// Two carry rounds over a 14-limb number given as signed 64-bit column sums (lane j: column j; lanes 14, 15: zero), lane 13
+// holding everything above bit 377 (the value's true top limb fits 32 bits).  Result limbs 0..12 in [-1, 2^29 + 1].
+__device__ __forceinline__ int32_t carry_top(int64_t t, int lane) {
+    const bool top = lane >= 13;
+    const int64_t c64 = t >> 29;
+    int32_t low = top ? (int32_t)t : ((int32_t)t & kM);
+    int32_t cmid = top ? 0 : (lane == 12 ? (int32_t)c64 : ((int32_t)c64 & kM));     // lane 12 hands its whole carry to the top limb
+    int32_t chi = (top || lane == 12) ? 0 : (int32_t)(t >> 58);
+    int32_t l = low + up(cmid, 1, lane) + up(chi, 2, lane);
+    int32_t c = top ? 0 : (l >> 29);
+    l = top ? l : (l & kM);
+    return l + up(c, 1, lane);
+}
+// The same for the LOW half of a 28-column number: all 14 lanes carry out; c14 / c15 = what moves into columns 14 and 15
+// (the same values on every lane of the group)
+__device__ __forceinline__ int32_t carry_low(int64_t t, int lane, int64_t& c14, int64_t& c15) {
+    const bool idle = lane >= 14;
+    int32_t low = idle ? 0 : ((int32_t)t & kM), cmid = idle ? 0 : ((int32_t)(t >> 29) & kM), chi = idle ? 0 : (int32_t)(t >> 58);
+    int32_t l = low + up(cmid, 1, lane) + up(chi, 2, lane);
+    const int32_t cm13 = from(cmid, 13), ch12 = from(chi, 12), ch13 = from(chi, 13);
+    int32_t c = idle ? 0 : (l >> 29);
+    l = (l & kM) + up(c, 1, lane);
+    if (idle) l = 0;
+    c14 = (int64_t)cm13 + ch12 + from(c, 13);
+    c15 = ch13;
+    return l;
+}
+// column sums of the 14 rows a group left in its scratch: rows[j][j + i] = row_j[i]; the other entries of a row stay zero
+__device__ __forceinline__ void store_rows(long long* S, const int64_t* row, int lane) {
+    if (lane < 14) {
+#pragma unroll
+        for (int i = 0; i < 14; i++) S[lane * 28 + lane + i] = row[i];
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ int64_t column_sum(const long long* S, int col) {
+    int64_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 14; j++) s += S[j * 28 + col];
+    return s;
+}
+__device__ __forceinline__ int64_t mulw(int32_t a, int32_t b) { uint64_t r = 0; f29::madw_s(r, a, b); return (int64_t)r; }
+
+__device__ __forceinline__ void exec_mul16(F29* regs, const uint32_t* ins, bool active, long long* S, int lane) {
+    const uint32_t w0 = ins[0], w1 = ins[1], w2 = ins[2];
+    const bool dual = (w2 >> 16) & 1u, neg = (w2 >> 17) & 1u;
+    const int32_t* A = reinterpret_cast<const int32_t*>(regs[w0 >> 16].l);
+    const int4* B = reinterpret_cast<const int4*>(regs[w1 & 0xffffu].l);
+    int64_t row[14];
+    {
+        const int32_t aj = A[lane];
+        const int4 b0 = B[0], b1 = B[1], b2 = B[2], b3 = B[3];
+        const int32_t bb[14] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y};
+#pragma unroll
+        for (int i = 0; i < 14; i++) row[i] = mulw(aj, bb[i]);
+    }
+    if (dual) {
+        const int32_t* C = reinterpret_cast<const int32_t*>(regs[w1 >> 16].l);
+        const int4* D = reinterpret_cast<const int4*>(regs[w2 & 0xffffu].l);
+        const int32_t cj = neg ? -C[lane] : C[lane];
+        const int4 d0 = D[0], d1 = D[1], d2 = D[2], d3 = D[3];
+        const int32_t dd[14] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, d2.x, d2.y, d2.z, d2.w, d3.x, d3.y};
+#pragma unroll
+        for (int i = 0; i < 14; i++) { uint64_t u = (uint64_t)row[i]; f29::madw_s(u, cj, dd[i]); row[i] = (int64_t)u; }
+    }
+    // T = a b +- c d by columns: lane k holds column k (lo) and column k + 14 (hi)
+    store_rows(S, row, lane);
+    int64_t lo = column_sum(S, lane), hi = column_sum(S, lane + 14);
+    if (lane >= 14) { lo = 0; hi = 0; }
+    __syncwarp();
+    int64_t c14, c15;
+    const int32_t tl = carry_low(lo, lane, c14, c15);
+    if (lane == 0) hi += c14;
+    if (lane == 1) hi += c15;
+    // m = T_lo * (-p^-1) mod 2^406 (low columns only)
+    {
+        constexpr uint32_t pinv[14] = KZG29_PINV_FULL;
+#pragma unroll
+        for (int i = 0; i < 14; i++) row[i] = mulw(tl, (int32_t)pinv[i]);
+    }
+    store_rows(S, row, lane);
+    int64_t mc = column_sum(S, lane);
+    if (lane >= 14) mc = 0;
+    __syncwarp();
+    int64_t d14, d15;
+    int32_t m = carry_low(mc, lane, d14, d15);         // carries beyond limb 13 are multiples of 2^406: dropped
+    if (lane == 13) m &= kM;
+    // T + m p
+    {
+        constexpr uint32_t pp[14] = KZG29_P;
+#pragma unroll
+        for (int i = 0; i < 14; i++) row[i] = mulw(m, (int32_t)pp[i]);
+    }
+    store_rows(S, row, lane);
+    int64_t lo2 = column_sum(S, lane), hi2 = column_sum(S, lane + 14);
+    if (lane >= 14) { lo2 = 0; hi2 = 0; }
+    __syncwarp();
+    // the low half is an exact multiple of 2^406: after the carry rounds it is -2^406, 0 or 2^406, told apart by its top limb
+    const int32_t zl = carry_low((int64_t)tl + lo2, lane, c14, c15);
+    const int32_t z13 = from(zl, 13);
+    hi += hi2;
+    if (lane == 0) hi += c14 + (int64_t)((z13 + (1 << 28)) >> 29);
+    if (lane == 1) hi += c15;
+    const int32_t r = carry_top(hi, lane);
+    if (active) reinterpret_cast<int32_t*>(regs[w0 & 0xffffu].l)[lane] = r;       // lanes 14, 15 write the zero padding
+}
+__device__ __forceinline__ void exec_lin16(F29* regs, const uint32_t* ins, const uint16_t* terms, bool active, const int32_t* p29s, int lane) {
+    // limb sums on 16-bit halves (48 units of 2^29 overflow 32 bits): two 32-bit multiply-adds per term, no wide multiplication
+    int32_t sl = 0, sh = 0;
+    const uint16_t* tt = terms + ins[1];
+    const uint32_t count = ins[2];
+    const int32_t* base = reinterpret_cast<const int32_t*>(regs) + lane;
+#pragma unroll 2
+    for (uint32_t k = 0; k < count; k++) {
+        const uint32_t e = tt[k];
+        const int32_t v = base[(e & 0x3fffu) * 16];
+        int32_t coef = (int32_t)((e >> 15) & 1u) + 1;
+        if (e & 0x4000u) coef = -coef;
+        sl += (v & 0xffff) * coef;
+        sh += (v >> 16) * coef;
+    }
+    int64_t t = (int64_t)sl + ((int64_t)sh << 16);
+    if (ins[3] & 1u) {
+        const float f = lane == 13 ? (float)t * 536870912.0f : (lane == 12 ? (float)t : 0.0f);
+        const float vf = __shfl_sync(kFull, f, 13, kGroupLanes) + __shfl_sync(kFull, f, 12, kGroupLanes);
+        const float pinv = 1.0f / ((float)f29::p29_rt(13) * 536870912.0f + (float)f29::p29_rt(12));
+        const int32_t q = (int32_t)rintf(vf * pinv);
+        t -= mulw(p29s[lane], q);
+    }
+    const int32_t r = carry_top(t, lane);
+    if (active) reinterpret_cast<int32_t*>(regs[ins[0]].l)[lane] = r;
+}
+#endif
+
+// run one program; every cooperating thread must call it (barriers inside).  Force-inlined: the pairing is driven by ONE interpreter
+// loop (run_script), so the executors exist once in the kernel and see the shared-memory address space of their operands.
+KZG_HD void run(int prog, F29* regs, const Lanes& L) {
     const Program p = L.tab.prog[prog];
     for (int lv = p.first_level; lv < p.first_level + p.n_levels; lv++) {
         const Level lev = L.tab.level[lv];
 #ifdef __CUDA_ARCH__
         long long c0 = L.ticks ? clock64() : 0;
-#endif
-        if (lev.kind == 1) { for (int k = L.tid; k < lev.count; k += L.n) exec_mul(regs, L.tab.mul[lev.first + k]); }
-        else { for (int k = L.tid; k < lev.count; k += L.n) exec_lin(regs, L.tab.lin[lev.first + k], L.tab.term); }
-#ifdef __CUDA_ARCH__
+        const int g = L.tid >> 4, ng = L.n >> 4, lane = L.tid & 15;
+        long long* S = L.scratch + (size_t)g * kScratchWords;
+        for (int base = 0; base < lev.count; base += ng) {
+            const int k = base + g;
+            if (base + (g & ~1) >= lev.count) break;              // neither group of this warp has an instruction left (warp-uniform)
+            const bool active = k < lev.count;                    // an idle second group runs along: the shuffles need every lane
+            const int idx = lev.first + (active ? k : base);
+            if (lev.kind == 1) exec_mul16(regs, L.tab.mul[idx], active, S, lane);
+            else exec_lin16(regs, L.tab.lin[idx], L.tab.term, active, L.p29s, lane);
+        }
         long long c1 = L.ticks ? clock64() : 0;
+#else
+        if (lev.kind == 1) { for (int k = 0; k < lev.count; k++) exec_mul_ref(regs, L.tab.mul[lev.first + k]); }
+        else { for (int k = 0; k < lev.count; k++) exec_lin_ref(regs, L.tab.lin[lev.first + k], L.tab.term); }
 #endif
         L.sync();
 #ifdef __CUDA_ARCH__
-        if (L.ticks && L.tid == 0) {   // profiling aid: body / barrier-wait cycles of lane 0 per level kind
+        if (L.ticks && L.tid == 0) {   // profiling aid: body / barrier-wait cycles of thread 0 per level kind
             long long c2 = clock64();
             int b = lev.kind == 1 ? 10 : 8;
             L.ticks[b] += c1 - c0; L.ticks[b + 1] += c2 - c1; L.ticks[b == 10 ? 13 : 12] += 1;
@@ -155,8 +328,17 @@ KZG_NI void run(int prog, F29* regs, const Lanes& L) {
 #endif
     }
 }
+// the same program on the sequential executors, one thread (GPU unit test of the 16-lane forms)
+KZG_NI void run_ref(int prog, F29* regs, const Tables& tab) {
+    const Program p = tab.prog[prog];
+    for (int lv = p.first_level; lv < p.first_level + p.n_levels; lv++) {
+        const Level lev = tab.level[lv];
+        if (lev.kind == 1) { for (int k = 0; k < lev.count; k++) exec_mul_ref(regs, tab.mul[lev.first + k]); }
+        else { for (int k = 0; k < lev.count; k++) exec_lin_ref(regs, tab.lin[lev.first + k], tab.term); }
+    }
+}
 // regs[dst .. dst+count) = regs[src ..)   (16-byte words)
-KZG_NI void copy_regs(F29* regs, int dst, int src, int count, const Lanes& L) {
+KZG_HD void copy_regs(F29* regs, int dst, int src, int count, const Lanes& L) {
     uint4* d = reinterpret_cast<uint4*>(regs + dst);
     const uint4* s = reinterpret_cast<const uint4*>(regs + src);
     for (int j = L.tid; j < count * 4; j += L.n) d[j] = s[j];
@@ -165,7 +347,7 @@ KZG_NI void copy_regs(F29* regs, int dst, int src, int count, const Lanes& L) {
 
 // Line tables in the engine's representation: per fixed G2 point, per Miller step, (A, B, C) as 6 values (setup: k_setup.cu)
 struct LineCoeffs29 { F29 v[6]; };
-KZG_NI void load_lines(F29* regs, const LineCoeffs29* c1, const LineCoeffs29* c2, int k, const Lanes& L) {
+KZG_HD void load_lines(F29* regs, const LineCoeffs29* c1, const LineCoeffs29* c2, int k, const Lanes& L) {
     uint4* d = reinterpret_cast<uint4*>(regs + kRegLines);
     for (int q = L.tid; q < 2 * 6 * 4; q += L.n) {
         const LineCoeffs29* src = q < 24 ? c1 : c2;
@@ -175,38 +357,28 @@ KZG_NI void load_lines(F29* regs, const LineCoeffs29* c1, const LineCoeffs29* c2
     L.sync();
 }
 
+// any register value (signed, |v| < bound p) -> the canonical integer of the field element it stands for
+KZG_NI Fp canonical_signed(const F29& v, int bound = kIoBound) {
+    int64_t t[14];
+    for (int i = 0; i < 14; i++) t[i] = (int64_t)limb(v, i) + (int64_t)bound * (int64_t)f29::p29_rt(i);
+    F29 u;
+    normalize_ref(u, t);                        // now non-negative, limbs in [0, 2^29)
+    return f29::canonical(u);
+}
 // v^-1 (both in the engine's representation); v != 0 mod p
 KZG_NI F29 inv29(const F29& v) {
-    Fp x = f29::canonical(v), y;
+    Fp x = canonical_signed(v), y;
     vliw::fp_inv_raw(y.l, x.l);
     return f29::from_raw(y);
 }
 
-constexpr int kSave0 = kMaxRegs;            // each save slot = 12 registers
+constexpr int kSave0 = kMaxRegs;            // each save slot = 12 registers (the scripts of tools/gen_vliw.py use the same layout)
 constexpr int kNumSaves = 5;
 constexpr int kTotalRegs = kMaxRegs + 12 * kNumSaves;
 
-KZG_HD void sqr_times(F29* regs, int k, const Lanes& L) {
-    for (; k > 0; k--) run(kProg_cyc_sqr1, regs, L);
-}
-// F <- conj(base^|x|) for base in the cyclotomic subgroup (save slot `base`); G is the multiplier slot
-KZG_HD void exp_by_x_slot(F29* regs, int base, const Lanes& L) {
-    copy_regs(regs, kRegF, base, 12, L);
-    int pending = 0;
-    for (int bit = 62; bit >= 0; bit--) {
-        pending++;
-        if ((KZG_BLS_X_ABS >> bit) & 1) {
-            sqr_times(regs, pending, L);
-            pending = 0;
-            copy_regs(regs, kRegG, base, 12, L);
-            run(kProg_f12_mul, regs, L);
-        }
-    }
-    sqr_times(regs, pending, L);
-    run(kProg_conj, regs, L);
-}
 // e(P1, Q1) e(P2, Q2) == 1 with the lines of Q1, Q2 precomputed (c1, c2).  All cooperating threads call it with the same
-// arguments; returns the same verdict to all.  regs: kTotalRegs values shared by the threads.
+// arguments; returns the same verdict to all.  regs: kTotalRegs values shared by the threads.  The sequence of engine steps
+// (Miller loop, final exponentiation) is the generated script (vliw29_programs.cuh: script2 = both pairs live, script1 = one).
 KZG_HD bool coop_pairing_product_is_one(F29* regs, const G1Affine& P1, const LineCoeffs29* c1, const G1Affine& P2, const LineCoeffs29* c2,
                                         const Lanes& L) {
     const bool live1 = !P1.inf, live2 = !P2.inf;
@@ -223,63 +395,24 @@ KZG_HD bool coop_pairing_product_is_one(F29* regs, const G1Affine& P1, const Lin
         } else regs[kRegF + (i - 14)] = i == 14 ? f29::f29_one() : f29::f29_zero();
     }
     L.sync();
-    L.tick(1);
-    // Miller loop
-    int k = 0;
-    for (int bit = 62; bit >= 0; bit--) {
-        load_lines(regs, ca, cb, k++, L);
-        if (cb) run(kProg_sqr_lines, regs, L); else { run(kProg_f12_sqr, regs, L); run(kProg_line1, regs, L); }
-        run(kProg_f12_mul, regs, L);
-        if ((KZG_BLS_X_ABS >> bit) & 1) {
-            load_lines(regs, ca, cb, k++, L);
-            run(cb ? kProg_lines : kProg_line1, regs, L);
-            run(kProg_f12_mul, regs, L);
-        }
+#ifdef __CUDA_ARCH__
+    const uint32_t* script = cb ? d_script2 : d_script1;
+#else
+    const uint32_t* script = cb ? h_script2 : h_script1;
+#endif
+    const int n_steps = cb ? kLen_script2 : kLen_script1;
+    for (int s = 0; s < n_steps; s++) {
+        const uint32_t w = script[s];
+        const int op = (int)(w & 0xffu), a = (int)((w >> 8) & 0xfffu), b = (int)(w >> 20);
+        if (op == kOpRun) run(a, regs, L);
+        else if (op == kOpCopy) copy_regs(regs, a, b, 12, L);
+        else if (op == kOpLines) load_lines(regs, ca, cb, a, L);
+        else if (op == kOpInv) { if (L.tid == 0) regs[kRegH + 8] = inv29(regs[kRegH + 8]); L.sync(); }
+        else L.tick(a);
     }
-    run(kProg_conj, regs, L);
-    L.tick(2);
-    // final exponentiation, f^(3(p^12-1)/r):  easy part
-    const int S0 = kSave0, S1 = kSave0 + 12, S2 = kSave0 + 24, S3 = kSave0 + 36, S4 = kSave0 + 48;
-    copy_regs(regs, S0, kRegF, 12, L);                       // S0 = f0
-    run(kProg_inv_prep, regs, L);
-    if (L.tid == 0) regs[kRegH + 8] = inv29(regs[kRegH + 8]);
-    L.sync();
-    run(kProg_inv_finish, regs, L);                          // F = f0^-1
-    copy_regs(regs, kRegG, kRegF, 12, L);
-    copy_regs(regs, kRegF, S0, 12, L);
-    run(kProg_conj, regs, L);
-    run(kProg_f12_mul, regs, L);                             // F = f0^(p^6-1)
-    run(kProg_frob2, regs, L);                               // G = F^(p^2)
-    run(kProg_f12_mul, regs, L);                             // F = f = f0^((p^6-1)(p^2+1))
-    copy_regs(regs, S0, kRegF, 12, L);                       // S0 = f
-    L.tick(3);
-    // hard part: (x-1)^2 (x+p)(x^2+p^2-1) + 3
-    exp_by_x_slot(regs, S0, L);                              // F = f^x
-    copy_regs(regs, kRegG, S0, 12, L); run(kProg_conj_g, regs, L); run(kProg_f12_mul, regs, L);     // f^(x-1)
-    copy_regs(regs, S1, kRegF, 12, L);
-    exp_by_x_slot(regs, S1, L);
-    copy_regs(regs, kRegG, S1, 12, L); run(kProg_conj_g, regs, L); run(kProg_f12_mul, regs, L);     // a = f^((x-1)^2)
-    copy_regs(regs, S1, kRegF, 12, L);                       // S1 = a
-    exp_by_x_slot(regs, S1, L);                              // a^x
-    copy_regs(regs, S2, kRegF, 12, L);
-    copy_regs(regs, kRegF, S1, 12, L); run(kProg_frob, regs, L);                                     // G = a^p
-    copy_regs(regs, kRegF, S2, 12, L); run(kProg_f12_mul, regs, L);                                  // b = a^(x+p)
-    copy_regs(regs, S2, kRegF, 12, L);                       // S2 = b
-    exp_by_x_slot(regs, S2, L);
-    copy_regs(regs, S3, kRegF, 12, L);
-    exp_by_x_slot(regs, S3, L);                              // b^(x^2)
-    copy_regs(regs, S4, kRegF, 12, L);
-    copy_regs(regs, kRegF, S2, 12, L); run(kProg_frob2, regs, L);                                    // G = b^(p^2)
-    copy_regs(regs, kRegF, S4, 12, L); run(kProg_f12_mul, regs, L);
-    copy_regs(regs, kRegG, S2, 12, L); run(kProg_conj_g, regs, L); run(kProg_f12_mul, regs, L);      // c = b^(x^2+p^2-1)
-    copy_regs(regs, S4, kRegF, 12, L);
-    copy_regs(regs, kRegF, S0, 12, L); run(kProg_f12_sqr, regs, L);
-    copy_regs(regs, kRegG, S0, 12, L); run(kProg_f12_mul, regs, L);                                  // f^3
-    copy_regs(regs, kRegG, S4, 12, L); run(kProg_f12_mul, regs, L);                                  // c f^3
-    L.tick(4);
-    // == 1 ?  (each coefficient canonicalised by its own thread; the verdict words land in the G slot)
+    // == 1 ?  (each coefficient canonicalised by its own thread; the verdict words land in the padding of the G slot)
     for (int i = L.tid; i < 12; i += L.n) {
-        Fp x = f29::canonical(regs[kRegF + i]);
+        Fp x = canonical_signed(regs[kRegF + i]);
         bool good = i == 0 ? (x.l[0] == 1u) : (x.l[0] == 0u);
         for (int w = 1; w < 12; w++) good = good && x.l[w] == 0u;
         regs[kRegG + i].l[15] = good ? 1u : 0u;
@@ -287,6 +420,8 @@ KZG_HD bool coop_pairing_product_is_one(F29* regs, const G1Affine& P1, const Lin
     L.sync();
     bool ok = true;
     for (int i = 0; i < 12; i++) ok = ok && regs[kRegG + i].l[15] == 1u;
+    L.sync();
+    for (int i = L.tid; i < 12; i += L.n) regs[kRegG + i].l[15] = 0;
     L.sync();
     return ok;
 }

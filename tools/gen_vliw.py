@@ -183,31 +183,27 @@ class Builder:
 BUILDER = Builder
 
 # ------------------------------------------------------------------------------------------ headroom programs (vliw29.cuh)
-# Second engine representation: Fp values as 14 limbs of 29 bits (406 bits, Montgomery radix 2^406 = 2^25.3 p), products as
-# carry-free 64-bit column sums (IMAD.WIDE without the carry chain: twice the issue rate of IMAD.WIDE.X, and independent
-# columns instead of one long chain).  The 25 spare bits replace the modular reduction after every sum: a register holds ANY
-# representative below bound * p, the bounds are tracked HERE, statically:
-#   MUL  d = (a b + c d') / 2^406 : needs A B + C D <= 2^23 (bounds in units of p) and yields a value below 1.25 p;
-#   LIN  d = K p + sum +-(1|2) src : K = ceil(sum of the bounds of the subtracted terms) keeps the sum non-negative; no
-#        reduction unless the bound leaves LIN_LIMIT (program outputs: IO_BOUND), in which case the instruction carries a
-#        `reduce` flag: the executing thread subtracts floor-estimate(v / p) * p (float estimate from the two top columns,
-#        error < 4), leaving a value below RED_BOUND * p.
-# A product subtracted as a whole, a b - c d, runs as signed column sums plus Kx p^2, Kx = ceil(C D).
+# Second engine representation: Fp values as 14 SIGNED limbs of 29 bits (Montgomery radix 2^406 = 2^25.3 p), products as
+# carry-free 64-bit column sums.  The 25 spare bits replace the modular reduction after every sum: a register holds ANY
+# representative v with |v| < bound * p; the bounds are tracked HERE, statically:
+#   MUL  d = (a b +- c d) / 2^406 (mod p): needs A B + C D <= 2^23 (bounds in units of p); |d| < 1.25 p;
+#   LIN  d = sum +-(1|2) src: no reduction unless the bound leaves LIN_LIMIT (program outputs: IO_BOUND), in which case the
+#        instruction carries a `reduce` flag: the executing lanes subtract round-estimate(v / p) * p (float estimate from the two
+#        top columns), leaving |d| < RED_BOUND * p.
 import math
 from fractions import Fraction
 
 W29, N29 = 29, 14
 R29 = 1 << (W29 * N29)
 IO_BOUND = 8
-RED_BOUND = 6
+RED_BOUND = 4
 LIN_LIMIT = 1024
 MUL_BOUND = Fraction(5, 4)
 MULSUM_LIMIT = 1 << 23
 
 
 class Terms(list):
-    """LIN payload of the headroom programs: the term list, the multiple of p added, the reduce flag"""
-    K = 0
+    """LIN payload of the headroom programs: the term list + the reduce flag"""
     reduce = False
 
 
@@ -217,7 +213,6 @@ class Builder29(Builder):
     def __init__(self, name, n_inputs):
         super().__init__(name, n_inputs)
         self.bound = {r: Fraction(IO_BOUND) for r in range(n_inputs)}
-        self.out_bounds = []
 
     @staticmethod
     def _terms(v):
@@ -232,14 +227,10 @@ class Builder29(Builder):
         return terms
 
     def _meta(self, terms, limit):
-        w = lambda t: (2 if t[2] else 1) * self.bound[t[0]]
-        pos = sum((w(t) for t in terms if not t[1]), Fraction(0))
-        neg = sum((w(t) for t in terms if t[1]), Fraction(0))
-        K = int(math.ceil(neg))
-        b = pos + K
+        b = sum(((2 if t[2] else 1) * self.bound[t[0]] for t in terms), Fraction(0))
         assert b < (1 << 20), "sum too large for the float quotient estimate"
         t = Terms(terms)
-        t.K, t.reduce = K, b > limit
+        t.reduce = b > limit
         return t, (Fraction(RED_BOUND) if t.reduce else b)
 
     def materialize(self, v):
@@ -266,19 +257,16 @@ class Builder29(Builder):
         return [(self.materialize(v), False)]
 
     def mul(self, a, b, c=None, d=None, neg=False):
-        """a b (+|-) c d.  A subtracted product is executed natively: signed column sums plus Kx p^2 with
-        Kx = ceil(C D) >= c d / p^2, so that the total stays non-negative for the Montgomery reduction."""
         ops = [self.operand(a), self.operand(b)]
         if c is not None:
             ops += [self.operand(c), self.operand(d)]
         bs = [self.bound[o[0][0]] for o in ops]
         total = bs[0] * bs[1] + (bs[2] * bs[3] if c is not None else 0)
-        kx = int(math.ceil(bs[2] * bs[3])) if (c is not None and neg) else 0
         assert total + 1 <= MULSUM_LIMIT, "operand bounds too large"
         level = 1 + max(self.level_of[r] for o in ops for r, _ in o)
         dst = self._new(level)
         self.bound[dst] = MUL_BOUND
-        self.instrs.append((level, "MUL", dst, (ops, ("neg", kx) if neg else False)))
+        self.instrs.append((level, "MUL", dst, (ops, bool(neg))))
         return Val({dst: 1})
 
     def output(self, v, reg):
@@ -292,12 +280,14 @@ class Builder29(Builder):
 
 
 def limbs29(v):
-    assert 0 <= v < R29
-    return [(v >> (W29 * i)) & ((1 << W29) - 1) for i in range(N29)]
+    """signed limbs: 13 limbs in [0, 2^29), the top limb carries the sign"""
+    assert -R29 < v < R29
+    l = [(v >> (W29 * i)) & ((1 << W29) - 1) for i in range(N29 - 1)]
+    return l + [v >> (W29 * (N29 - 1))]
 
 
 def lin29_exact(values, pay):
-    """the LIN instruction exactly as vliw29.cuh executes it: 64-bit column sums, K p added, the float32 quotient estimate"""
+    """the LIN instruction as vliw29.cuh executes it: 64-bit column sums, then the float32 quotient estimate"""
     import numpy as np
     f32 = np.float32
     pl = limbs29(P)
@@ -306,23 +296,17 @@ def lin29_exact(values, pay):
         c = (2 if db else 1) * (-1 if ng else 1)
         for i, x in enumerate(limbs29(values[r])):
             t[i] += c * x
-    for i in range(N29):
-        t[i] += pay.K * pl[i]
-        assert -(1 << 63) <= t[i] < (1 << 63)
     if pay.reduce:
         vf = f32(f32(t[13]) * f32(536870912.0)) + f32(t[12])
-        pinv = f32(1.0) / f32(f32(f32(pl[13]) * f32(536870912.0)) + f32(pl[12]) + f32(1.0))
-        q = int(f32(vf * pinv)) - 2
-        if q < 0:
-            q = 0
+        pinv = f32(1.0) / f32(f32(f32(pl[13]) * f32(536870912.0)) + f32(pl[12]))
+        q = int(np.rint(f32(vf * pinv)))
         for i in range(N29):
             t[i] -= q * pl[i]
-    v = sum(x << (W29 * i) for i, x in enumerate(t))
-    return v
+    return sum(x << (W29 * i) for i, x in enumerate(t))
 
 
 def run29_exact(prog, regs):
-    """registers hold the actual integers (Montgomery residues to the radix 2^406 with slack); bounds are asserted"""
+    """registers hold the actual (signed) integers: Montgomery residues to the radix 2^406 with slack; bounds are asserted"""
     pinv = (-pow(P, -1, R29)) % R29
     for kind, ins in prog:
         new = {}
@@ -331,25 +315,27 @@ def run29_exact(prog, regs):
                 ops, neg = pay
                 assert all(len(o) == 1 and not o[0][1] for o in ops)
                 x = [regs[o[0][0]] for o in ops]
-                t = x[0] * x[1] + (x[2] * x[3] if len(x) == 4 else 0)
-                if neg:
-                    t = x[0] * x[1] - x[2] * x[3] + neg[1] * P * P
-                    assert t >= 0
+                t = x[0] * x[1]
+                if len(x) == 4:
+                    t = t - x[2] * x[3] if neg else t + x[2] * x[3]
                 m = (t * pinv) % R29
                 v = (t + m * P) >> (W29 * N29)
-                assert v < MUL_BOUND * P
+                assert (t + m * P) % R29 == 0 and abs(v) < MUL_BOUND * P
             else:
                 v = lin29_exact(regs, pay)
-                assert 0 <= v < (RED_BOUND if pay.reduce else 1 << 20) * P, (v // P, pay.K, pay.reduce)
-            assert 0 <= v < R29 and (dst >= N_IN or v < IO_BOUND * P)
+                assert abs(v) < (RED_BOUND if pay.reduce else 1 << 20) * P, (v // P, pay.reduce)
+            assert dst >= N_IN or abs(v) < IO_BOUND * P
             new[dst] = v
         regs.update(new)
 
 
 def run29(prog, regs):
-    """selftest adapter: canonical values in, canonical values out; inside, random representatives below IO_BOUND p"""
+    """selftest adapter: canonical values in, canonical values out; inside, random representatives with |v| < IO_BOUND p"""
     rnd = random.Random(len(prog) * 7919 + 1)
-    enc = {k: v * R29 % P + rnd.randrange(IO_BOUND) * P if rnd.random() < 0.7 else v * R29 % P + (IO_BOUND - 1) * P for k, v in regs.items()}
+    def rep(v):
+        k = rnd.randrange(-IO_BOUND, IO_BOUND) if rnd.random() < 0.7 else rnd.choice((-IO_BOUND, IO_BOUND - 1))
+        return v * R29 % P + k * P
+    enc = {k: rep(v) for k, v in regs.items()}
     run29_exact(prog, enc)
     rinv = pow(R29, -1, P)
     for k, v in enc.items():
@@ -855,9 +841,64 @@ def emit(sets, path):
     open(path, "w").write("\n".join(out) + "\n")
 
 
+OP_RUN, OP_COPY, OP_LINES, OP_INV, OP_TICK = range(5)
+BLS_X_ABS = 0xd201000000010000
+
+
+def pairing_script(names, max_regs, two_pairs):
+    """The pairing check e(P1, Q1) e(P2, Q2) == 1 (one pair when the other G1 argument is the identity) as a straight list of
+    engine steps -- run a program, copy an Fp12 slot, load the line coefficients of Miller step k, invert one register, stamp a
+    profiling tick -- so that the kernel contains ONE interpreter loop with the two instruction executors inlined once.
+    Same sequence as vliw.cuh coop_pairing_product_is_one: Miller loop with precomputed lines, then f^(3(p^12-1)/r) with the
+    hard part (x-1)^2 (x+p)(x^2+p^2-1) + 3 on cyclotomic squarings."""
+    P = {n: i for i, n in enumerate(names)}
+    S = [max_regs + 12 * i for i in range(5)]
+    F, G = 0, RG
+    s = []
+    run = lambda n: s.append((OP_RUN, P[n], 0))
+    copy = lambda d, src: s.append((OP_COPY, d, src))
+    tick = lambda i: s.append((OP_TICK, i, 0))
+    def exp_by_x(base):
+        copy(F, base)
+        pending = 0
+        for bit in range(62, -1, -1):
+            pending += 1
+            if (BLS_X_ABS >> bit) & 1:
+                for _ in range(pending): run("cyc_sqr1")
+                pending = 0
+                copy(G, base); run("f12_mul")
+        for _ in range(pending): run("cyc_sqr1")
+        run("conj")
+    tick(1)
+    k = 0
+    for bit in range(62, -1, -1):
+        s.append((OP_LINES, k, 0)); k += 1
+        if two_pairs:
+            run("sqr_lines")
+        else:
+            run("f12_sqr"); run("line1")
+        run("f12_mul")
+        if (BLS_X_ABS >> bit) & 1:
+            s.append((OP_LINES, k, 0)); k += 1
+            run("lines" if two_pairs else "line1"); run("f12_mul")
+    run("conj"); tick(2)
+    copy(S[0], F); run("inv_prep"); s.append((OP_INV, 0, 0)); run("inv_finish")
+    copy(G, F); copy(F, S[0]); run("conj"); run("f12_mul")          # f0^(p^6-1)
+    run("frob2"); run("f12_mul"); copy(S[0], F); tick(3)            # S0 = f = f0^((p^6-1)(p^2+1))
+    exp_by_x(S[0]); copy(G, S[0]); run("conj_g"); run("f12_mul"); copy(S[1], F)          # f^(x-1)
+    exp_by_x(S[1]); copy(G, S[1]); run("conj_g"); run("f12_mul"); copy(S[1], F)          # a = f^((x-1)^2)
+    exp_by_x(S[1]); copy(S[2], F); copy(F, S[1]); run("frob"); copy(F, S[2]); run("f12_mul"); copy(S[2], F)   # b = a^(x+p)
+    exp_by_x(S[2]); copy(S[3], F); exp_by_x(S[3]); copy(S[4], F)                          # b^(x^2)
+    copy(F, S[2]); run("frob2"); copy(F, S[4]); run("f12_mul")
+    copy(G, S[2]); run("conj_g"); run("f12_mul"); copy(S[4], F)                           # c = b^(x^2+p^2-1)
+    copy(F, S[0]); run("f12_sqr"); copy(G, S[0]); run("f12_mul")                          # f^3
+    copy(G, S[4]); run("f12_mul"); tick(4)                                                # c f^3
+    return [op | a << 8 | b << 20 for op, a, b in s]
+
+
 def emit29(progs, path):
-    """tables of the headroom programs (vliw29.cuh): MUL row = {dst | a << 16, b | c << 16, d | flags << 16, Kx} with flags bit 0 =
-    dual product, bit 1 = the second product is subtracted; LIN row = {dst, first term, term count, K | reduce << 31}"""
+    """tables of the headroom programs (vliw29.cuh): MUL row = {dst | a << 16, b | c << 16, d | flags << 16, 0} with flags bit 0 =
+    dual product, bit 1 = the second product is subtracted; LIN row = {dst, first term, term count, reduce}"""
     mul_tab, lin_tab, term_tab, level_tab, prog_tab, names = [], [], [], [], [], []
     print("-- lat29")
     for name, prog in progs.items():
@@ -868,13 +909,13 @@ def emit29(progs, path):
                 for _, dst, (ops, neg) in ins:
                     r = [o[0][0] for o in ops] + [0xffff] * (4 - len(ops))
                     flags = (1 if len(ops) == 4 else 0) | (2 if neg else 0)
-                    mul_tab.append((dst | r[0] << 16, r[1] | r[2] << 16, r[3] | flags << 16, neg[1] if neg else 0))
+                    mul_tab.append((dst | r[0] << 16, r[1] | r[2] << 16, r[3] | flags << 16, 0))
                     n_regs = max(n_regs, dst + 1)
                 nmul += len(ins)
             else:
                 level_tab.append((0, len(ins), len(lin_tab)))
                 for _, dst, terms in ins:
-                    lin_tab.append((dst, len(term_tab), len(terms), terms.K | (1 << 31 if terms.reduce else 0)))
+                    lin_tab.append((dst, len(term_tab), len(terms), 1 if terms.reduce else 0))
                     for r, ng, db in terms:
                         term_tab.append(r | (1 << 14 if ng else 0) | (1 << 15 if db else 0))
                     n_regs = max(n_regs, dst + 1)
@@ -901,8 +942,14 @@ def emit29(progs, path):
         out.append("%s uint16_t %s_term[%d] = {%s};" % (qual, pre, len(term_tab), ",".join(str(t) for t in term_tab)))
         out.append("%s Level %s_level[%d] = {%s};" % (qual, pre, len(level_tab), ",".join(row(l) for l in level_tab)))
         out.append("%s Program %s_prog[%d] = {%s};" % (qual, pre, len(prog_tab), ",".join(row(p) for p in prog_tab)))
+        for tag, two in (("script2", True), ("script1", False)):
+            sc = pairing_script(names, max(p[2] for p in prog_tab), two)
+            if pre == "d":
+                out.append("constexpr int kLen_%s = %d;" % (tag, len(sc)))
+            out.append("%s uint32_t %s_%s[%d] = {%s};" % (qual, pre, tag, len(sc), ",".join(str(x) for x in sc)))
         if pre == "h":
             out.append("#endif")
+    out.append("enum ScriptOp { kOpRun = %d, kOpCopy = %d, kOpLines = %d, kOpInv = %d, kOpTick = %d };   // step = op | a << 8 | b << 20" % (OP_RUN, OP_COPY, OP_LINES, OP_INV, OP_TICK))
     out.append("}}  // namespace kzgb200::vliw29")
     open(path, "w").write("\n".join(out) + "\n")
 

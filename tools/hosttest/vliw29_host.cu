@@ -1,6 +1,8 @@
 // CPU unit test of the 29-bit-limb cooperative pairing engine (fp29.cuh, vliw29.cuh): Montgomery products against the
-// 12 x 32 field layer, conversions, inversion, and the same verdicts as the scalar path on the reference's
-// verify_kzg_proof vectors.  Built and run by tests/test_host_cuda_logic.py.
+// 12 x 32 field layer, conversions, inversion, the sequential reference executors of the two engine instructions on signed
+// representatives, and the same verdicts as the scalar path on the reference's verify_kzg_proof vectors (the engine programs
+// run on the reference executors here; the 16-lane device forms are compared with them on the GPU).
+// Built and run by tests/test_host_cuda_logic.py.
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -32,6 +34,17 @@ int main(int argc, char** argv) {
     f29::mont_mul29(r.l, a.l, b.l, b.l, b.l, true, true, 2); r.l[14] = r.l[15] = 0;
     if (!(f29::canonical(r) == (x * y - y * y).to_raw())) { puts("neg dual mismatch"); return 4; }
     if (!(f29::canonical(vliw29::inv29(a)) == vliw::fp_inv_bingcd(x).to_raw())) { puts("inverse mismatch"); return 4; }
+    // reference executors on signed representatives: r3 = a b - b b ; r4 = r3 - 2 a + b (reduced)
+    f29::F29 file[8]; file[0] = a; file[1] = b;
+    const uint32_t mul_ins[4] = {3u | (0u << 16), 1u | (1u << 16), 1u | (3u << 16), 0u};
+    vliw29::exec_mul_ref(file, mul_ins);
+    if (!(vliw29::canonical_signed(file[3]) == (x * y - y * y).to_raw())) { puts("exec_mul_ref mismatch"); return 4; }
+    const uint16_t terms[3] = {3, (uint16_t)(0 | 0x4000 | 0x8000), 1};
+    for (uint32_t red = 0; red < 2; red++) {
+      const uint32_t lin_ins[4] = {4u, 0u, 3u, red};
+      vliw29::exec_lin_ref(file, lin_ins, terms);
+      if (!(vliw29::canonical_signed(file[4]) == (x * y - y * y - x - x + y).to_raw())) { puts("exec_lin_ref mismatch"); return 4; }
+    }
   }
   std::vector<f29::F29> regs(vliw29::kTotalRegs);
   vliw29::Lanes L{0, 1, vliw29::default_tables()};
