@@ -351,7 +351,9 @@ def count_launches(n, resident, mode, world=1, leader=True):
         chunks = math.ceil(n / (math.ceil(max(1024, math.ceil(n / 64)) / 16) * 16))
         head = 2 * chunks
     transcript = {"exact": 1, "tree": 2 * chunks + 1, "device": 2 * chunks}[mode]
-    tail = 5 + 1 + 1 if world == 1 else (5 + (3 if leader else 1))     # msm x5, pairing, flag merge | + wait_flags on the leader
+    # msm x6 (scalars, sort, bucket, bucket join, window, combine), final check x2 (G1 prelude + pairing engine), flag merge | the
+    # leader of a group also launches wait_flags
+    tail = 6 + 2 + 1 if world == 1 else (6 + (4 if leader else 1))
     return 2 + head + (1 if resident else 0) + transcript + tail        # 2 = G1 decompression + subgroup checks; export of z / y on resident calls
 
 

@@ -33,7 +33,7 @@ constexpr int32_t kM = (int32_t)f29::kMask;
 struct Tables {
     const uint32_t (*mul)[4];
     const uint32_t (*lin)[4];
-    const uint16_t* term;
+    const uint32_t* term;
     const Level* level;
     const Program* prog;
 };
@@ -66,7 +66,7 @@ KZG_HD Tables default_tables() {
 struct SharedTables {
     uint32_t mul[kNumMul][4];
     uint32_t lin[kNumLin][4];
-    uint16_t term[kNumTerm];
+    uint32_t term[kNumTerm];
     Level level[kNumLevel];
     Program prog[kNumPrograms];
     int32_t p29[16];              // limbs of p, one per lane (lanes 14, 15: 0)
@@ -133,15 +133,14 @@ KZG_NI void exec_mul_ref(F29* regs, const uint32_t* ins) {
     normalize_ref(r, t + 14);
     regs[w0 & 0xffffu] = r;
 }
-// LIN row: {dst, first term, term count, reduce}; a term = reg | neg << 14 | dbl << 15
-KZG_NI void exec_lin_ref(F29* regs, const uint32_t* ins, const uint16_t* terms) {
+// LIN row: {dst, first term, term count, reduce}; a term = byte offset of the source register (reg * 64) | coefficient << 16
+KZG_NI void exec_lin_ref(F29* regs, const uint32_t* ins, const uint32_t* terms) {
     int64_t t[14];
     for (int i = 0; i < 14; i++) t[i] = 0;
     for (uint32_t k = 0; k < ins[2]; k++) {
         const uint32_t e = terms[ins[1] + k];
-        const F29& v = regs[e & 0x3fffu];
-        int32_t coef = (int32_t)((e >> 15) & 1u) + 1;
-        if (e & 0x4000u) coef = -coef;
+        const F29& v = regs[(e & 0xffffu) >> 6];
+        const int32_t coef = (int32_t)e >> 16;
         for (int i = 0; i < 14; i++) t[i] += (int64_t)limb(v, i) * coef;
     }
     if (ins[3] & 1u) {
@@ -267,28 +266,29 @@ __device__ __forceinline__ void exec_mul16(F29* regs, const uint32_t* ins, bool 
     const int32_t r = carry_top(hi, lane);
     if (active) reinterpret_cast<int32_t*>(regs[w0 & 0xffffu].l)[lane] = r;       // lanes 14, 15 write the zero padding
 }
-__device__ __forceinline__ void exec_lin16(F29* regs, const uint32_t* ins, const uint16_t* terms, bool active, const int32_t* p29s, int lane) {
+__device__ __forceinline__ void exec_lin16(F29* regs, const uint32_t* ins, const uint32_t* terms, bool active, const int32_t* p29s, int lane) {
     // limb sums on 16-bit halves (48 units of 2^29 overflow 32 bits): two 32-bit multiply-adds per term, no wide multiplication
     int32_t sl = 0, sh = 0;
-    const uint16_t* tt = terms + ins[1];
+    const uint32_t* tt = terms + ins[1];
     const uint32_t count = ins[2];
-    const int32_t* base = reinterpret_cast<const int32_t*>(regs) + lane;
-#pragma unroll 2
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(regs) + 4 * lane;
+#pragma unroll 4
     for (uint32_t k = 0; k < count; k++) {
         const uint32_t e = tt[k];
-        const int32_t v = base[(e & 0x3fffu) * 16];
-        int32_t coef = (int32_t)((e >> 15) & 1u) + 1;
-        if (e & 0x4000u) coef = -coef;
+        const int32_t v = *reinterpret_cast<const int32_t*>(base + (e & 0xffffu));
+        const int32_t coef = (int32_t)e >> 16;
         sl += (v & 0xffff) * coef;
         sh += (v >> 16) * coef;
     }
     int64_t t = (int64_t)sl + ((int64_t)sh << 16);
-    if (ins[3] & 1u) {
+    {   // the shuffles are outside the flag test: the two groups of a warp may run instructions with different flags
         const float f = lane == 13 ? (float)t * 536870912.0f : (lane == 12 ? (float)t : 0.0f);
         const float vf = __shfl_sync(kFull, f, 13, kGroupLanes) + __shfl_sync(kFull, f, 12, kGroupLanes);
-        const float pinv = 1.0f / ((float)f29::p29_rt(13) * 536870912.0f + (float)f29::p29_rt(12));
-        const int32_t q = (int32_t)rintf(vf * pinv);
-        t -= mulw(p29s[lane], q);
+        if (ins[3] & 1u) {
+            const float pinv = 1.0f / ((float)f29::p29_rt(13) * 536870912.0f + (float)f29::p29_rt(12));
+            const int32_t q = (int32_t)rintf(vf * pinv);
+            t -= mulw(p29s[lane], q);
+        }
     }
     const int32_t r = carry_top(t, lane);
     if (active) reinterpret_cast<int32_t*>(regs[ins[0]].l)[lane] = r;

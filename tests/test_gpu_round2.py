@@ -318,6 +318,21 @@ def _sum_partials(api, parts):
     return {"A": A, "B_prime": Bp, "sum_r_y": s}
 
 
+def test_pairing_engine_16_lane_instructions_match_their_reference(K, settings):
+    """csrc/vliw29.cuh: every generated engine program (Fp12 products and squarings, cyclotomic squaring, line products,
+    Frobenius maps, inversion halves, G1 formulas) on the 16-lane cooperative executors versus the sequential reference
+    executors -- the ones the CPU suite runs the reference's 114 verify_kzg_proof vectors on (tools/hosttest/vliw29_host.cu) --
+    from the same seeded register files, programs chained so that the loose signed limb forms feed later programs; every
+    register compared as a canonical field element after every program."""
+    lib, ctx = K.Library.get().dll, settings.context(0)
+    lib.kzgb200_debug_engine_selftest.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
+    for seed in (1, 2, 3, 0xB200):
+        mis = (C.c_uint32 * 32)()
+        n = C.c_int(0)
+        assert lib.kzgb200_debug_engine_selftest(ctx, seed, 2, mis, C.byref(n)) == 0
+        assert n.value >= 12 and not any(mis[i] for i in range(32)), (seed, list(mis))
+
+
 def test_group_across_all_visible_gpus(K, settings, oracle):
     """One process driving every visible GPU (kzgb200_group_create with device ids 0..N-1): the partial sums travel by peer
     stores over NVLink into the leader GPU.  Skipped on a single-GPU box (the two-contexts-on-one-GPU tests cover the protocol)."""

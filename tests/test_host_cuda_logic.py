@@ -2,7 +2,9 @@
 pairing / cooperative-engine code is unit-tested here on the CPU (nvcc host compile of the same headers):
   * Montgomery products (single, fused dual, dedicated squaring), add, sub vs Python integers, edge values included;
   * per-proof verification logic (decompression, subgroup check, G1-side pairing equation with precomputed lines)
-    and the cooperative pairing engine + binary-GCD inversion vs the reference's 114 well-formed verify_kzg_proof vectors;
+    and the cooperative pairing engines + binary-GCD inversion vs the reference's 114 well-formed verify_kzg_proof vectors
+    (vliw_host: the 12 x 32-limb engine of the many-tuple path; vliw29_host: the 29-bit signed-limb engine of the batch path on
+    its sequential reference executors, plus its Montgomery products and conversions against the 12 x 32 field layer);
   * the generated engine programs vs the Python oracle (tools/gen_vliw.py self-test).
 """
 import os
@@ -56,7 +58,7 @@ def _vector_records(vectors):
     return b"".join(recs), "".join(want)
 
 
-@pytest.mark.parametrize("prog", ["verify_host", "vliw_host"])
+@pytest.mark.parametrize("prog", ["verify_host", "vliw_host", "vliw29_host"])
 def test_verification_logic_on_reference_vectors(tmp_path, vectors, prog):
     exe = build(str(tmp_path), prog)
     recs, want = _vector_records(vectors)

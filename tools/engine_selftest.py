@@ -10,6 +10,7 @@ lib.kzgb200_debug_engine_selftest.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C
 bad = 0
 for seed in range(int(sys.argv[1]) if len(sys.argv) > 1 else 4):
     mis = (C.c_uint32 * 32)(); n = C.c_int(0)
+    print("seed", seed, "...", flush=True)
     rc = lib.kzgb200_debug_engine_selftest(ctx, seed, int(sys.argv[2]) if len(sys.argv) > 2 else 2, mis, C.byref(n))
     print("seed", seed, "rc", rc, "mismatches per program", list(mis)[:n.value])
     bad += rc != 0 or any(mis[i] for i in range(n.value))

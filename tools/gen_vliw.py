@@ -898,7 +898,7 @@ def pairing_script(names, max_regs, two_pairs):
 
 def emit29(progs, path):
     """tables of the headroom programs (vliw29.cuh): MUL row = {dst | a << 16, b | c << 16, d | flags << 16, 0} with flags bit 0 =
-    dual product, bit 1 = the second product is subtracted; LIN row = {dst, first term, term count, reduce}"""
+    dual product, bit 1 = the second product is subtracted; LIN row = {dst, first term, term count, reduce}; a term = byte offset of the source register | coefficient (+-1, +-2) << 16"""
     mul_tab, lin_tab, term_tab, level_tab, prog_tab, names = [], [], [], [], [], []
     print("-- lat29")
     for name, prog in progs.items():
@@ -917,7 +917,8 @@ def emit29(progs, path):
                 for _, dst, terms in ins:
                     lin_tab.append((dst, len(term_tab), len(terms), 1 if terms.reduce else 0))
                     for r, ng, db in terms:
-                        term_tab.append(r | (1 << 14 if ng else 0) | (1 << 15 if db else 0))
+                        coef = (2 if db else 1) * (-1 if ng else 1)
+                        term_tab.append((r * 64) | ((coef & 0xffff) << 16))
                     n_regs = max(n_regs, dst + 1)
                 nlin += len(ins)
         prog_tab.append((first_level, len(level_tab) - first_level, n_regs))
@@ -939,7 +940,7 @@ def emit29(progs, path):
             out.append("#ifndef __CUDA_ARCH__")
         out.append("%s uint32_t %s_mul[%d][4] = {%s};" % (qual, pre, len(mul_tab), ",".join(row(m) for m in mul_tab)))
         out.append("%s uint32_t %s_lin[%d][4] = {%s};" % (qual, pre, len(lin_tab), ",".join(row(m) for m in lin_tab)))
-        out.append("%s uint16_t %s_term[%d] = {%s};" % (qual, pre, len(term_tab), ",".join(str(t) for t in term_tab)))
+        out.append("%s uint32_t %s_term[%d] = {%s};" % (qual, pre, len(term_tab), ",".join("%du" % t for t in term_tab)))
         out.append("%s Level %s_level[%d] = {%s};" % (qual, pre, len(level_tab), ",".join(row(l) for l in level_tab)))
         out.append("%s Program %s_prog[%d] = {%s};" % (qual, pre, len(prog_tab), ",".join(row(p) for p in prog_tab)))
         for tag, two in (("script2", True), ("script1", False)):

@@ -39,7 +39,7 @@ int main(int argc, char** argv) {
     const uint32_t mul_ins[4] = {3u | (0u << 16), 1u | (1u << 16), 1u | (3u << 16), 0u};
     vliw29::exec_mul_ref(file, mul_ins);
     if (!(vliw29::canonical_signed(file[3]) == (x * y - y * y).to_raw())) { puts("exec_mul_ref mismatch"); return 4; }
-    const uint16_t terms[3] = {3, (uint16_t)(0 | 0x4000 | 0x8000), 1};
+    const uint32_t terms[3] = {3u * 64u | (1u << 16), 0u * 64u | (0xfffeu << 16), 1u * 64u | (1u << 16)};
     for (uint32_t red = 0; red < 2; red++) {
       const uint32_t lin_ins[4] = {4u, 0u, 3u, red};
       vliw29::exec_lin_ref(file, lin_ins, terms);
