@@ -96,7 +96,9 @@ constexpr int kManySmemBytes = kManyGroups * kManyStride * 4 + (int)sizeof(vliw:
 // ---- kernels (k_*.cu) ----------------------------------------------------------------------------------------
 __global__ void setup_tables_kernel(DeviceTables* T, const uint8_t* g2_points);
 __global__ void setup_lines29_kernel(DeviceTables* T);
-void launch_challenge(int stages, cudaStream_t st, const uint8_t* blobs, const uint8_t* commitments, int n, Fr* z_mont, ZY* zy, Fr* zpow);   // K2
+constexpr int kChallengeSlabs = 8;   // slab-wise arrival of the last host chunk (k_challenge.cu)
+void launch_challenge(int stages, cudaStream_t st, const uint8_t* blobs, const uint8_t* commitments, int n, Fr* z_mont, ZY* zy, Fr* zpow,
+                      const uint8_t* slab_flags = nullptr);   // K2
 __global__ void eval_kernel(const uint8_t* __restrict__ blobs, int n, const Fr* __restrict__ zpow, const DeviceTables* __restrict__ T,
                             ZY* __restrict__ zy, uint32_t* __restrict__ status);
 __global__ void g1_decompress_kernel(const uint8_t* __restrict__ commitments, const uint8_t* __restrict__ proofs, int n, G1Affine* __restrict__ C,

@@ -330,14 +330,31 @@ int launch_phase1(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t* h_blo
         for (int c = 0; c < nchunks; c++) {
             size_t lo = ctx->chunks[c].lo, cnt = ctx->chunks[c].cnt;
             cudaStream_t sw = ctx->s_work[c % kWorkStreams];
-            int rc = h2d_blobs(ctx, const_cast<uint8_t*>(d_blobs) + lo * kBytesPerBlob, h_blobs + lo * kBytesPerBlob, cnt * (size_t)kBytesPerBlob, direct);
-            if (rc) return rc;
-            CK(cudaEventRecord(ctx->ev_h2d[c], ctx->s_copy));
+            int rc = KZGB200_OK;
+            // The last chunk of a multi-chunk copy arrives slab-wise (bytes [16 KiB q, 16 KiB (q+1)) of all its blobs, q = 0..7) and
+            // its hash kernel starts behind slab 0: the per-blob chain (2.7 ms whatever the blob count) then ends ~0.5 ms after the
+            // last byte instead of a whole chain after it.
+            const bool slabs = direct && ctx->slab_tail && nchunks > 1 && c == nchunks - 1 && cnt >= 64;
+            uint8_t* slab_flags = ctx->d_scratch + 480;
+            if (slabs) {
+                const size_t sb = kBytesPerBlob / kChallengeSlabs;
+                CK(cudaMemcpyAsync(slab_flags, ctx->h_flags, kChallengeSlabs, cudaMemcpyHostToDevice, ctx->s_copy));     // zeros; by the copy engine, in order with the slabs
+                for (int q = 0; q < kChallengeSlabs; q++) {
+                    CK(cudaMemcpy2DAsync(const_cast<uint8_t*>(d_blobs) + lo * kBytesPerBlob + q * sb, kBytesPerBlob, h_blobs + lo * kBytesPerBlob + q * sb,
+                                         kBytesPerBlob, sb, cnt, cudaMemcpyHostToDevice, ctx->s_copy));
+                    CK(cudaMemcpyAsync(slab_flags + q, ctx->h_flags + 8, 1, cudaMemcpyHostToDevice, ctx->s_copy));        // a one
+                    if (q == 0) CK(cudaEventRecord(ctx->ev_h2d[c], ctx->s_copy));
+                }
+            } else {
+                rc = h2d_blobs(ctx, const_cast<uint8_t*>(d_blobs) + lo * kBytesPerBlob, h_blobs + lo * kBytesPerBlob, cnt * (size_t)kBytesPerBlob, direct);
+                if (rc) return rc;
+                CK(cudaEventRecord(ctx->ev_h2d[c], ctx->s_copy));
+            }
             CK(cudaStreamWaitEvent(sw, ctx->ev_h2d[c], 0));
             CK(cudaStreamWaitEvent(sw, ctx->ev_begin, 0));
             phase_begin(ctx, kPhChallenge, sw);
             launch_challenge(ctx->sha_stages, sw, d_blobs + lo * kBytesPerBlob, d_c + lo * 48, (int)cnt, ctx->d_z_mont + lo,
-                                                                                                   ctx->d_zy + lo, ctx->d_zpow + lo * 13);
+                             ctx->d_zy + lo, ctx->d_zpow + lo * 13, slabs ? slab_flags : nullptr);
             phase_end(ctx, kPhChallenge, sw);
             phase_begin(ctx, kPhEval, sw);
             eval_kernel<<<(int)cnt, kEvalThreads, 0, sw>>>(d_blobs + lo * kBytesPerBlob, (int)cnt, ctx->d_zpow + lo * 13, ctx->tables, ctx->d_zy + lo, ctx->d_status + lo);
@@ -427,6 +444,7 @@ extern "C" int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_p
         if (const char* v = getenv("KZGB200_PARSE_FUSED")) ctx->parse_fused = atoi(v);
         if (const char* v = getenv("KZGB200_DEFER_SUBGROUP")) ctx->defer_subgroup = atoi(v);
         if (const char* v = getenv("KZGB200_SHA_STAGES")) ctx->sha_stages = atoi(v);
+        if (const char* v = getenv("KZGB200_SLAB_TAIL")) ctx->slab_tail = atoi(v) != 0;
         if (const char* v = getenv("KZGB200_PAGEABLE")) ctx->pageable_mode = !strcmp(v, "direct") ? 1 : (!strcmp(v, "register") ? 2 : 0);
         if (const char* v = getenv("KZGB200_TRANSCRIPT")) ctx->transcript_mode = !strcmp(v, "tree") ? KZGB200_TRANSCRIPT_TREE : (!strcmp(v, "device") ? KZGB200_TRANSCRIPT_EXACT_DEVICE : KZGB200_TRANSCRIPT_EXACT);
         CK(cudaFuncSetAttribute(g1_subgroup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailHogSmem));
@@ -455,6 +473,8 @@ extern "C" int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_p
         CK(cudaMalloc(&ctx->d_halfsum, kMsmRows * kBuckets * sizeof(G1)));
         CK(cudaMalloc(&ctx->d_windows, kMsmSets * kWindows * sizeof(G1)));
         CK(cudaMallocHost(&ctx->h_result, 16));
+        CK(cudaMallocHost(&ctx->h_flags, 16));
+        memset(ctx->h_flags, 0, 8); memset(ctx->h_flags + 8, 1, 8);
         CK(cudaMallocHost(&ctx->h_digest, 32));
         CK(cudaMallocHost(&ctx->h_partial, sizeof(Partial)));
         uint8_t* d_g2 = nullptr;
@@ -492,7 +512,7 @@ extern "C" void kzgb200_destroy(kzgb200_ctx* ctx) {
                     ctx->d_digits, ctx->d_order, ctx->d_start, ctx->d_buckets, ctx->d_halfsum, ctx->d_part, ctx->d_windows, ctx->d_lag_table, ctx->d_scalars, ctx->d_zpow,
                     ctx->d_chain_state, ctx->d_scratch, ctx->d_digest};
     for (void* p : ptrs) if (p) cudaFree(p);
-    void* hptrs[] = {ctx->h_result, ctx->h_digest, ctx->h_partial, ctx->h_zy, ctx->h_c, ctx->h_p, ctx->h_stage[0], ctx->h_stage[1], ctx->h_stage[2], ctx->h_stage[3]};
+    void* hptrs[] = {ctx->h_flags, ctx->h_result, ctx->h_digest, ctx->h_partial, ctx->h_zy, ctx->h_c, ctx->h_p, ctx->h_stage[0], ctx->h_stage[1], ctx->h_stage[2], ctx->h_stage[3]};
     for (void* p : hptrs) if (p) cudaFreeHost(p);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

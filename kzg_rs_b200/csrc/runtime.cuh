@@ -93,6 +93,7 @@ struct kzgb200_ctx {
     int num_sms = 148;
     int parse_fused = 0;            // tuning: decompression + subgroup check in one kernel (env KZGB200_PARSE_FUSED; measured slower)
     int defer_subgroup = 1;         // subgroup checks run beside the latency-bound tail on their own SMs (env KZGB200_DEFER_SUBGROUP)
+    bool slab_tail = true;          // last host chunk copied slab-wise with the hash kernel waiting on arrival flags (env KZGB200_SLAB_TAIL=0: off)
     int sha_stages = 8;             // cp.async ring depth of the challenge hash (env KZGB200_SHA_STAGES: 4 or 8)
     int pageable_mode = 0;          // 0 = pinned staging ring, 1 = plain cudaMemcpyAsync (driver staging), 2 = cudaHostRegister in place
     bool subgroup_pending = false;
@@ -101,6 +102,7 @@ struct kzgb200_ctx {
     cudaEvent_t ev_begin = nullptr, ev_parse = nullptr, ev_decomp = nullptr, ev_bucket = nullptr, ev_sha_all = nullptr, ev_leaf = nullptr;
     cudaEvent_t ev_h2d[kzgb200::kMaxChunks] = {nullptr}, ev_zy[kzgb200::kMaxChunks] = {nullptr}, ev_zyh[kzgb200::kMaxChunks] = {nullptr};
     uint32_t* d_chain_state = nullptr;
+    uint8_t* h_flags = nullptr;     // pinned: 8 zeros, 8 ones (arrival flags of the slab-wise last chunk)
     uint8_t* d_scratch = nullptr;   // 512 bytes for small exports
     // pinned staging ring for pageable caller memory
     static constexpr int kStageBufs = 4;
