@@ -1,0 +1,25 @@
+#!/bin/bash
+# final single-GPU job of round 2: tests, bench lines, launch list, full captures, sanitizers
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
+timeout 1500 python -m pytest tests -m gpu -q --durations=10 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/pytest_gpu.log
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/bench.err
+timeout 900 python bench.py --config tuples --tuples 1000000 --steps 3 --warmup 2 > gpurun_out/bench_tuples.json 2> gpurun_out/bench_tuples.err; echo "tuples rc=$?" >> gpurun_out/bench_tuples.err
+timeout 600 python tools/bench_configs.py > gpurun_out/bench_configs.json 2> gpurun_out/bench_configs.err; echo "configs rc=$?" >> gpurun_out/bench_configs.err
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r02.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_bench.log 2>&1
+B="python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-extras --blobs 16384"
+for k in pairing_check_kernel challenge_kernel eval_kernel batch_final_kernel; do
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -f -o gpurun_out/full_$k $B > gpurun_out/ncu_$k.log 2>&1
+  ncu -i gpurun_out/full_$k.ncu-rep --page raw --csv > gpurun_out/ncu_raw_$k.csv 2>/dev/null
+  rm -f gpurun_out/full_$k.ncu-rep
+done
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest "tests/test_gpu_parity.py::test_synthetic_batch_64_against_oracle" -x -q > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?" >> gpurun_out/sanitizer_memcheck.log
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest "tests/test_gpu_parity.py::test_synthetic_batch_64_against_oracle" -x -q > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?" >> gpurun_out/sanitizer_racecheck.log
+tail -2 gpurun_out/bench.err gpurun_out/bench_tuples.err gpurun_out/bench_configs.err; tail -3 gpurun_out/sanitizer_memcheck.log gpurun_out/sanitizer_racecheck.log
+python - <<'PY'
+import json
+o=json.loads(open('gpurun_out/bench.json').read().strip().split('\n')[-1])
+print(o['value'], o['ms_per_step'], json.dumps(o['phases_ms']), o['e2e'])
+PY
