@@ -184,6 +184,10 @@ int kzgb200_compute_blob_kzg_proof_batch(kzgb200_ctx* ctx, const uint8_t* d_blob
  * {G1 decompression, challenge, evaluate, transcript r (exposed part: last chunk copy + host hash + upload), lincomb terms, reduce,
  * final pairing, deferred subgroup checks (run beside the last three)} of the last call. */
 int kzgb200_set_profiling(kzgb200_ctx* ctx, int on);
+/* Host-memory batches copy their last chunk slab-wise, with the challenge-hash kernel started behind the first slab (on by default:
+ * it shortens a blocking call by ~2 ms).  The streaming front-end turns it off for its contexts: with several calls in flight the
+ * tail of one call already runs under the copies of the next, and the strided copies would only interleave badly. */
+int kzgb200_set_slab_tail(kzgb200_ctx* ctx, int on);
 int kzgb200_get_phase_ms(kzgb200_ctx* ctx, float* out8);
 /* profiling aid: SM clock stamps of the sections of the last single-GPU final pairing kernel */
 int kzgb200_debug_final_ticks(kzgb200_ctx* ctx, long long* out14);

@@ -49,7 +49,7 @@ constexpr int kWindows = 16, kBuckets = 256, kMsmSets = 3, kDigitRows = 4 * kWin
 constexpr int kSlice = 32, kMsmRows = kMsmSets * 2 * kWindows;   // bucket accumulation: entries per thread; rows = (set, GLV half, window)
 constexpr int kWinLanes = 64, kWinPer = kBuckets / kWinLanes;     // 64 lanes x 4 buckets: 48 CTAs still fit the tail's 8 SMs in one wave
 constexpr int kFinalThreads = 64;       // G1 prelude of the final check (sums, [s]G, affine conversion)
-constexpr int kPairThreads = 768;       // pairing engine: 48 groups of 16 lanes, one engine instruction per group
+constexpr int kPairThreads = 768;       // pairing engine: 24 warps = 24 products (one per warp) or 48 sums (16 lanes each) at a time
 constexpr int kManyThreads = 384, kManyGroups = 21;   // many_pairing_kernel: checks run in lockstep by one CTA
 constexpr int kManyWarps = 4;         // many_pairing_warp_kernel (identity inputs): one check per warp
 constexpr int kHarnessMaxDegree = 16;
@@ -72,8 +72,8 @@ __device__ __forceinline__ Fr ldg_fr(const Fr* p) {
 
 // per-rank partial result exchanged between ranks (the payload of the allgather)
 struct Partial {
-    G1 a, b;          // sum r_i pi_i ; sum (r_i C_i + r_i z_i pi_i)
-    Fr ry;            // sum r_i y_i (normal form)
+    G1 a, b;          // sum r_i pi_i ; sum (r_i C_i + r_i z_i pi_i) - [sum r_i y_i]G (the fixed-base term is folded in by msm_combine_kernel)
+    Fr ry;            // a scalar s still to be applied as - [s]G by the final check (normal form); zero since the term is folded into b
     uint32_t err;     // OR of the per-blob error flags of this rank
     uint32_t pad[7];
 };
@@ -86,7 +86,6 @@ struct FinalSmem {                       // prelude kernels (padded: see kTailPa
 struct PairSmem {                        // pairing_check_kernel
     f29::F29 regs[vliw29::kTotalRegs];
     vliw29::SharedTables stab;
-    long long scratch[(kPairThreads / vliw29::kGroupLanes) * vliw29::kScratchWords];
 };
 // hand-over from the prelude kernel to the pairing kernel (device memory, 256 bytes into the context's 512-byte scratch)
 struct FinalPts { G1Affine pts[2]; uint32_t go; };
@@ -127,7 +126,7 @@ __global__ void msm_bucket_join_kernel(int n, const uint32_t* __restrict__ start
                                        G1* __restrict__ buckets);
 __global__ void msm_window_kernel(const G1* __restrict__ buckets, G1* __restrict__ windows);
 __global__ void msm_combine_kernel(const G1* __restrict__ windows, const Fr* __restrict__ ry, const uint32_t* __restrict__ status, int n,
-                                   Partial* __restrict__ out, uint32_t* flag, uint32_t epoch);
+                                   const DeviceTables* __restrict__ T, Partial* __restrict__ out, uint32_t* flag, uint32_t epoch);
 __global__ void wait_flags_kernel(const uint32_t* flags, int count, uint32_t epoch, uint32_t* __restrict__ timed_out);
 __global__ void batch_final_kernel(const Partial* __restrict__ parts, int nparts, const DeviceTables* __restrict__ T, uint32_t* __restrict__ result,
                                    FinalPts* __restrict__ out);

@@ -24,7 +24,8 @@ __global__ void __launch_bounds__(kFinalThreads) batch_final_kernel(const Partia
     }
     __syncthreads();
     if (s_err) { if (t == 0) { result[0] = kBadArgs; result[1] = s_err; out->go = 0; } return; }
-    G1 sg = coop_fixed_base_mul(s_sum, T, sm);
+    G1 sg = G1::identity();
+    if (!s_sum.is_zero()) sg = coop_fixed_base_mul(s_sum, T, sm);      // zero on the batch path: msm_combine_kernel folded - [s]G into b
     if ((t & 31) == 0) {     // lane 0 of warp 0 and of warp 1: the two data-dependent inversion loops run side by side, not serialised
         int w = t >> 5;
         G1 acc = G1::identity();
@@ -38,7 +39,7 @@ __global__ void __launch_bounds__(kFinalThreads) batch_final_kernel(const Partia
     }
 }
 
-// e(pts[1], G2) e(pts[0], [tau]G2) == 1 on the cooperative engine (vliw29.cuh): kPairThreads threads = 48 groups of 16 lanes.
+// e(pts[1], G2) e(pts[0], [tau]G2) == 1 on the cooperative engine (vliw29.cuh): kPairThreads threads = 24 warps.
 __global__ void __launch_bounds__(kPairThreads) pairing_check_kernel(const FinalPts* __restrict__ in, const DeviceTables* __restrict__ T,
                                                                      uint32_t* __restrict__ result, long long* __restrict__ ticks) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -46,9 +47,8 @@ __global__ void __launch_bounds__(kPairThreads) pairing_check_kernel(const Final
     const int t = threadIdx.x;
     if (in->go == 0) return;            // the prelude already wrote the result
     if (ticks && t == 0) { ticks[0] = clock64(); for (int i = 8; i < 14; i++) ticks[i] = 0; }
-    for (int i = t; i < (int)(sizeof(S.scratch) / sizeof(long long)); i += kPairThreads) S.scratch[i] = 0;
     vliw29::Tables tab = vliw29::load_tables(&S.stab, t, kPairThreads);
-    vliw29::Lanes L{t, kPairThreads, tab, ticks, S.scratch, S.stab.p29};
+    vliw29::Lanes L{t, kPairThreads, tab, ticks, S.stab.p29};
     const G1Affine p0 = in->pts[0], p1 = in->pts[1];
     bool ok = vliw29::coop_pairing_product_is_one(S.regs, p1, T->lines29[0], p0, T->lines29[1], L);
     L.tick(5);
@@ -62,9 +62,8 @@ __global__ void __launch_bounds__(kPairThreads) engine_selftest_kernel(uint32_t 
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     PairSmem& S = *reinterpret_cast<PairSmem*>(dyn_smem);
     const int t = threadIdx.x;
-    for (int i = t; i < (int)(sizeof(S.scratch) / sizeof(long long)); i += kPairThreads) S.scratch[i] = 0;
     vliw29::Tables tab = vliw29::load_tables(&S.stab, t, kPairThreads);
-    vliw29::Lanes L{t, kPairThreads, tab, nullptr, S.scratch, S.stab.p29};
+    vliw29::Lanes L{t, kPairThreads, tab, nullptr, S.stab.p29};
     for (int i = t; i < vliw29::kTotalRegs; i += kPairThreads) {
         Fp x;
         uint32_t s = seed * 2654435761u + (uint32_t)i * 40503u + 1u;

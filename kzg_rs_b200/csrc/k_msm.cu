@@ -159,14 +159,17 @@ __global__ void __launch_bounds__(kWinLanes) msm_window_kernel(const G1* __restr
 }
 // window sums -> A = sum_w 256^w W[0][w], B' = sum_w 256^w (W[1][w] + W[2][w]) (Horner, 8 doublings per window):
 // warp 0 does A, warp 1 does B' with the cooperative point operations above; the other warps OR the per-blob error
-// flags and tree-sum the r_i y_i.
+// flags, tree-sum s = sum r_i y_i and then -- still in the shadow of the Horner chains -- form [s]G from the fixed-base table
+// (64 lookups, a 6-level tree); the partial carries B' - [s]G and ry = 0, so the final check has no fixed-base work left
+// (round 2: 0.1 ms off the serial tail; with several ranks each folds its own [s_k]G).
 // `out` may be a peer-mapped pointer into the group leader's exchange buffer (multi-GPU: the partial-sum gather is this kernel's
 // last store, over NVLink); then `flag` (same buffer) receives `epoch` after the partial, with a system-scope fence in between.
 __global__ void __launch_bounds__(256) msm_combine_kernel(const G1* __restrict__ windows, const Fr* __restrict__ ry, const uint32_t* __restrict__ status,
-                                                          int n, Partial* __restrict__ out, uint32_t* flag, uint32_t epoch) {
+                                                          int n, const DeviceTables* __restrict__ T, Partial* __restrict__ out, uint32_t* flag, uint32_t epoch) {
     __shared__ uint32_t s_err;
     __shared__ Fr s_ry[256];
     __shared__ CoopPoint cp[3];
+    __shared__ G1 s_sg[64];
     int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     if (t == 0) s_err = 0;
     __syncthreads();
@@ -193,14 +196,26 @@ __global__ void __launch_bounds__(256) msm_combine_kernel(const G1* __restrict__
             if (h < span && h + span < kHelpers) s_ry[h] = s_ry[h].add_inl(s_ry[h + span]);
             asm volatile("bar.sync 1, %0;" ::"n"(kHelpers) : "memory");
         }
+        // [s]G: helper h < 64 takes the h-th 4-bit digit of s (normal form), then a tree over the 64 table points
+        if (h < 64) {
+            const Fr sv = s_ry[0];
+            const uint32_t d = (sv.l[h / 8] >> (4 * (h % 8))) & 15u;
+            s_sg[h] = d ? G1::from_affine(T->gen_table[h][d - 1]) : G1::identity();
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kHelpers) : "memory");
+        for (int span = 32; span >= 1; span >>= 1) {
+            if (h < span) s_sg[h] = s_sg[h].add(s_sg[h + span]);
+            asm volatile("bar.sync 1, %0;" ::"n"(kHelpers) : "memory");
+        }
     }
     __syncthreads();
-    if (warp == 1) {          // B' = set 1 + set 2
+    if (warp == 1) {          // B' = set 1 + set 2 - [s]G
         G1 q = {cp[2].v[0], cp[2].v[1], cp[2].v[2]};
         coop_add(&cp[1], q, lane);
+        coop_add(&cp[1], s_sg[0].neg(), lane);
     }
     if (warp < 2 && lane == 0) { G1 r = {cp[warp].v[0], cp[warp].v[1], cp[warp].v[2]}; if (warp == 1) out->b = r; else out->a = r; }
-    if (t == 0) { out->ry = s_ry[0]; out->err = s_err; }
+    if (t == 0) { out->ry = Fr::zero(); out->err = s_err; }
     if (flag) {
         __threadfence_system();
         __syncthreads();

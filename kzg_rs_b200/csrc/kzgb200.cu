@@ -403,7 +403,7 @@ int launch_lincomb(kzgb200_ctx* ctx, size_t offset, Partial* d_out, bool wait_su
     phase_begin(ctx, kPhReduce, ctx->stream);
     msm_window_kernel<<<kMsmSets * kWindows, kWinLanes, kTailPadSmem, ctx->stream>>>(ctx->d_buckets, ctx->d_windows);
     if (wait_subgroup) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_parse, 0));    // combine ORs the per-blob error flags
-    msm_combine_kernel<<<1, 256, kTailPadSmem, ctx->stream>>>(ctx->d_windows, ctx->d_ry, ctx->d_status, n, d_out, d_flag, epoch);
+    msm_combine_kernel<<<1, 256, kTailPadSmem, ctx->stream>>>(ctx->d_windows, ctx->d_ry, ctx->d_status, n, ctx->tables, d_out, d_flag, epoch);
     phase_end(ctx, kPhReduce, ctx->stream);
     CK(cudaGetLastError());
     return KZGB200_OK;
@@ -921,6 +921,12 @@ extern "C" int kzgb200_debug_final_ticks(kzgb200_ctx* ctx, long long* out14) {
     std::lock_guard<std::mutex> g(ctx->lock);
     DeviceGuard dev(ctx->device);
     CK(cudaMemcpy(out14, ctx->d_scratch + 128, 112, cudaMemcpyDeviceToHost));
+    return KZGB200_OK;
+}
+extern "C" int kzgb200_set_slab_tail(kzgb200_ctx* ctx, int on) {
+    if (!ctx) return KZGB200_BAD_ARGS;
+    std::lock_guard<std::mutex> g(ctx->lock);
+    ctx->slab_tail = on != 0;
     return KZGB200_OK;
 }
 extern "C" int kzgb200_debug_engine_selftest(kzgb200_ctx* ctx, uint32_t seed, int rounds, uint32_t* mismatches32, int* n_programs) {

@@ -74,6 +74,7 @@ extern "C" int kzgb200_pipeline_create(kzgb200_pipeline** out, int device, const
     for (int i = 0; i < depth; i++) {
         kzgb200_ctx* c = nullptr;
         int rc = kzgb200_create(&c, device, g2_points, g2_points_len);
+        if (rc == KZGB200_OK && depth > 1) kzgb200_set_slab_tail(c, 0);     // the next call's copies already hide this call's tail
         if (rc != KZGB200_OK) {
             for (kzgb200_ctx* x : p->ctx) kzgb200_destroy(x);
             delete p;

@@ -18,7 +18,7 @@ namespace kzgb200 {
 constexpr int kTailSms = 8;                    // SMs kept free of deferred subgroup checks for the latency-bound tail kernels
 constexpr int kTailHogSmem = 200 * 1024;       // dynamic shared memory of a subgroup-check CTA in deferred mode (never touched)
 constexpr int kTailPadSmem = 28 * 1024;        // ... and of the tail kernels: 200 KB + 28 KB do not fit one SM
-static_assert(sizeof(FinalSmem) >= (size_t)kTailPadSmem, "the pairing kernel must not fit beside a subgroup-check CTA");
+static_assert(sizeof(FinalSmem) >= (size_t)kTailPadSmem && sizeof(PairSmem) >= (size_t)kTailPadSmem, "the final-check kernels must not fit beside a subgroup-check CTA");
 static_assert(sizeof(Partial) == KZGB200_PARTIAL_BYTES, "Partial layout is part of the ABI");
 static_assert(sizeof(ZY) == 64, "ZY layout is part of the ABI");
 

@@ -5,18 +5,18 @@
 //   * values are SIGNED 14-limb numbers (limbs 0..12 in [-1, 2^29 + 1], limb 13 signed, |v| < 2^405) and ANY representative of
 //     their residue: 2^406 = 2^25.3 p of headroom replaces the modular reduction after every sum; the bounds that make this
 //     sound are tracked statically by tools/gen_vliw.py;
-//   * ONE INSTRUCTION RUNS ON 16 LANES (one limb per lane), not on one thread.  Measured on B200 (tools/microbench/lonewarp.cu): a
-//     lone warp issues an IMAD.WIDE only every ~7 clocks however many lanes are active, so a one-thread Montgomery product (620
-//     wide multiplications) costs ~4200 clocks and a level of 36 of them leaves 32 lanes busy on two sub-partitions.  Per lane
-//     the 16-lane form needs 56 wide multiplications per dual product:
-//       MUL  dst = (a b +- c d) / 2^406 : lane j forms the row a_j * b[0..13] (+- c_j * d[0..13]); the rows are summed by columns
-//            through a per-group shared-memory scratch; two carry rounds; m = T_lo * (-p^-1) mod 2^406 and m * p the same way
-//            (constant operands as immediates); the low half of T + m p is an exact multiple of 2^406, so its carry into the
-//            high half is read off its top limb without a ripple loop;
-//       LIN  dst = sum +-(1|2) src      : lane j adds limb j of every term (32-bit multiply-adds on 16-bit halves: no wide
+//   * ONE INSTRUCTION RUNS ON MANY LANES, not on one thread.  Measured on B200 (tools/microbench/lonewarp.cu): a lone warp issues
+//     an IMAD.WIDE only every ~7 clocks however many lanes are active, so a one-thread Montgomery product (620 wide
+//     multiplications) costs ~4200 clocks and a level of 36 of them leaves 32 lanes busy on two sub-partitions.
+//       MUL  dst = (a b +- c d) / 2^406 : ONE WARP, lane k owns column k of the 28-column product: T_k = sum_s b_s a_(k-s) with b_s
+//            broadcast and a_(k-s) a shuffle-rotation of the lane-resident limbs (lanes 14..31 hold zeros: the wrap-around is the
+//            zero fill); two carry rounds; m = T_lo * (-p^-1) mod 2^406 and m * p the same way with the constants as immediates;
+//            the low half of T + m p is an exact multiple of 2^406, so its carry into the high half is read off its top limb
+//            without a ripple loop.  56 wide multiplications per lane and dual product, no shared-memory traffic but the operands;
+//       LIN  dst = sum +-(1|2) src      : 16 lanes, lane j adds limb j of every term (32-bit multiply-adds on 16-bit halves: no wide
 //            multiplication), two carry rounds; with the `reduce` flag round(v / p) p is subtracted first (float estimate from
 //            the two top columns), leaving |v| < 4 p.
-//   A 768-thread CTA runs 48 instructions at a time.
+//   A 768-thread CTA runs 24 products or 48 sums at a time.
 //
 // The sequential executors (exec_*_ref, host + device) are the specification of the two instructions: the CPU unit test runs the
 // pairing with them (tools/hosttest/vliw29_host.cu), the GPU unit test compares the 16-lane forms with them limb for limb.
@@ -38,12 +38,10 @@ struct Tables {
     const Program* prog;
 };
 constexpr int kGroupLanes = 16;
-constexpr int kScratchWords = 14 * 28 + 4;        // 64-bit words per group: rows[14][28] (+ pad for the idle lanes' reads)
 struct Lanes {
     int tid, n;                   // this thread's index and the number of cooperating threads (host: 0, 1)
     Tables tab;
     long long* ticks = nullptr;   // optional: per-section clock64() stamps (profiling aid)
-    long long* scratch = nullptr; // device: kScratchWords 64-bit words per 16-lane group, zero-initialised
     const int32_t* p29s = nullptr;   // device: limbs of p, one per lane, in shared memory
     KZG_HD void tick(int i) const {
 #ifdef __CUDA_ARCH__
@@ -173,100 +171,87 @@ __device__ __forceinline__ int32_t carry_top(int64_t t, int lane) {
     l = top ? l : (l & kM);
     return l + up(c, 1, lane);
 }
-// The same for the LOW half of a 28-column number: all 14 lanes carry out; c14 / c15 = what moves into columns 14 and 15
-// (the same values on every lane of the group)
-__device__ __forceinline__ int32_t carry_low(int64_t t, int lane, int64_t& c14, int64_t& c15) {
-    const bool idle = lane >= 14;
-    int32_t low = idle ? 0 : ((int32_t)t & kM), cmid = idle ? 0 : ((int32_t)(t >> 29) & kM), chi = idle ? 0 : (int32_t)(t >> 58);
-    int32_t l = low + up(cmid, 1, lane) + up(chi, 2, lane);
-    const int32_t cm13 = from(cmid, 13), ch12 = from(chi, 12), ch13 = from(chi, 13);
-    int32_t c = idle ? 0 : (l >> 29);
-    l = (l & kM) + up(c, 1, lane);
-    if (idle) l = 0;
-    c14 = (int64_t)cm13 + ch12 + from(c, 13);
-    c15 = ch13;
+// ---- MUL on one warp: lane k owns column k of the 28-column product (lanes 28..31 idle) -----------------------------------
+// T_k = sum_s b_s a_(k-s): b_s is the same for every lane (broadcast load), a_(k-s) is lane k-s's limb -- a rotation of the lane-
+// resident operand by s, one shuffle, with lanes 14..31 holding zeros so that the wrap-around brings the zero fill.  No shared-
+// memory traffic beyond the operand loads, no lo/hi bookkeeping; m = T_lo (-p^-1) mod 2^406 and m p use the same rotation with the
+// constants as immediates.  (Round 2 first ran a MUL on 16 lanes with the rows summed by columns through a shared-memory
+// scratch: 12.5 KB of traffic per product made a 36-product level wait ~3500 clocks for the SM's shared-memory port.)
+__device__ __forceinline__ int64_t mulw(int32_t a, int32_t b) { uint64_t r = 0; f29::madw_s(r, a, b); return (int64_t)r; }
+__device__ __forceinline__ int32_t up32(int32_t v, int d, int k) { int32_t r = __shfl_up_sync(kFull, v, d); return k < d ? 0 : r; }
+__device__ __forceinline__ int32_t rot(int32_t v, int k, int s) { return __shfl_sync(kFull, v, (k - s) & 31); }
+// two carry rounds over lanes 0..nlow-1 (all of them carry out); the lanes above receive the outgoing carries into their 64-bit
+// column t.  Returns the limb (lanes < nlow; 0 above).
+__device__ __forceinline__ int32_t carry_split(int64_t& t, int k, int nlow) {
+    const bool lowlane = k < nlow;
+    const int32_t low = lowlane ? ((int32_t)t & kM) : 0, cmid = lowlane ? ((int32_t)(t >> 29) & kM) : 0, chi = lowlane ? (int32_t)(t >> 58) : 0;
+    const int32_t u1 = up32(cmid, 1, k), u2 = up32(chi, 2, k);
+    int32_t l = low + u1 + u2;
+    if (!lowlane) t += (int64_t)u1 + (int64_t)u2;
+    const int32_t c = lowlane ? (l >> 29) : 0;
+    const int32_t u = up32(c, 1, k);
+    l = lowlane ? ((l & kM) + u) : 0;
+    if (!lowlane) t += (int64_t)u;
     return l;
 }
-// column sums of the 14 rows a group left in its scratch: rows[j][j + i] = row_j[i]; the other entries of a row stay zero
-__device__ __forceinline__ void store_rows(long long* S, const int64_t* row, int lane) {
-    if (lane < 14) {
-#pragma unroll
-        for (int i = 0; i < 14; i++) S[lane * 28 + lane + i] = row[i];
-    }
-    __syncwarp();
+// two carry rounds over the 28 columns of lanes 0..27, lane 27 keeping everything above (the true top limb fits 32 bits)
+__device__ __forceinline__ int32_t carry_full(int64_t t, int k) {
+    const bool top = k >= 27;
+    const int64_t c64 = t >> 29;
+    const int32_t low = top ? (int32_t)t : ((int32_t)t & kM);
+    const int32_t cmid = top ? 0 : (k == 26 ? (int32_t)c64 : ((int32_t)c64 & kM));
+    const int32_t chi = (top || k == 26) ? 0 : (int32_t)(t >> 58);
+    int32_t l = low + up32(cmid, 1, k) + up32(chi, 2, k);
+    const int32_t c = top ? 0 : (l >> 29);
+    l = top ? l : (l & kM);
+    return l + up32(c, 1, k);
 }
-// (Reading only the one entry per row that lies inside the row -- predicated on j <= lane -- was measured: the selects cost more
-// issue slots than the saved shared-memory traffic gives back, 2.05 -> 2.3 us per MUL level.)
-__device__ __forceinline__ int64_t column_sum(const long long* S, int col) {
-    int64_t s = 0;
-#pragma unroll
-    for (int j = 0; j < 14; j++) s += S[j * 28 + col];
-    return s;
-}
-__device__ __forceinline__ int64_t mulw(int32_t a, int32_t b) { uint64_t r = 0; f29::madw_s(r, a, b); return (int64_t)r; }
-
-__device__ __forceinline__ void exec_mul16(F29* regs, const uint32_t* ins, bool active, long long* S, int lane) {
+__device__ __forceinline__ void exec_mul32(F29* regs, const uint32_t* ins, int k) {
     const uint32_t w0 = ins[0], w1 = ins[1], w2 = ins[2];
     const bool dual = (w2 >> 16) & 1u, neg = (w2 >> 17) & 1u;
-    const int32_t* A = reinterpret_cast<const int32_t*>(regs[w0 >> 16].l);
-    const int4* B = reinterpret_cast<const int4*>(regs[w1 & 0xffffu].l);
-    int64_t row[14];
+    uint64_t acc = 0;
     {
-        const int32_t aj = A[lane];
+        const int32_t av = k < 16 ? reinterpret_cast<const int32_t*>(regs[w0 >> 16].l)[k] : 0;      // limbs 14, 15 are zero padding
+        const int4* B = reinterpret_cast<const int4*>(regs[w1 & 0xffffu].l);
         const int4 b0 = B[0], b1 = B[1], b2 = B[2], b3 = B[3];
         const int32_t bb[14] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y};
 #pragma unroll
-        for (int i = 0; i < 14; i++) row[i] = mulw(aj, bb[i]);
+        for (int s = 0; s < 14; s++) f29::madw_s(acc, rot(av, k, s), bb[s]);
     }
     if (dual) {
-        const int32_t* C = reinterpret_cast<const int32_t*>(regs[w1 >> 16].l);
+        int32_t cv = k < 16 ? reinterpret_cast<const int32_t*>(regs[w1 >> 16].l)[k] : 0;
+        if (neg) cv = -cv;
         const int4* D = reinterpret_cast<const int4*>(regs[w2 & 0xffffu].l);
-        const int32_t cj = neg ? -C[lane] : C[lane];
         const int4 d0 = D[0], d1 = D[1], d2 = D[2], d3 = D[3];
         const int32_t dd[14] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, d2.x, d2.y, d2.z, d2.w, d3.x, d3.y};
 #pragma unroll
-        for (int i = 0; i < 14; i++) { uint64_t u = (uint64_t)row[i]; f29::madw_s(u, cj, dd[i]); row[i] = (int64_t)u; }
+        for (int s = 0; s < 14; s++) f29::madw_s(acc, rot(cv, k, s), dd[s]);
     }
-    // T = a b +- c d by columns: lane k holds column k (lo) and column k + 14 (hi)
-    store_rows(S, row, lane);
-    int64_t lo = column_sum(S, lane), hi = column_sum(S, lane + 14);
-    if (lane >= 14) { lo = 0; hi = 0; }
-    __syncwarp();
-    int64_t c14, c15;
-    const int32_t tl = carry_low(lo, lane, c14, c15);
-    if (lane == 0) hi += c14;
-    if (lane == 1) hi += c15;
-    // m = T_lo * (-p^-1) mod 2^406 (low columns only)
+    // low half: limbs for m; its carries move into columns 14, 15
+    int64_t hi = (int64_t)acc;
+    const int32_t tl = carry_split(hi, k, 14);
+    // m = T_lo * (-p^-1) mod 2^406
+    uint64_t mc = 0;
     {
         constexpr uint32_t pinv[14] = KZG29_PINV_FULL;
 #pragma unroll
-        for (int i = 0; i < 14; i++) row[i] = mulw(tl, (int32_t)pinv[i]);
+        for (int s = 0; s < 14; s++) f29::madw_s(mc, rot(tl, k, s), (int32_t)pinv[s]);
     }
-    store_rows(S, row, lane);
-    int64_t mc = column_sum(S, lane);
-    if (lane >= 14) mc = 0;
-    __syncwarp();
-    int64_t d14, d15;
-    int32_t m = carry_low(mc, lane, d14, d15);         // carries beyond limb 13 are multiples of 2^406: dropped
-    if (lane == 13) m &= kM;
-    // T + m p
+    int64_t mcol = k < 14 ? (int64_t)mc : 0;         // columns beyond 13 are multiples of 2^406: dropped
+    int32_t m = carry_split(mcol, k, 14);
+    if (k == 13) m &= kM;
+    // T + m p: the low half becomes an exact multiple of 2^406 (-2^406, 0 or 2^406 after the carry rounds, told apart by limb 13)
+    uint64_t mp = 0;
     {
         constexpr uint32_t pp[14] = KZG29_P;
 #pragma unroll
-        for (int i = 0; i < 14; i++) row[i] = mulw(m, (int32_t)pp[i]);
+        for (int s = 0; s < 14; s++) f29::madw_s(mp, rot(m, k, s), (int32_t)pp[s]);
     }
-    store_rows(S, row, lane);
-    int64_t lo2 = column_sum(S, lane), hi2 = column_sum(S, lane + 14);
-    if (lane >= 14) { lo2 = 0; hi2 = 0; }
-    __syncwarp();
-    // the low half is an exact multiple of 2^406: after the carry rounds it is -2^406, 0 or 2^406, told apart by its top limb
-    const int32_t zl = carry_low((int64_t)tl + lo2, lane, c14, c15);
-    const int32_t z13 = from(zl, 13);
-    hi += hi2;
-    if (lane == 0) hi += c14 + (int64_t)((z13 + (1 << 28)) >> 29);
-    if (lane == 1) hi += c15;
-    const int32_t r = carry_top(hi, lane);
-    if (active) reinterpret_cast<int32_t*>(regs[w0 & 0xffffu].l)[lane] = r;       // lanes 14, 15 write the zero padding
+    const int64_t tot = (k < 14 ? (int64_t)tl : hi) + (int64_t)mp;
+    int32_t r = carry_full(tot, k);
+    const int32_t z13 = __shfl_sync(kFull, r, 13);
+    if (k == 14) r += (z13 + (1 << 28)) >> 29;
+    if (k >= 14 && k < 30) reinterpret_cast<int32_t*>(regs[w0 & 0xffffu].l)[k - 14] = k < 28 ? r : 0;   // lanes 28, 29: the zero padding
 }
 __device__ __forceinline__ void exec_lin16(F29* regs, const uint32_t* ins, const uint32_t* terms, bool active, const int32_t* p29s, int lane) {
     // limb sums on 16-bit halves (48 units of 2^29 overflow 32 bits): two 32-bit multiply-adds per term, no wide multiplication
@@ -283,7 +268,7 @@ __device__ __forceinline__ void exec_lin16(F29* regs, const uint32_t* ins, const
         sh += (v >> 16) * coef;
     }
     int64_t t = (int64_t)sl + ((int64_t)sh << 16);
-    {   // the shuffles are outside the flag test: the two groups of a warp may run instructions with different flags
+    if (__any_sync(kFull, ins[3] & 1u)) {   // warp-uniform test: the two groups of a warp may run instructions with different flags
         const float f = lane == 13 ? (float)t * 536870912.0f : (lane == 12 ? (float)t : 0.0f);
         const float vf = __shfl_sync(kFull, f, 13, kGroupLanes) + __shfl_sync(kFull, f, 12, kGroupLanes);
         if (ins[3] & 1u) {
@@ -305,15 +290,20 @@ KZG_HD void run(int prog, F29* regs, const Lanes& L) {
         const Level lev = L.tab.level[lv];
 #ifdef __CUDA_ARCH__
         long long c0 = L.ticks ? clock64() : 0;
-        const int g = L.tid >> 4, ng = L.n >> 4, lane = L.tid & 15;
-        long long* S = L.scratch + (size_t)g * kScratchWords;
-        for (int base = 0; base < lev.count; base += ng) {
-            const int k = base + g;
-            if (base + (g & ~1) >= lev.count) break;              // neither group of this warp has an instruction left (warp-uniform)
-            const bool active = k < lev.count;                    // an idle second group runs along: the shuffles need every lane
-            const int idx = lev.first + (active ? k : base);
-            if (lev.kind == 1) exec_mul16(regs, L.tab.mul[idx], active, S, lane);
-            else exec_lin16(regs, L.tab.lin[idx], L.tab.term, active, L.p29s, lane);
+        if (lev.kind == 1) {
+            // one product per warp; a level of more products than warps runs in balanced passes (36 on 24 warps: 18 + 18)
+            const int w = L.tid >> 5, nw = L.n >> 5;
+            const int passes = (lev.count + nw - 1) / nw, per = (lev.count + passes - 1) / passes;
+            if (w < per)
+                for (int k = w; k < lev.count; k += per) exec_mul32(regs, L.tab.mul[lev.first + k], L.tid & 31);
+        } else {
+            const int g = L.tid >> 4, ng = L.n >> 4, lane = L.tid & 15;
+            for (int base = 0; base < lev.count; base += ng) {
+                const int k = base + g;
+                if (base + (g & ~1) >= lev.count) break;              // neither group of this warp has an instruction left (warp-uniform)
+                const bool active = k < lev.count;                    // an idle second group runs along: the shuffles need every lane
+                exec_lin16(regs, L.tab.lin[lev.first + (active ? k : base)], L.tab.term, active, L.p29s, lane);
+            }
         }
         long long c1 = L.ticks ? clock64() : 0;
 #else
