@@ -209,14 +209,14 @@ __device__ __forceinline__ int32_t carry_full(int64_t t, int k) {
 __device__ __forceinline__ void exec_mul32(F29* regs, const uint32_t* ins, int k) {
     const uint32_t w0 = ins[0], w1 = ins[1], w2 = ins[2];
     const bool dual = (w2 >> 16) & 1u, neg = (w2 >> 17) & 1u;
-    uint64_t acc = 0;
+    uint64_t acc = 0, acc1 = 0;           // two accumulators: the wide multiply-adds of a column do not form one dependency chain
     {
         const int32_t av = k < 16 ? reinterpret_cast<const int32_t*>(regs[w0 >> 16].l)[k] : 0;      // limbs 14, 15 are zero padding
         const int4* B = reinterpret_cast<const int4*>(regs[w1 & 0xffffu].l);
         const int4 b0 = B[0], b1 = B[1], b2 = B[2], b3 = B[3];
         const int32_t bb[14] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y};
 #pragma unroll
-        for (int s = 0; s < 14; s++) f29::madw_s(acc, rot(av, k, s), bb[s]);
+        for (int s = 0; s < 14; s++) f29::madw_s((s & 1) ? acc1 : acc, rot(av, k, s), bb[s]);
     }
     if (dual) {
         int32_t cv = k < 16 ? reinterpret_cast<const int32_t*>(regs[w1 >> 16].l)[k] : 0;
@@ -225,29 +225,29 @@ __device__ __forceinline__ void exec_mul32(F29* regs, const uint32_t* ins, int k
         const int4 d0 = D[0], d1 = D[1], d2 = D[2], d3 = D[3];
         const int32_t dd[14] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, d2.x, d2.y, d2.z, d2.w, d3.x, d3.y};
 #pragma unroll
-        for (int s = 0; s < 14; s++) f29::madw_s(acc, rot(cv, k, s), dd[s]);
+        for (int s = 0; s < 14; s++) f29::madw_s((s & 1) ? acc1 : acc, rot(cv, k, s), dd[s]);
     }
     // low half: limbs for m; its carries move into columns 14, 15
-    int64_t hi = (int64_t)acc;
+    int64_t hi = (int64_t)(acc + acc1);
     const int32_t tl = carry_split(hi, k, 14);
     // m = T_lo * (-p^-1) mod 2^406
-    uint64_t mc = 0;
+    uint64_t mc = 0, mc1 = 0;
     {
         constexpr uint32_t pinv[14] = KZG29_PINV_FULL;
 #pragma unroll
-        for (int s = 0; s < 14; s++) f29::madw_s(mc, rot(tl, k, s), (int32_t)pinv[s]);
+        for (int s = 0; s < 14; s++) f29::madw_s((s & 1) ? mc1 : mc, rot(tl, k, s), (int32_t)pinv[s]);
     }
-    int64_t mcol = k < 14 ? (int64_t)mc : 0;         // columns beyond 13 are multiples of 2^406: dropped
+    int64_t mcol = k < 14 ? (int64_t)(mc + mc1) : 0;         // columns beyond 13 are multiples of 2^406: dropped
     int32_t m = carry_split(mcol, k, 14);
     if (k == 13) m &= kM;
     // T + m p: the low half becomes an exact multiple of 2^406 (-2^406, 0 or 2^406 after the carry rounds, told apart by limb 13)
-    uint64_t mp = 0;
+    uint64_t mp = 0, mp1 = 0;
     {
         constexpr uint32_t pp[14] = KZG29_P;
 #pragma unroll
-        for (int s = 0; s < 14; s++) f29::madw_s(mp, rot(m, k, s), (int32_t)pp[s]);
+        for (int s = 0; s < 14; s++) f29::madw_s((s & 1) ? mp1 : mp, rot(m, k, s), (int32_t)pp[s]);
     }
-    const int64_t tot = (k < 14 ? (int64_t)tl : hi) + (int64_t)mp;
+    const int64_t tot = (k < 14 ? (int64_t)tl : hi) + (int64_t)(mp + mp1);
     int32_t r = carry_full(tot, k);
     const int32_t z13 = __shfl_sync(kFull, r, 13);
     if (k == 14) r += (z13 + (1 << 28)) >> 29;
