@@ -234,10 +234,12 @@ __global__ void __launch_bounds__(64) challenge_ws_kernel(const uint8_t* __restr
 void launch_challenge(int stages, cudaStream_t st, const uint8_t* blobs, const uint8_t* commitments, int n, Fr* z_mont, ZY* zy, Fr* zpow,
                       const uint8_t* slab_flags) {
     unsigned grid = (unsigned)((n + kShaThreads - 1) / kShaThreads);
-    // The warp-specialised form has the shorter chain per blob but loses when every sub-partition already holds a chain (16384
-    // blobs: 3.98 against 3.38 ms in the step); it is used where latency is all that matters -- the slab-wise last host chunk --
-    // and everywhere with kzgb200_ctx::sha_stages = -1 (KZGB200_SHA_STAGES=-1).
-    if (stages < 0 || (slab_flags && stages != 4)) {
+    // The warp-specialised form has the shorter chain per blob (2.18 against 2.71 ms for a 1024-blob launch) but needs two warps per
+    // 32 blobs: once chains alone fill the 592 sub-partitions it loses (16384 blobs: 3.49 against 2.91 ms).  It is used where the
+    // launch leaves sub-partitions free -- up to kWsMaxBlobs blobs -- and for the slab-wise last host chunk; stages = -1 forces it,
+    // stages = 4 keeps the one-warp form everywhere.
+    constexpr int kWsMaxBlobs = 8192;
+    if (stages < 0 || (stages != 4 && (slab_flags || n <= kWsMaxBlobs))) {
         unsigned g2 = (unsigned)((n + 31) / 32);
         if (slab_flags) challenge_ws_kernel<true><<<g2, 64, 0, st>>>(blobs, commitments, n, z_mont, zy, zpow, slab_flags);
         else challenge_ws_kernel<false><<<g2, 64, 0, st>>>(blobs, commitments, n, z_mont, zy, zpow, nullptr);
