@@ -117,107 +117,125 @@ __global__ void __launch_bounds__(kShaThreads) challenge_kernel(const uint8_t* _
 constexpr int kWsStride = 68;      // words per thread in a tile: 16-byte aligned rows, conflict-free 128-bit accesses
 __device__ __forceinline__ void ws_bar_sync(int id) { asm volatile("barrier.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void ws_bar_arrive(int id) { asm volatile("barrier.arrive %0, 64;" ::"r"(id) : "memory"); }
-template <bool kWait>
-__global__ void __launch_bounds__(64) challenge_ws_kernel(const uint8_t* __restrict__ blobs, const uint8_t* __restrict__ commitments, int n,
-                                                          Fr* __restrict__ z_mont, ZY* __restrict__ zy, Fr* __restrict__ zpow,
-                                                          const volatile uint8_t* flags) {
+// kConsumers = 2 (one producer warp feeding two consumer warps, 768 instead of 1024 warps for 16384 blobs) was measured: the producer
+// becomes the bottleneck, 5.19 against 3.36 ms in the step; only kConsumers = 1 is instantiated.
+template <bool kWait, int kConsumers>
+__global__ void __launch_bounds__(32 * (kConsumers + 1)) challenge_ws_kernel(const uint8_t* __restrict__ blobs, const uint8_t* __restrict__ commitments, int n,
+                                                                             Fr* __restrict__ z_mont, ZY* __restrict__ zy, Fr* __restrict__ zpow,
+                                                                             const volatile uint8_t* flags) {
     constexpr int kStages = 8;
-    __shared__ uint4 ring[kStages][4][32];
-    __shared__ __align__(16) uint32_t tile[2][32][kWsStride];
+    extern __shared__ __align__(16) unsigned char ws_smem[];       // dynamic: two consumers need 66 KB
+    uint4 (*ring)[kStages][4][32] = reinterpret_cast<uint4 (*)[kStages][4][32]>(ws_smem);
+    uint32_t (*tile)[2][32][kWsStride] = reinterpret_cast<uint32_t (*)[2][32][kWsStride]>(ws_smem + sizeof(uint4) * kConsumers * kStages * 4 * 32);
     const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
-    int i = blockIdx.x * 32 + lane;
-    if (i >= n) i = n - 1;                                   // the tail CTA: surplus lanes redo the last blob (no divergent barriers)
-    const bool store = blockIdx.x * 32 + lane < n;
-    const uint4* bp = reinterpret_cast<const uint4*>(blobs + (size_t)i * kBytesPerBlob);
-    if (role == 1) {
-        // ---- producer: blocks 0 .. 2049 -> W + K tiles
-        const uint32_t* cp = reinterpret_cast<const uint32_t*>(commitments + (size_t)i * 48);
+    if (role == kConsumers) {
+        // ---- producer: blocks 0 .. 2049 of kConsumers x 32 blobs -> W tiles (the consumers add K[t] as an immediate)
+        const uint4* bp[kConsumers];
+        const uint32_t* cp[kConsumers];
+#pragma unroll
+        for (int c = 0; c < kConsumers; c++) {
+            int i = (blockIdx.x * kConsumers + c) * 32 + lane;
+            if (i >= n) i = n - 1;
+            bp[c] = reinterpret_cast<const uint4*>(blobs + (size_t)i * kBytesPerBlob);
+            cp[c] = reinterpret_cast<const uint32_t*>(commitments + (size_t)i * 48);
+        }
         int have = 1;
         for (int k = 1; k < kStages; k++) {
 #pragma unroll
-            for (int q = 0; q < 4; q++) sha_cp_async16(&ring[k % kStages][q][lane], bp + (4 * k - 2) + q);
+            for (int c = 0; c < kConsumers; c++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) sha_cp_async16(&ring[c][k % kStages][q][lane], bp[c] + (4 * k - 2) + q);
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
 #pragma unroll 1
         for (int b = 0; b < 2050; b++) {
-            uint32_t w[16];
-            if (b == 0) {
-                w[0] = 0x4653424c; w[1] = 0x4f425645; w[2] = 0x52494659; w[3] = 0x5f56315f;   // "FSBLOBVERIFY_V1_"
-                w[4] = 0; w[5] = 0; w[6] = 0; w[7] = 4096;
-                uint4 a = __ldg(bp), c = __ldg(bp + 1);
-                w[8] = sha_bswap(a.x); w[9] = sha_bswap(a.y); w[10] = sha_bswap(a.z); w[11] = sha_bswap(a.w);
-                w[12] = sha_bswap(c.x); w[13] = sha_bswap(c.y); w[14] = sha_bswap(c.z); w[15] = sha_bswap(c.w);
-            } else if (b < 2048) {
-                asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 2) : "memory");
-                uint4 (*sg)[32] = ring[b % kStages];
-                uint4 a = sg[0][lane], bb = sg[1][lane], c = sg[2][lane], d = sg[3][lane];
-                if (b + kStages - 1 < 2048) {
-                    if (kWait && (b + kStages - 1) / kSlabBlocks >= have) wait_slab(flags, have++);
-                    const uint4* p = bp + (4 * (b + kStages - 1) - 2);
-#pragma unroll
-                    for (int q = 0; q < 4; q++) sha_cp_async16(&ring[(b + kStages - 1) % kStages][q][lane], p + q);
-                }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                w[0] = sha_bswap(a.x); w[1] = sha_bswap(a.y); w[2] = sha_bswap(a.z); w[3] = sha_bswap(a.w);
-                w[4] = sha_bswap(bb.x); w[5] = sha_bswap(bb.y); w[6] = sha_bswap(bb.z); w[7] = sha_bswap(bb.w);
-                w[8] = sha_bswap(c.x); w[9] = sha_bswap(c.y); w[10] = sha_bswap(c.z); w[11] = sha_bswap(c.w);
-                w[12] = sha_bswap(d.x); w[13] = sha_bswap(d.y); w[14] = sha_bswap(d.z); w[15] = sha_bswap(d.w);
-            } else if (b == 2048) {
-                if (kWait) wait_slab(flags, kSlabs - 1);
-                uint4 a = __ldg(bp + 8190), c = __ldg(bp + 8191);
-                w[0] = sha_bswap(a.x); w[1] = sha_bswap(a.y); w[2] = sha_bswap(a.z); w[3] = sha_bswap(a.w);
-                w[4] = sha_bswap(c.x); w[5] = sha_bswap(c.y); w[6] = sha_bswap(c.z); w[7] = sha_bswap(c.w);
-                for (int j = 0; j < 8; j++) w[8 + j] = sha_bswap(__ldg(cp + j));
-            } else {
-                for (int j = 0; j < 4; j++) w[j] = sha_bswap(__ldg(cp + 8 + j));
-                w[4] = 0x80000000u;
-                for (int j = 5; j < 15; j++) w[j] = 0;
-                w[15] = 131152u * 8u;
+            if (b >= 1 && b < 2048) {
+                asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 2) : "memory");      // block b of every consumer has landed
+                if (kWait && b + kStages - 1 < 2048 && (b + kStages - 1) / kSlabBlocks >= have) wait_slab(flags, have++);
             }
-            const int buf = b & 1;
-            if (b >= 2) ws_bar_sync(3 + buf);                 // the consumer has copied tile `buf` (block b - 2) into registers
-            uint32_t* out = tile[buf][lane];
+            if (kWait && b == 2048) wait_slab(flags, kSlabs - 1);
 #pragma unroll
-            for (int t = 0; t < 64; t += 4) {
-                uint32_t v[4];
+            for (int c = 0; c < kConsumers; c++) {
+                uint32_t w[16];
+                if (b == 0) {
+                    w[0] = 0x4653424c; w[1] = 0x4f425645; w[2] = 0x52494659; w[3] = 0x5f56315f;   // "FSBLOBVERIFY_V1_"
+                    w[4] = 0; w[5] = 0; w[6] = 0; w[7] = 4096;
+                    uint4 a = __ldg(bp[c]), e = __ldg(bp[c] + 1);
+                    w[8] = sha_bswap(a.x); w[9] = sha_bswap(a.y); w[10] = sha_bswap(a.z); w[11] = sha_bswap(a.w);
+                    w[12] = sha_bswap(e.x); w[13] = sha_bswap(e.y); w[14] = sha_bswap(e.z); w[15] = sha_bswap(e.w);
+                } else if (b < 2048) {
+                    uint4 (*sg)[32] = ring[c][b % kStages];
+                    uint4 a = sg[0][lane], bb = sg[1][lane], e = sg[2][lane], d = sg[3][lane];
+                    if (b + kStages - 1 < 2048) {
+                        const uint4* p = bp[c] + (4 * (b + kStages - 1) - 2);
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int x = t + u;
-                    if (x >= 16) {
-                        uint32_t w15 = w[(x + 1) & 15], w2 = w[(x + 14) & 15];
-                        uint32_t s0 = sha_rotr(w15, 7) ^ sha_rotr(w15, 18) ^ (w15 >> 3);
-                        uint32_t s1 = sha_rotr(w2, 17) ^ sha_rotr(w2, 19) ^ (w2 >> 10);
-                        w[x & 15] = w[x & 15] + s0 + w[(x + 9) & 15] + s1;
+                        for (int q = 0; q < 4; q++) sha_cp_async16(&ring[c][(b + kStages - 1) % kStages][q][lane], p + q);
                     }
-                    v[u] = w[x & 15] + sha_k(x);
+                    w[0] = sha_bswap(a.x); w[1] = sha_bswap(a.y); w[2] = sha_bswap(a.z); w[3] = sha_bswap(a.w);
+                    w[4] = sha_bswap(bb.x); w[5] = sha_bswap(bb.y); w[6] = sha_bswap(bb.z); w[7] = sha_bswap(bb.w);
+                    w[8] = sha_bswap(e.x); w[9] = sha_bswap(e.y); w[10] = sha_bswap(e.z); w[11] = sha_bswap(e.w);
+                    w[12] = sha_bswap(d.x); w[13] = sha_bswap(d.y); w[14] = sha_bswap(d.z); w[15] = sha_bswap(d.w);
+                } else if (b == 2048) {
+                    uint4 a = __ldg(bp[c] + 8190), e = __ldg(bp[c] + 8191);
+                    w[0] = sha_bswap(a.x); w[1] = sha_bswap(a.y); w[2] = sha_bswap(a.z); w[3] = sha_bswap(a.w);
+                    w[4] = sha_bswap(e.x); w[5] = sha_bswap(e.y); w[6] = sha_bswap(e.z); w[7] = sha_bswap(e.w);
+                    for (int j = 0; j < 8; j++) w[8 + j] = sha_bswap(__ldg(cp[c] + j));
+                } else {
+                    for (int j = 0; j < 4; j++) w[j] = sha_bswap(__ldg(cp[c] + 8 + j));
+                    w[4] = 0x80000000u;
+                    for (int j = 5; j < 15; j++) w[j] = 0;
+                    w[15] = 131152u * 8u;
                 }
-                *reinterpret_cast<uint4*>(out + t) = make_uint4(v[0], v[1], v[2], v[3]);
+                const int buf = b & 1;
+                if (b >= 2) ws_bar_sync(3 + 4 * c + buf);         // consumer c has copied tile `buf` (block b - 2) into registers
+                uint32_t* out = tile[c][buf][lane];
+#pragma unroll
+                for (int t = 0; t < 64; t += 4) {
+                    uint32_t v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int x = t + u;
+                        if (x >= 16) {
+                            uint32_t w15 = w[(x + 1) & 15], w2 = w[(x + 14) & 15];
+                            uint32_t s0 = sha_rotr(w15, 7) ^ sha_rotr(w15, 18) ^ (w15 >> 3);
+                            uint32_t s1 = sha_rotr(w2, 17) ^ sha_rotr(w2, 19) ^ (w2 >> 10);
+                            w[x & 15] = w[x & 15] + s0 + w[(x + 9) & 15] + s1;
+                        }
+                        v[u] = w[x & 15];
+                    }
+                    *reinterpret_cast<uint4*>(out + t) = make_uint4(v[0], v[1], v[2], v[3]);
+                }
+                __threadfence_block();
+                ws_bar_arrive(1 + 4 * c + buf);                   // tile `buf` of consumer c is full
             }
-            __threadfence_block();
-            ws_bar_arrive(1 + buf);                           // tile `buf` is full
+            if (b >= 1 && b < 2048) asm volatile("cp.async.commit_group;" ::: "memory");
         }
         return;
     }
-    // ---- consumer: the 64 rounds of every block
+    // ---- consumer `role`: the 64 rounds of every block of its 32 blobs
+    const int c = role;
+    int i = (blockIdx.x * kConsumers + c) * 32 + lane;
+    const bool store = i < n;                                 // the tail CTA: surplus lanes redo the last blob (no divergent barriers)
+    if (i >= n) i = n - 1;
     uint32_t st[8];
     sha256_init(st);
 #pragma unroll 1
     for (int b = 0; b < 2050; b++) {
         const int buf = b & 1;
-        ws_bar_sync(1 + buf);
+        ws_bar_sync(1 + 4 * c + buf);
         uint32_t wk[64];
-        const uint4* in = reinterpret_cast<const uint4*>(tile[buf][lane]);
+        const uint4* in = reinterpret_cast<const uint4*>(tile[c][buf][lane]);
 #pragma unroll
         for (int t = 0; t < 16; t++) { uint4 v = in[t]; wk[4 * t] = v.x; wk[4 * t + 1] = v.y; wk[4 * t + 2] = v.z; wk[4 * t + 3] = v.w; }
-        if (b + 2 < 2050) ws_bar_arrive(3 + buf);             // the tile may be refilled (block b + 2)
-        uint32_t a = st[0], bq = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+        if (b + 2 < 2050) ws_bar_arrive(3 + 4 * c + buf);     // the tile may be refilled (block b + 2)
+        uint32_t a = st[0], bq = st[1], cc = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
 #pragma unroll
         for (int t = 0; t < 64; t++) {
-            uint32_t t1 = (h + wk[t]) + (sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25)) + ((e & f) ^ (~e & g));
-            uint32_t t2 = (sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22)) + ((a & bq) ^ (a & c) ^ (bq & c));
-            h = g; g = f; f = e; e = d + t1; d = c; c = bq; bq = a; a = t1 + t2;
+            uint32_t t1 = (h + wk[t] + sha_k(t)) + (sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25)) + ((e & f) ^ (~e & g));
+            uint32_t t2 = (sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22)) + ((a & bq) ^ (a & cc) ^ (bq & cc));
+            h = g; g = f; f = e; e = d + t1; d = cc; cc = bq; bq = a; a = t1 + t2;
         }
-        st[0] += a; st[1] += bq; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+        st[0] += a; st[1] += bq; st[2] += cc; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
     }
     if (!store) return;
     Fr raw;
@@ -239,10 +257,11 @@ void launch_challenge(int stages, cudaStream_t st, const uint8_t* blobs, const u
     // launch leaves sub-partitions free -- up to kWsMaxBlobs blobs -- and for the slab-wise last host chunk; stages = -1 forces it,
     // stages = 4 keeps the one-warp form everywhere.
     constexpr int kWsMaxBlobs = 8192;
+    auto ws_bytes = [](int consumers) { return (size_t)consumers * (sizeof(uint4) * 8 * 4 * 32 + sizeof(uint32_t) * 2 * 32 * kWsStride); };
     if (stages < 0 || (stages != 4 && (slab_flags || n <= kWsMaxBlobs))) {
         unsigned g2 = (unsigned)((n + 31) / 32);
-        if (slab_flags) challenge_ws_kernel<true><<<g2, 64, 0, st>>>(blobs, commitments, n, z_mont, zy, zpow, slab_flags);
-        else challenge_ws_kernel<false><<<g2, 64, 0, st>>>(blobs, commitments, n, z_mont, zy, zpow, nullptr);
+        if (slab_flags) challenge_ws_kernel<true, 1><<<g2, 64, ws_bytes(1), st>>>(blobs, commitments, n, z_mont, zy, zpow, slab_flags);
+        else challenge_ws_kernel<false, 1><<<g2, 64, ws_bytes(1), st>>>(blobs, commitments, n, z_mont, zy, zpow, nullptr);
         return;
     }
     if (slab_flags) challenge_kernel<8, true><<<grid, kShaThreads, 0, st>>>(blobs, commitments, n, z_mont, zy, zpow, 1u, slab_flags);
