@@ -50,7 +50,7 @@ constexpr int kSlice = 32, kMsmRows = kMsmSets * 2 * kWindows;   // bucket accum
 constexpr int kWinLanes = 64, kWinPer = kBuckets / kWinLanes;     // 64 lanes x 4 buckets: 48 CTAs still fit the tail's 8 SMs in one wave
 constexpr int kFinalThreads = 64;       // G1 prelude of the final check (sums, [s]G, affine conversion)
 constexpr int kPairThreads = 768;       // pairing engine: 24 warps = 24 products (one per warp) or 48 sums (16 lanes each) at a time
-constexpr int kManyThreads = 384, kManyGroups = 21;   // many_pairing_kernel: checks run in lockstep by one CTA
+constexpr int kManyThreads = 512, kManyGroups = 28;   // many_pairing_kernel: checks run in lockstep by one CTA (28 x 36 products = 1.97 x 512; 128 registers)
 constexpr int kManyWarps = 4;         // many_pairing_warp_kernel (identity inputs): one check per warp
 constexpr int kHarnessMaxDegree = 16;
 constexpr int kLagWindows = 32, kLagEntries = 255;
@@ -91,7 +91,8 @@ struct PairSmem {                        // pairing_check_kernel
 struct FinalPts { G1Affine pts[2]; uint32_t go; };
 
 constexpr int kManyStride = vliw::kTotalRegsThr * 12 + 1;     // words between the register files of consecutive groups (odd: bank skew)
-constexpr int kManySmemBytes = kManyGroups * kManyStride * 4 + (int)sizeof(vliw::SharedTables) + kManyGroups * (2 * (int)sizeof(G1Affine) + 2) + 64;
+constexpr int kManySmemBytes = kManyGroups * kManyStride * 4 + (int)sizeof(vliw::SharedTables) + vliw::kNumSharedRegs * (int)sizeof(Fp) +
+                               kManyGroups * (2 * (int)sizeof(G1Affine) + 2) + 64;
 // ---- kernels (k_*.cu) ----------------------------------------------------------------------------------------
 __global__ void setup_tables_kernel(DeviceTables* T, const uint8_t* g2_points);
 __global__ void setup_lines29_kernel(DeviceTables* T);

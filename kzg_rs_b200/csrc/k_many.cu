@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(128) many_lhs_zy_kernel(const ZY* __restrict__
 struct ManySmem {
     uint32_t regs[kManyGroups * kManyStride];     // kManyGroups register files, an odd number of words apart
     vliw::SharedTables stab;
+    Fp shared[vliw::kNumSharedRegs];               // line coefficients of the current Miller step + Frobenius constants: the same for every check
     G1Affine x[kManyGroups], np[kManyGroups];
     uint8_t ok[kManyGroups], use[kManyGroups];
 };
@@ -58,9 +59,11 @@ __global__ void __launch_bounds__(kManyThreads, 1) many_pairing_kernel(const G1A
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     ManySmem& S = *reinterpret_cast<ManySmem*>(dyn_smem);
     vliw::Tables tab = vliw::load_tables(&S.stab, threadIdx.x, blockDim.x, true);
+    vliw::remap_tables_multi(&S.stab, threadIdx.x, blockDim.x);
+    __syncthreads();
     const int t = threadIdx.x;
     vliw::Lanes L{t, kManyThreads, tab, nullptr, false};
-    L.groups = kManyGroups; L.stride = kManyStride;
+    L.groups = kManyGroups; L.stride = kManyStride; L.shared = S.shared;
     const size_t nbatch = (m + kManyGroups - 1) / kManyGroups;
     for (size_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {      // uniform trip count for the whole CTA
         if (t < kManyGroups) {

@@ -30,6 +30,8 @@ struct Lanes {
                                   // WORDS after group g-1's; an odd stride puts the same register of 32 groups on 32 different banks
                                   // (consecutive threads run the SAME instruction for consecutive groups: uniform control flow,
                                   // broadcast table reads, conflict-free register-file accesses)
+    Fp* shared = nullptr;         // multi-group form: the registers every check reads alike -- line coefficients and Frobenius constants,
+                                  // 22 values -- live ONCE here; the group files hold the rest, compacted (see remap_multi)
     KZG_HD Fp* file(Fp* regs, int g) const { return reinterpret_cast<Fp*>(reinterpret_cast<uint32_t*>(regs) + (size_t)g * stride); }
     KZG_HD void tick(int i) const {
 #ifdef __CUDA_ARCH__
@@ -65,6 +67,23 @@ struct SharedTables {
     Level level[kNumLevelMax];
     Program prog[kNumPrograms];
 };
+// Multi-group register numbering: logical registers [kRegLines, kRegP) are the shared ones (flag 0x2000 | offset), the logical
+// registers above them move down by their count.  Applied to the table copy the multi-group kernels execute from.
+constexpr int kNumSharedRegs = kRegP - kRegLines;
+constexpr uint32_t kSharedFlag = 0x2000u;
+KZG_HD uint32_t remap_multi(uint32_t idx) {
+    if (idx == 0xffffu) return idx;
+    if (idx >= (uint32_t)kRegLines && idx < (uint32_t)kRegP) return kSharedFlag | (idx - kRegLines);
+    return idx >= (uint32_t)kRegP ? idx - kNumSharedRegs : idx;
+}
+KZG_HD int compact_multi(int idx, bool multi) { return (multi && idx >= kRegP) ? idx - kNumSharedRegs : idx; }
+KZG_HD const Fp& rreg(const Fp* regs, const Fp* shared, uint32_t idx) { return (idx & kSharedFlag) ? shared[idx & 0x1fffu] : regs[idx]; }
+// in-place remap of a throughput-table copy (mul: dst + 16 slots; lin: dst; term: register bits)
+KZG_HD void remap_tables_multi(SharedTables* st, int tid, int n) {
+    for (int i = tid; i < thr::kNumMul * 17; i += n) { uint16_t& v = st->mul[i / 17][i % 17]; v = (uint16_t)remap_multi(v); }
+    for (int i = tid; i < thr::kNumLin; i += n) st->lin[i][0] = remap_multi(st->lin[i][0]);
+    for (int i = tid; i < thr::kNumTerm; i += n) { uint16_t e = st->term[i]; st->term[i] = (uint16_t)((e & 0xc000u) | remap_multi(e & 0x3fffu)); }
+}
 #ifdef __CUDACC__
 __device__ __forceinline__ Tables load_tables(SharedTables* st, int tid, int n, bool throughput = false) {
     const Tables src = throughput ? throughput_tables() : default_tables();
@@ -83,14 +102,14 @@ __device__ __forceinline__ Tables load_tables(SharedTables* st, int tid, int n, 
 // One multiplication operand = up to four registers with signs, summed by the multiplying thread itself (no LIN level, no
 // barrier): lazily, sum(pos) + #neg * p - sum(neg) < 4p, then one conditional subtraction of 2p for three or four terms, so the
 // operand is < 2p -- the Montgomery products tolerate that: a b + c d < 8 p^2 < R p (R = 2^384 = 9.8 p), result < p as usual.
-KZG_HD Fp mul_operand(const Fp* regs, const uint16_t* slot, uint32_t signs) {
-    Fp x = regs[slot[0]];                                   // the first term is always positive
+KZG_HD Fp mul_operand(const Fp* regs, const uint16_t* slot, uint32_t signs, const Fp* shared = nullptr) {
+    Fp x = rreg(regs, shared, slot[0]);                     // the first term is always positive
     if (slot[1] == 0xffff) return x;
     const Fp p = Fp::modulus();
     int n = 1;
 #pragma unroll 1
     for (int j = 1; j < 4 && slot[j] != 0xffff; j++, n++) {
-        Fp y = regs[slot[j]];
+        Fp y = rreg(regs, shared, slot[j]);
         if ((signs >> j) & 1u) { add_n<12>(x.l, x.l, p.l); sub_n<12>(x.l, x.l, y.l); }
         else add_n<12>(x.l, x.l, y.l);
     }
@@ -104,7 +123,7 @@ KZG_HD Fp mul_operand(const Fp* regs, const uint16_t* slot, uint32_t signs) {
     return x;
 }
 // ins: dst, 4 operands x 4 slots, sign bits (4 per operand), negate-second-product flag
-KZG_HD void exec_mul(Fp* regs, const uint16_t* ins, bool plain) {
+KZG_HD void exec_mul(Fp* regs, const uint16_t* ins, bool plain, const Fp* shared = nullptr) {
     if (plain) {            // latency programs: every operand is one register
         Fp a = regs[ins[1]], b = regs[ins[5]];
         if (ins[9] == 0xffff) { regs[ins[0]] = a.mul_inl(b); return; }
@@ -114,11 +133,11 @@ KZG_HD void exec_mul(Fp* regs, const uint16_t* ins, bool plain) {
         return;
     }
     const uint32_t signs = ins[17];
-    Fp a = mul_operand(regs, ins + 1, signs), b = mul_operand(regs, ins + 5, signs >> 4);
+    Fp a = mul_operand(regs, ins + 1, signs, shared), b = mul_operand(regs, ins + 5, signs >> 4, shared);
     if (ins[9] == 0xffff) {
         regs[ins[0]] = a.mul_inl(b);
     } else {
-        Fp c = mul_operand(regs, ins + 9, signs >> 8), d = mul_operand(regs, ins + 13, signs >> 12);
+        Fp c = mul_operand(regs, ins + 9, signs >> 8, shared), d = mul_operand(regs, ins + 13, signs >> 12, shared);
         if (ins[18] & 1) {                                  // - c d = (2p - c) d with 2p - c in (0, 2p]
             Fp p2, p = Fp::modulus();
             add_n<12>(p2.l, p.l, p.l);
@@ -132,7 +151,7 @@ KZG_HD void exec_mul(Fp* regs, const uint16_t* ins, bool plain) {
 // added with the sign as carry-in to ONE signed 14-limb accumulator (two's complement subtraction through the adder).
 // The signed total S in (-48p, 48p) is then made positive (D = S + 64p) and reduced once: quotient estimate from the top
 // words, one multiply-subtract, the candidates D - p, D - 2p, D - 3p side by side.
-KZG_HD void exec_lin(Fp* regs, const uint32_t* ins, const uint16_t* terms) {
+KZG_HD void exec_lin(Fp* regs, const uint32_t* ins, const uint16_t* terms, const Fp* shared = nullptr) {
     uint32_t acc[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) acc[i] = 0;
@@ -140,7 +159,7 @@ KZG_HD void exec_lin(Fp* regs, const uint32_t* ins, const uint16_t* terms) {
     const uint16_t* t = terms + ins[1];
     for (uint32_t k = 0; k < ins[2]; k++) {
         uint16_t e = t[k];
-        const Fp& v = regs[e & 0x3fff];
+        const Fp& v = rreg(regs, shared, e & 0x3fffu);
         uint32_t sh = (e >> 15) & 1u, m = (e & 0x4000) ? 0xffffffffu : 0u;
         uint32_t wv[12], prev = 0;
 #pragma unroll
@@ -202,8 +221,8 @@ KZG_HD void run(int prog, Fp* regs, const Lanes& L) {
             else { for (int k = L.tid; k < lev.count; k += L.n) exec_lin(regs, L.tab.lin[lev.first + k], L.tab.term); }
         } else {
             const int total = lev.count * L.groups;
-            if (lev.kind == 1) { for (int j = L.tid; j < total; j += L.n) { int k = j / L.groups, g = j - k * L.groups; exec_mul(L.file(regs, g), L.tab.mul[lev.first + k], L.tab.plain); } }
-            else { for (int j = L.tid; j < total; j += L.n) { int k = j / L.groups, g = j - k * L.groups; exec_lin(L.file(regs, g), L.tab.lin[lev.first + k], L.tab.term); } }
+            if (lev.kind == 1) { for (int j = L.tid; j < total; j += L.n) { int k = j / L.groups, g = j - k * L.groups; exec_mul(L.file(regs, g), L.tab.mul[lev.first + k], L.tab.plain, L.shared); } }
+            else { for (int j = L.tid; j < total; j += L.n) { int k = j / L.groups, g = j - k * L.groups; exec_lin(L.file(regs, g), L.tab.lin[lev.first + k], L.tab.term, L.shared); } }
         }
 #ifdef __CUDA_ARCH__
         long long c1 = L.ticks ? clock64() : 0;
@@ -220,6 +239,7 @@ KZG_HD void run(int prog, Fp* regs, const Lanes& L) {
 }
 // regs[dst .. dst+count) = regs[src ..)
 KZG_HD void copy_regs(Fp* regs, int dst, int src, int count, const Lanes& L) {
+    dst = compact_multi(dst, L.shared != nullptr); src = compact_multi(src, L.shared != nullptr);     // logical -> group-file numbering
     const int per = count * 12;
     for (int j = L.tid; j < per * L.groups; j += L.n) {
         int k = j / L.groups, g = j - k * L.groups;
@@ -272,9 +292,21 @@ constexpr int kMaxRegs = lat::kMaxRegs;
 constexpr int kSave0 = kMaxRegs;            // each save slot = 12 registers
 constexpr int kNumSaves = 5;
 constexpr int kTotalRegs = kMaxRegs + 12 * kNumSaves;
-constexpr int kSave0Thr = thr::kMaxRegs, kTotalRegsThr = thr::kMaxRegs + 12 * kNumSaves;   // register file of the lockstep form (throughput programs)
+// register file of the lockstep (multi-group) form, throughput programs: logical numbering up to kSave0Thr + 60 with the 22
+// shared registers (lines, constants) taken out of the group files
+constexpr int kSave0Thr = thr::kMaxRegsNoSqrLines, kTotalRegsThr = thr::kMaxRegsNoSqrLines - kNumSharedRegs + 12 * kNumSaves;
 
 KZG_HD void load_lines(Fp* regs, const LineCoeffs* c1, const LineCoeffs* c2, int k, const Lanes& L) {
+    if (L.shared) {          // multi-group form: the lines are the same for every check -- one copy
+        for (int i = L.tid; i < 12 * 12; i += L.n) {
+            int fe = i / 12, limb = i % 12, j = fe / 6, e = fe % 6;
+            const LineCoeffs* src = j == 0 ? c1 : c2;
+            const Fp2& f2 = e < 2 ? src[k].A : (e < 4 ? src[k].B : src[k].C);
+            L.shared[fe].l[limb] = (e & 1) ? f2.c1.l[limb] : f2.c0.l[limb];
+        }
+        L.sync();
+        return;
+    }
     // 6 Fp per line (A, B, C as Fp2) into regs[kRegLines + 6 j ..]
     for (int q = L.tid; q < 12 * 12 * L.groups; q += L.n) {
         int i = q / L.groups, g = q - i * L.groups;
@@ -395,12 +427,16 @@ KZG_HD bool coop_pairing_product_is_one(Fp* regs, const G1Affine& P1, const Line
 // all cooperating threads see) receives the verdicts.  regs: L.groups register files, L.stride words apart.
 KZG_HD void coop_pairing_multi(Fp* regs, const G1Affine* P1, const LineCoeffs* c1, const G1Affine* P2, const LineCoeffs* c2, const Lanes& L,
                                uint8_t* ok) {
-    for (int gi = L.tid; gi < L.groups; gi += L.n) {
-        Fp* r = L.file(regs, gi);
+    // L.shared must be set: the Frobenius constants (and, per Miller step, the line coefficients) live once for all groups
+    if (L.tid == 0) {
         const uint32_t g[10][12] = {KZG_FP_FROB6_1_C0_M, KZG_FP_FROB6_1_C1_M, KZG_FP_FROB6_2_C0_M, KZG_FP_FROB6_2_C1_M, KZG_FP_FROB6_3_C0_M,
                                     KZG_FP_FROB6_3_C1_M, KZG_FP_FROB6_4_C0_M, KZG_FP_FROB6_4_C1_M, KZG_FP_FROB6_5_C0_M, KZG_FP_FROB6_5_C1_M};
-        for (int i = 0; i < 10; i++) r[kRegConst + i] = fp_const(g[i]);
-        r[kRegP] = P1[gi].x; r[kRegP + 1] = P1[gi].y; r[kRegP + 2] = P2[gi].x; r[kRegP + 3] = P2[gi].y;
+        for (int i = 0; i < 10; i++) L.shared[kRegConst - kRegLines + i] = fp_const(g[i]);
+    }
+    const int rp = compact_multi(kRegP, true);
+    for (int gi = L.tid; gi < L.groups; gi += L.n) {
+        Fp* r = L.file(regs, gi);
+        r[rp] = P1[gi].x; r[rp + 1] = P1[gi].y; r[rp + 2] = P2[gi].x; r[rp + 3] = P2[gi].y;
         for (int i = 0; i < 12; i++) r[kRegF + i] = Fp::zero();
         r[kRegF] = Fp::one();
     }
@@ -408,7 +444,8 @@ KZG_HD void coop_pairing_multi(Fp* regs, const G1Affine* P1, const LineCoeffs* c
     int k = 0;
     for (int bit = 62; bit >= 0; bit--) {
         load_lines(regs, c1, c2, k++, L);
-        run(kProg_sqr_lines, regs, L);
+        run(kProg_f12_sqr, regs, L);        // (sqr_lines in one program needs 18 registers more per group)
+        run(kProg_lines, regs, L);
         run(kProg_f12_mul, regs, L);
         if ((KZG_BLS_X_ABS >> bit) & 1) {
             load_lines(regs, c1, c2, k++, L);

@@ -346,6 +346,52 @@ def mul_srcs(ops):
     return [r for o in ops for r, _ in o]
 
 
+def reallocate(prog, n_inputs):
+    """Register reuse.  The builders number their temporaries in SSA fashion (a fresh register per instruction); here they are
+    packed by a linear scan over the levels: a temporary's register is free again from the level AFTER its last read (a level may
+    not write a register that another instruction of the same level still reads).  The register file of a check shrinks, so more
+    checks fit one CTA's shared memory (many-tuple kernel) -- registers below n_inputs (inputs / outputs) keep their numbers."""
+    srcs_of = lambda kind, pay: mul_srcs(pay[0]) if kind == "MUL" else [r for r, _, _ in pay]
+    last_use = {}
+    for lv, (kind, ins) in enumerate(prog):
+        for _, dst, pay in ins:
+            for r in srcs_of(kind, pay):
+                last_use[r] = lv
+    phys, free, next_phys, busy_until = {}, [], n_inputs, {}
+    out = []
+    for lv, (kind, ins) in enumerate(prog):
+        for r, until in list(busy_until.items()):
+            if until < lv:
+                free.append(phys[r]); del busy_until[r]
+        free.sort()
+        new_ins = []
+        for k, dst, pay in ins:
+            if dst >= n_inputs:
+                if free:
+                    p = free.pop(0)
+                else:
+                    p = next_phys; next_phys += 1
+                phys[dst] = p
+                busy_until[dst] = last_use.get(dst, lv)
+            new_ins.append((k, dst, pay))
+        out.append((kind, new_ins))
+    m = lambda r: phys.get(r, r)
+    res = []
+    for kind, ins in out:
+        mapped = []
+        for k, dst, pay in ins:
+            if kind == "MUL":
+                ops, neg = pay
+                npay = ([[(m(r), minus) for r, minus in o] for o in ops], neg)
+            else:
+                npay = type(pay)((m(r), ng, db) for r, ng, db in pay)
+                if isinstance(pay, Terms):
+                    npay.reduce = pay.reduce
+            mapped.append((k, m(dst), npay))
+        res.append((kind, mapped))
+    return res
+
+
 def check_hazards(prog, n_inputs):
     """within a level no instruction may read a register written in the same level"""
     for kind, ins in prog:
@@ -820,6 +866,8 @@ def emit(sets, path):
         maxes = [max(a, b) for a, b in zip(maxes, [len(mul_tab), len(lin_tab), len(term_tab), len(level_tab)])]
         out.append("namespace %s {" % tag)
         out.append("constexpr int kMaxRegs = %d;" % max(p[2] for p in prog_tab))
+        out.append("constexpr int kMaxRegsNoSqrLines = %d;   // the multi-group form runs f12_sqr and lines separately: smaller register files" %
+                   max(p[2] for p, nm in zip(prog_tab, names) if nm != "sqr_lines"))
         out.append("constexpr int kNumMul = %d, kNumLin = %d, kNumTerm = %d, kNumLevel = %d;" % (len(mul_tab), len(lin_tab), len(term_tab), len(level_tab)))
         row = lambda m: "{" + ",".join(str(x) for x in m) + "}"
         for qual, pre in (("static __device__ const", "d"), ("static const", "h")):
@@ -962,7 +1010,7 @@ def build_all(max_operand_terms, builder=Builder):
     progs = {}
     for mk in PROGRAMS:
         B = mk()
-        prog = B.finish()
+        prog = reallocate(B.finish(), N_IN)
         check_hazards(prog, N_IN)
         progs[B.name] = prog
     selftest(progs, run29 if builder is Builder29 else None)

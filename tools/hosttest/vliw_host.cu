@@ -1,6 +1,7 @@
 // CPU unit test of the cooperative pairing engine (vliw.cuh) and of fp_inv_bingcd: the same verdicts as the
 // scalar path on the reference's verify_kzg_proof vectors.  Built and run by tests/test_host_cuda_logic.py.
 #include <cstdio>
+#include <cstring>
 #include <cstdlib>
 #include <vector>
 #include "verify.cuh"
@@ -36,8 +37,17 @@ int main(int argc, char** argv) {
   // the same checks three at a time in lockstep (multi-group form used by the many-tuple kernel)
   const int G = 3;
   std::vector<Fp> mregs(G * (vliw::kTotalRegs + 1));
-  vliw::Lanes LM{0, 1, vliw::throughput_tables()};
-  LM.groups = G; LM.stride = vliw::kTotalRegsThr * 12 + 1;
+  static vliw::SharedTables mt;      // the multi-group form executes from a remapped copy of the throughput tables (shared registers)
+  {
+    vliw::Tables src = vliw::throughput_tables();
+    memcpy(mt.mul, src.mul, sizeof(uint16_t) * 19 * vliw::thr::kNumMul); memcpy(mt.lin, src.lin, sizeof(uint32_t) * 3 * vliw::thr::kNumLin);
+    memcpy(mt.term, src.term, sizeof(uint16_t) * vliw::thr::kNumTerm); memcpy(mt.level, src.level, sizeof(vliw::Level) * vliw::thr::kNumLevel);
+    memcpy(mt.prog, src.prog, sizeof(vliw::Program) * vliw::kNumPrograms);
+    vliw::remap_tables_multi(&mt, 0, 1);
+  }
+  static Fp mshared[vliw::kNumSharedRegs];
+  vliw::Lanes LM{0, 1, vliw::Tables{mt.mul, mt.lin, mt.term, mt.level, mt.prog, false}};
+  LM.groups = G; LM.stride = vliw::kTotalRegsThr * 12 + 1; LM.shared = mshared;
   for (size_t i = 0; i + G <= mx.size() && i < 12; i += G) {
     uint8_t ok[G];
     vliw::coop_pairing_multi(mregs.data(), &mx[i], T.g2_gen, &mp[i], T.tau_g2, LM, ok);
