@@ -51,6 +51,7 @@ constexpr int kWinLanes = 64, kWinPer = kBuckets / kWinLanes;     // 64 lanes x 
 constexpr int kFinalThreads = 64;       // G1 prelude of the final check (sums, [s]G, affine conversion)
 constexpr int kPairThreads = 768;       // pairing engine: 24 warps = 24 products (one per warp) or 48 sums (16 lanes each) at a time
 constexpr int kManyThreads = 512, kManyGroups = 28;   // many_pairing_kernel: checks run in lockstep by one CTA (28 x 36 products = 1.97 x 512; 128 registers)
+constexpr int kManyCtasPerSm = 1;                     // (two CTAs of 14 checks per SM, not in lockstep with each other: 491 k instead of 555 k checks/s)
 constexpr int kManyWarps = 4;         // many_pairing_warp_kernel (identity inputs): one check per warp
 constexpr int kHarnessMaxDegree = 16;
 constexpr int kLagWindows = 32, kLagEntries = 255;

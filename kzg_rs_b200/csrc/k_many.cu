@@ -53,7 +53,7 @@ struct ManySmem {
     uint8_t ok[kManyGroups], use[kManyGroups];
 };
 static_assert(sizeof(ManySmem) <= kManySmemBytes, "keep kManySmemBytes (common.cuh) in step with ManySmem");
-__global__ void __launch_bounds__(kManyThreads, 1) many_pairing_kernel(const G1Affine* __restrict__ X, const G1Affine* __restrict__ P,
+__global__ void __launch_bounds__(kManyThreads, kManyCtasPerSm) many_pairing_kernel(const G1Affine* __restrict__ X, const G1Affine* __restrict__ P,
                                                                        const uint32_t* __restrict__ status, size_t m,
                                                                        const DeviceTables* __restrict__ T, uint8_t* __restrict__ verdicts) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];

@@ -522,10 +522,11 @@ extern "C" const char* kzgb200_last_error(const kzgb200_ctx* ctx) { return ctx ?
 
 // per tuple of the many-tuple path: 3 affine points, a status word, 160 input bytes, a verdict byte (rounded up)
 constexpr size_t kManyBytesPerTuple = 3 * sizeof(G1Affine) + 4 + 160 + 4;
-// the pairing checks of m parsed tuples: kManyGroups per CTA in lockstep (one persistent CTA per SM), then the rare identity inputs
+// the pairing checks of m parsed tuples: kManyGroups per CTA in lockstep (kManyCtasPerSm persistent CTAs per SM), then the rare identity inputs
 static int launch_many_pairings(kzgb200_ctx* ctx, const G1Affine* X, const G1Affine* P, const uint32_t* status, size_t m, uint8_t* dv) {
     size_t nbatch = (m + kManyGroups - 1) / kManyGroups;
-    unsigned grid = (unsigned)(nbatch < (size_t)ctx->num_sms ? nbatch : (size_t)ctx->num_sms);
+    const size_t slots = (size_t)ctx->num_sms * kManyCtasPerSm;
+    unsigned grid = (unsigned)(nbatch < slots ? nbatch : slots);
     many_pairing_kernel<<<grid, kManyThreads, kManySmemBytes, ctx->stream>>>(X, P, status, m, ctx->tables, dv);
     size_t nw = (m + kManyWarps - 1) / kManyWarps;
     many_pairing_warp_kernel<<<(unsigned)(nw < (size_t)ctx->num_sms ? nw : (size_t)ctx->num_sms), 32 * kManyWarps, kManySmemBytes, ctx->stream>>>(X, P, m, ctx->tables, dv);

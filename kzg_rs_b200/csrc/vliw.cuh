@@ -294,7 +294,8 @@ constexpr int kNumSaves = 5;
 constexpr int kTotalRegs = kMaxRegs + 12 * kNumSaves;
 // register file of the lockstep (multi-group) form, throughput programs: logical numbering up to kSave0Thr + 60 with the 22
 // shared registers (lines, constants) taken out of the group files
-constexpr int kSave0Thr = thr::kMaxRegsNoSqrLines, kTotalRegsThr = thr::kMaxRegsNoSqrLines - kNumSharedRegs + 12 * kNumSaves;
+constexpr int kNumSavesThr = 3;      // the final exponentiation needs three saved Fp12 values at a time (see coop_pairing_multi)
+constexpr int kSave0Thr = thr::kMaxRegs, kTotalRegsThr = thr::kMaxRegs - kNumSharedRegs + 12 * kNumSavesThr;
 
 KZG_HD void load_lines(Fp* regs, const LineCoeffs* c1, const LineCoeffs* c2, int k, const Lanes& L) {
     if (L.shared) {          // multi-group form: the lines are the same for every check -- one copy
@@ -444,8 +445,7 @@ KZG_HD void coop_pairing_multi(Fp* regs, const G1Affine* P1, const LineCoeffs* c
     int k = 0;
     for (int bit = 62; bit >= 0; bit--) {
         load_lines(regs, c1, c2, k++, L);
-        run(kProg_f12_sqr, regs, L);        // (sqr_lines in one program needs 18 registers more per group)
-        run(kProg_lines, regs, L);
+        run(kProg_sqr_lines, regs, L);
         run(kProg_f12_mul, regs, L);
         if ((KZG_BLS_X_ABS >> bit) & 1) {
             load_lines(regs, c1, c2, k++, L);
@@ -454,7 +454,8 @@ KZG_HD void coop_pairing_multi(Fp* regs, const G1Affine* P1, const LineCoeffs* c
         }
     }
     run(kProg_conj, regs, L);
-    const int S0 = kSave0Thr, S1 = kSave0Thr + 12, S2 = kSave0Thr + 24, S3 = kSave0Thr + 36, S4 = kSave0Thr + 48;
+    // three save slots: S0 = f to the end; S1 = f^(x-1), a; S2 = a^x, b; S3 (b^x) and S4 (b^(x^2), c) take S1's slot once a is dead
+    const int S0 = kSave0Thr, S1 = kSave0Thr + 12, S2 = kSave0Thr + 24, S3 = S1, S4 = S1;
     copy_regs(regs, S0, kRegF, 12, L);
     run(kProg_inv_prep, regs, L);
     for (int gi = L.tid; gi < L.groups; gi += L.n) { Fp* r = L.file(regs, gi); r[kRegH + 8] = fp_inv_bingcd(r[kRegH + 8]); }
