@@ -157,44 +157,117 @@ __global__ void __launch_bounds__(kWinLanes) msm_window_kernel(const G1* __restr
     }
     if (l == 0) windows[sw] = sm[0];
 }
-// window sums -> A = sum_w 256^w W[0][w], B' = sum_w 256^w (W[1][w] + W[2][w]) (Horner, 8 doublings per window):
-// warp 0 does A, warp 1 does B' with the cooperative point operations above; the other warps OR the per-blob error
-// flags, tree-sum s = sum r_i y_i and then -- still in the shadow of the Horner chains -- form [s]G from the fixed-base table
-// (64 lookups, a 6-level tree); the partial carries B' - [s]G and ry = 0, so the final check has no fixed-base work left
-// (round 2: 0.1 ms off the serial tail; with several ranks each folds its own [s_k]G).
+// window sums -> A = sum_w 256^w W[0][w], B' = sum_w 256^w (W[1][w] + W[2][w]) (Horner, 8 doublings per window): the serial part
+// of the MSM, 120 doublings + 16 additions per point set.
+//
+// Round 2: the three chains run in LOCKSTEP on the cooperative engine of the pairing check (vliw29.cuh: programs g1_dbl / g1_add over
+// three register files, one warp per Fp product, 16 lanes per sum) on 384 threads -- a doubling is 6 short levels (~2 us) instead of
+// three lone-thread Fp products in a row (~4.9 us).  The generic addition formula is only valid for distinct non-identity points;
+// identities are tracked exactly (flags from the window sums), and the astronomically unlikely equal-x case (H = 0, checked after
+// every addition) switches the whole kernel back to round 1's warp-cooperative chains (coop.cuh), which handle every case.
+// Beside the chains, 160 helper threads OR the per-blob error flags, tree-sum s = sum r_i y_i and form [s]G from the fixed-base
+// table (64 lookups, a 6-level tree); the partial carries B' - [s]G and ry = 0, so the final check has no fixed-base work left.
 // `out` may be a peer-mapped pointer into the group leader's exchange buffer (multi-GPU: the partial-sum gather is this kernel's
 // last store, over NVLink); then `flag` (same buffer) receives `epoch` after the partial, with a system-scope fence in between.
-__global__ void __launch_bounds__(256) msm_combine_kernel(const G1* __restrict__ windows, const Fr* __restrict__ ry, const uint32_t* __restrict__ status,
-                                                          int n, const DeviceTables* __restrict__ T, Partial* __restrict__ out, uint32_t* flag, uint32_t epoch) {
-    __shared__ uint32_t s_err;
-    __shared__ Fr s_ry[256];
+constexpr int kCombEngine = 384, kCombHelpers = 160;          // kCombineThreads = 544 (common.cuh)
+constexpr int kCombRegs = 96;                                  // registers per chain: g1_add needs 83; 90..92 = saved accumulator
+static_assert(kCombEngine + kCombHelpers == kCombineThreads, "thread split of msm_combine_kernel");
+struct CombineSmem {
+    f29::F29 regs[kMsmSets][kCombRegs];
+    f29::F29 win[kMsmSets][kWindows][3];
+    vliw29::SharedTables stab;
+};
+static_assert(sizeof(CombineSmem) <= kCombineSmemBytes, "keep kCombineSmemBytes (common.cuh) in step with CombineSmem");
+__global__ void __launch_bounds__(kCombineThreads) msm_combine_kernel(const G1* __restrict__ windows, const Fr* __restrict__ ry, const uint32_t* __restrict__ status,
+                                                                      int n, const DeviceTables* __restrict__ T, Partial* __restrict__ out, uint32_t* flag, uint32_t epoch) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    CombineSmem& S = *reinterpret_cast<CombineSmem*>(dyn_smem);
+    __shared__ uint32_t s_err, s_fallback;
+    __shared__ uint8_t s_wid[kMsmSets][kWindows];
+    __shared__ Fr s_ry[kCombHelpers];
     __shared__ CoopPoint cp[3];
     __shared__ G1 s_sg[64];
-    int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    if (t == 0) s_err = 0;
+    const int t = threadIdx.x;
+    if (t == 0) { s_err = 0; s_fallback = 0; }
     __syncthreads();
-    if (warp < kMsmSets) {
-        // warps 0..2: Horner recombination of one point set each (15 x 8 doublings + 16 additions, the serial part of the tail)
-        CoopPoint* s = &cp[warp];
-        if (lane == 0) { s->v[0] = Fp::one(); s->v[1] = Fp::one(); s->v[2] = Fp::zero(); }
-        __syncwarp();
+    if (t < kCombEngine) {
+        auto ebar = [] { asm volatile("bar.sync 2, %0;" ::"n"(kCombEngine) : "memory"); };
+        // program tables + the window sums in the engine's representation
+        {
+            const vliw29::Tables src = vliw29::default_tables();
+            for (int i = t; i < vliw29::kNumMul * 4; i += kCombEngine) (&S.stab.mul[0][0])[i] = (&src.mul[0][0])[i];
+            for (int i = t; i < vliw29::kNumLin * 4; i += kCombEngine) (&S.stab.lin[0][0])[i] = (&src.lin[0][0])[i];
+            for (int i = t; i < vliw29::kNumTerm; i += kCombEngine) S.stab.term[i] = src.term[i];
+            for (int i = t; i < vliw29::kNumLevel; i += kCombEngine) S.stab.level[i] = src.level[i];
+            for (int i = t; i < vliw29::kNumPrograms; i += kCombEngine) S.stab.prog[i] = src.prog[i];
+            if (t < 16) S.stab.p29[t] = t < 14 ? (int32_t)f29::p29_rt(t) : 0;
+        }
+        for (int i = t; i < kMsmSets * kWindows * 3; i += kCombEngine) {
+            const int sw = i / 3, c = i % 3;
+            const G1& w = windows[sw];
+            S.win[sw / kWindows][sw % kWindows][c] = f29::from_fp(c == 0 ? w.x : (c == 1 ? w.y : w.z));
+            if (c == 2) s_wid[sw / kWindows][sw % kWindows] = w.z.is_zero() ? 1 : 0;
+        }
+        for (int i = t; i < kMsmSets * kCombRegs; i += kCombEngine) S.regs[i / kCombRegs][i % kCombRegs] = f29::f29_zero();
+        ebar();
+        vliw29::Lanes L{t, kCombEngine, vliw29::Tables{S.stab.mul, S.stab.lin, S.stab.term, S.stab.level, S.stab.prog}, nullptr, S.stab.p29};
+        L.groups = kMsmSets; L.gstride = kCombRegs; L.bar_id = 2; L.bar_threads = kCombEngine;
+        f29::F29* regs = &S.regs[0][0];
+        bool acc_id[kMsmSets] = {true, true, true};       // the accumulator of chain g is the identity (same value in every thread)
         for (int w = kWindows - 1; w >= 0; w--) {
-            if (w != kWindows - 1) for (int k = 0; k < 8; k++) coop_dbl(s, lane);
-            coop_add(s, windows[warp * kWindows + w], lane);
+            if (w != kWindows - 1) for (int k = 0; k < 8; k++) vliw29::run(vliw29::kProg_g1_dbl, regs, L);
+            // (X, Y, Z) += window sum w of every chain: addend into registers 3..5, accumulator saved in 90..92
+            for (int i = t; i < kMsmSets * 3 * 4; i += kCombEngine) {
+                const int g = i / 12, c = (i / 4) % 3, q = i % 4;
+                reinterpret_cast<uint4*>(&S.regs[g][3 + c])[q] = reinterpret_cast<const uint4*>(&S.win[g][w][c])[q];
+                reinterpret_cast<uint4*>(&S.regs[g][90 + c])[q] = reinterpret_cast<const uint4*>(&S.regs[g][c])[q];
+            }
+            ebar();
+            vliw29::run(vliw29::kProg_g1_add, regs, L);
+            // the cases the generic formula does not cover
+            for (int i = t; i < kMsmSets * 3 * 4; i += kCombEngine) {
+                const int g = i / 12, c = (i / 4) % 3, q = i % 4;
+                if (s_wid[g][w]) reinterpret_cast<uint4*>(&S.regs[g][c])[q] = reinterpret_cast<const uint4*>(&S.regs[g][90 + c])[q];     // + identity
+                else if (acc_id[g]) reinterpret_cast<uint4*>(&S.regs[g][c])[q] = reinterpret_cast<const uint4*>(&S.regs[g][3 + c])[q];    // identity + W
+            }
+            if (t < kMsmSets && !s_wid[t][w] && !acc_id[t]) {          // equal x (P = +-Q): not handled here
+                if (vliw29::canonical_signed(S.regs[t][6]).is_zero()) s_fallback = 1;
+            }
+#pragma unroll
+            for (int g = 0; g < kMsmSets; g++) acc_id[g] = acc_id[g] && s_wid[g][w];
+            ebar();
+        }
+        // back to the 12 x 32 Montgomery form for the last two additions (coop.cuh handles every case)
+        if (t < kMsmSets * 3) {
+            const int g = t / 3, c = t % 3;
+            Fp v = Fp::from_raw(vliw29::canonical_signed(S.regs[g][c]));
+            if (acc_id[g]) v = c == 2 ? Fp::zero() : Fp::one();
+            cp[g].v[c] = v;
+        }
+        ebar();
+        if (s_fallback && t < 32 * kMsmSets) {        // round 1's chains
+            const int warp = t >> 5, lane = t & 31;
+            CoopPoint* s = &cp[warp];
+            __syncwarp();
+            if (lane == 0) { s->v[0] = Fp::one(); s->v[1] = Fp::one(); s->v[2] = Fp::zero(); }
+            __syncwarp();
+            for (int w = kWindows - 1; w >= 0; w--) {
+                if (w != kWindows - 1) for (int k = 0; k < 8; k++) coop_dbl(s, lane);
+                coop_add(s, windows[warp * kWindows + w], lane);
+            }
         }
     } else {
-        // warps 3..7, beside the recombination: OR of the per-blob error flags and sum r_i y_i
-        constexpr int kHelpers = 256 - 32 * kMsmSets;
-        int h = t - 32 * kMsmSets;
+        // helpers, beside the chains: OR of the per-blob error flags, s = sum r_i y_i, [s]G
+        const int h = t - kCombEngine;
         uint32_t e = 0;
         Fr acc_ry = Fr::zero();
-        for (int i = h; i < n; i += kHelpers) { e |= status[i]; acc_ry = acc_ry.add_inl(ry[i]); }
+        for (int i = h; i < n; i += kCombHelpers) { e |= status[i]; acc_ry = acc_ry.add_inl(ry[i]); }
         if (e) atomicOr(&s_err, e);
         s_ry[h] = acc_ry;
-        asm volatile("bar.sync 1, %0;" ::"n"(kHelpers) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kCombHelpers) : "memory");
         for (int span = 128; span >= 1; span >>= 1) {
-            if (h < span && h + span < kHelpers) s_ry[h] = s_ry[h].add_inl(s_ry[h + span]);
-            asm volatile("bar.sync 1, %0;" ::"n"(kHelpers) : "memory");
+            if (h < span && h + span < kCombHelpers) s_ry[h] = s_ry[h].add_inl(s_ry[h + span]);
+            asm volatile("bar.sync 1, %0;" ::"n"(kCombHelpers) : "memory");
         }
         // [s]G: helper h < 64 takes the h-th 4-bit digit of s (normal form), then a tree over the 64 table points
         if (h < 64) {
@@ -202,13 +275,14 @@ __global__ void __launch_bounds__(256) msm_combine_kernel(const G1* __restrict__
             const uint32_t d = (sv.l[h / 8] >> (4 * (h % 8))) & 15u;
             s_sg[h] = d ? G1::from_affine(T->gen_table[h][d - 1]) : G1::identity();
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(kHelpers) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kCombHelpers) : "memory");
         for (int span = 32; span >= 1; span >>= 1) {
             if (h < span) s_sg[h] = s_sg[h].add(s_sg[h + span]);
-            asm volatile("bar.sync 1, %0;" ::"n"(kHelpers) : "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(kCombHelpers) : "memory");
         }
     }
     __syncthreads();
+    const int warp = t >> 5, lane = t & 31;
     if (warp == 1) {          // B' = set 1 + set 2 - [s]G
         G1 q = {cp[2].v[0], cp[2].v[1], cp[2].v[2]};
         coop_add(&cp[1], q, lane);

@@ -403,7 +403,7 @@ int launch_lincomb(kzgb200_ctx* ctx, size_t offset, Partial* d_out, bool wait_su
     phase_begin(ctx, kPhReduce, ctx->stream);
     msm_window_kernel<<<kMsmSets * kWindows, kWinLanes, kTailPadSmem, ctx->stream>>>(ctx->d_buckets, ctx->d_windows);
     if (wait_subgroup) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_parse, 0));    // combine ORs the per-blob error flags
-    msm_combine_kernel<<<1, 256, kTailPadSmem, ctx->stream>>>(ctx->d_windows, ctx->d_ry, ctx->d_status, n, ctx->tables, d_out, d_flag, epoch);
+    msm_combine_kernel<<<1, kCombineThreads, kCombineSmemBytes, ctx->stream>>>(ctx->d_windows, ctx->d_ry, ctx->d_status, n, ctx->tables, d_out, d_flag, epoch);
     phase_end(ctx, kPhReduce, ctx->stream);
     CK(cudaGetLastError());
     return KZGB200_OK;
@@ -462,6 +462,7 @@ extern "C" int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_p
         CK(cudaFuncSetAttribute(batch_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinalSmem)));
         CK(cudaFuncSetAttribute(single_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinalSmem)));
         CK(cudaFuncSetAttribute(pairing_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairSmem)));
+        CK(cudaFuncSetAttribute(msm_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombineSmemBytes));
         CK(cudaFuncSetAttribute(many_pairing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kManySmemBytes));
         CK(cudaFuncSetAttribute(many_pairing_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kManySmemBytes));
         CK(cudaMalloc(&ctx->tables, sizeof(DeviceTables)));

@@ -43,6 +43,8 @@ struct Lanes {
     Tables tab;
     long long* ticks = nullptr;   // optional: per-section clock64() stamps (profiling aid)
     const int32_t* p29s = nullptr;   // device: limbs of p, one per lane, in shared memory
+    int groups = 1, gstride = 0;     // independent register files run in lockstep through the same program, gstride registers apart
+    int bar_id = 0, bar_threads = 0; // != 0: the cooperating threads are a subset of the CTA and meet at this named barrier
     KZG_HD void tick(int i) const {
 #ifdef __CUDA_ARCH__
         if (ticks && tid == 0) ticks[i] = clock64();
@@ -50,7 +52,8 @@ struct Lanes {
     }
     KZG_HD void sync() const {
 #ifdef __CUDA_ARCH__
-        __syncthreads();
+        if (bar_threads) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
+        else __syncthreads();
 #endif
     }
 };
@@ -290,25 +293,32 @@ KZG_HD void run(int prog, F29* regs, const Lanes& L) {
         const Level lev = L.tab.level[lv];
 #ifdef __CUDA_ARCH__
         long long c0 = L.ticks ? clock64() : 0;
+        const int total = lev.count * L.groups;                   // instruction instances: (instruction k, register file g)
         if (lev.kind == 1) {
             // one product per warp; a level of more products than warps runs in balanced passes (36 on 24 warps: 18 + 18)
             const int w = L.tid >> 5, nw = L.n >> 5;
-            const int passes = (lev.count + nw - 1) / nw, per = (lev.count + passes - 1) / passes;
+            const int passes = (total + nw - 1) / nw, per = (total + passes - 1) / passes;
             if (w < per)
-                for (int k = w; k < lev.count; k += per) exec_mul32(regs, L.tab.mul[lev.first + k], L.tid & 31);
+                for (int i = w; i < total; i += per) {
+                    const int k = i / L.groups, g = i - k * L.groups;
+                    exec_mul32(regs + g * L.gstride, L.tab.mul[lev.first + k], L.tid & 31);
+                }
         } else {
-            const int g = L.tid >> 4, ng = L.n >> 4, lane = L.tid & 15;
-            for (int base = 0; base < lev.count; base += ng) {
-                const int k = base + g;
-                if (base + (g & ~1) >= lev.count) break;              // neither group of this warp has an instruction left (warp-uniform)
-                const bool active = k < lev.count;                    // an idle second group runs along: the shuffles need every lane
-                exec_lin16(regs, L.tab.lin[lev.first + (active ? k : base)], L.tab.term, active, L.p29s, lane);
+            const int slot = L.tid >> 4, nslots = L.n >> 4, lane = L.tid & 15;
+            for (int base = 0; base < total; base += nslots) {
+                const int i = base + slot;
+                if (base + (slot & ~1) >= total) break;               // neither group of this warp has an instruction left (warp-uniform)
+                const bool active = i < total;                        // an idle second group runs along: the shuffles need every lane
+                const int ii = active ? i : base, k = ii / L.groups, g = ii - k * L.groups;
+                exec_lin16(regs + g * L.gstride, L.tab.lin[lev.first + k], L.tab.term, active, L.p29s, lane);
             }
         }
         long long c1 = L.ticks ? clock64() : 0;
 #else
-        if (lev.kind == 1) { for (int k = 0; k < lev.count; k++) exec_mul_ref(regs, L.tab.mul[lev.first + k]); }
-        else { for (int k = 0; k < lev.count; k++) exec_lin_ref(regs, L.tab.lin[lev.first + k], L.tab.term); }
+        for (int g = 0; g < L.groups; g++) {
+            if (lev.kind == 1) { for (int k = 0; k < lev.count; k++) exec_mul_ref(regs + g * L.gstride, L.tab.mul[lev.first + k]); }
+            else { for (int k = 0; k < lev.count; k++) exec_lin_ref(regs + g * L.gstride, L.tab.lin[lev.first + k], L.tab.term); }
+        }
 #endif
         L.sync();
 #ifdef __CUDA_ARCH__
