@@ -5,10 +5,15 @@ timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; 
 tail -3 gpurun_out/pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/bench.err
+timeout 900 python bench.py --config tuples --tuples 1000000 --steps 3 --warmup 2 > gpurun_out/bench_tuples.json 2> gpurun_out/bench_tuples.err
+timeout 600 python tools/bench_configs.py > gpurun_out/bench_configs.json 2> gpurun_out/bench_configs.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r02.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_bench.log 2>&1
 B="python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-extras --blobs 16384"
-for k in pairing_check_kernel msm_combine_kernel batch_final_kernel; do
-  timeout 400 ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -f -o gpurun_out/full_$k $B > gpurun_out/ncu_$k.log 2>&1
+BT="python bench.py --config tuples --tuples 16384 --steps 1 --warmup 0"
+for k in pairing_check_kernel msm_combine_kernel batch_final_kernel challenge_ws_kernel many_pairing_kernel; do
+  CMD="$B"; if [ $k = many_pairing_kernel ]; then CMD="$BT"; fi
+  if [ $k = challenge_ws_kernel ]; then CMD="python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-extras --blobs 8192"; fi
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -f -o gpurun_out/full_$k $CMD > gpurun_out/ncu_$k.log 2>&1
   ncu -i gpurun_out/full_$k.ncu-rep --page raw --csv > gpurun_out/ncu_raw_$k.csv 2>/dev/null
   rm -f gpurun_out/full_$k.ncu-rep
 done
