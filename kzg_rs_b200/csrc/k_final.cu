@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(kPairThreads) pairing_check_kernel(const Final
     PairSmem& S = *reinterpret_cast<PairSmem*>(dyn_smem);
     const int t = threadIdx.x;
     if (in->go == 0) return;            // the prelude already wrote the result
-    if (ticks && t == 0) { ticks[0] = clock64(); for (int i = 8; i < 14; i++) ticks[i] = 0; }
+    if (ticks && t == 0) { ticks[0] = clock64(); for (int i = 6; i < 14; i++) ticks[i] = 0; }
     vliw29::Tables tab = vliw29::load_tables(&S.stab, t, kPairThreads);
     vliw29::Lanes L{t, kPairThreads, tab, ticks, S.stab.p29};
     const G1Affine p0 = in->pts[0], p1 = in->pts[1];

@@ -300,7 +300,7 @@ KZG_HD void run(int prog, F29* regs, const Lanes& L) {
             const int passes = (total + nw - 1) / nw, per = (total + passes - 1) / passes;
             if (w < per)
                 for (int i = w; i < total; i += per) {
-                    const int k = i / L.groups, g = i - k * L.groups;
+                    const int k = L.groups == 1 ? i : i / L.groups, g = i - k * L.groups;
                     exec_mul32(regs + g * L.gstride, L.tab.mul[lev.first + k], L.tid & 31);
                 }
         } else {
@@ -309,7 +309,7 @@ KZG_HD void run(int prog, F29* regs, const Lanes& L) {
                 const int i = base + slot;
                 if (base + (slot & ~1) >= total) break;               // neither group of this warp has an instruction left (warp-uniform)
                 const bool active = i < total;                        // an idle second group runs along: the shuffles need every lane
-                const int ii = active ? i : base, k = ii / L.groups, g = ii - k * L.groups;
+                const int ii = active ? i : base, k = L.groups == 1 ? ii : ii / L.groups, g = ii - k * L.groups;
                 exec_lin16(regs + g * L.gstride, L.tab.lin[lev.first + k], L.tab.term, active, L.p29s, lane);
             }
         }
@@ -406,11 +406,17 @@ KZG_HD bool coop_pairing_product_is_one(F29* regs, const G1Affine& P1, const Lin
     for (int s = 0; s < n_steps; s++) {
         const uint32_t w = script[s];
         const int op = (int)(w & 0xffu), a = (int)((w >> 8) & 0xfffu), b = (int)(w >> 20);
+#ifdef __CUDA_ARCH__
+        const long long s0 = L.ticks ? clock64() : 0;
+#endif
         if (op == kOpRun) run(a, regs, L);
         else if (op == kOpCopy) copy_regs(regs, a, b, 12, L);
         else if (op == kOpLines) load_lines(regs, ca, cb, a, L);
         else if (op == kOpInv) { if (L.tid == 0) regs[kRegH + 8] = inv29(regs[kRegH + 8]); L.sync(); }
         else L.tick(a);
+#ifdef __CUDA_ARCH__
+        if (L.ticks && L.tid == 0 && (op == kOpCopy || op == kOpLines)) L.ticks[op == kOpCopy ? 6 : 7] += clock64() - s0;   // profiling aid
+#endif
     }
     // == 1 ?  (each coefficient canonicalised by its own thread; the verdict words land in the padding of the G slot)
     for (int i = L.tid; i < 12; i += L.n) {

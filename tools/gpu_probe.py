@@ -54,5 +54,6 @@ for n in [int(x) for x in (sys.argv[1:] or ["64", "1024", "4096"])]:
         print("  final kernel sections (us @1.965GHz):", {k: round((tk[i + 1] - tk[i]) / 1965.0, 1) for i, k in enumerate(names2)})
         print("  engine levels (lane 0): LIN body %.0f us, LIN barrier wait %.0f us over %d levels; MUL body %.0f us, MUL wait %.0f us over %d levels"
               % (tk[8] / 1965.0, tk[9] / 1965.0, tk[12], tk[10] / 1965.0, tk[11] / 1965.0, tk[13]))
+        print("  slot copies %.0f us, line loads %.0f us (thread 0, barrier included)" % (tk[6] / 1965.0, tk[7] / 1965.0))
     except Exception as e:
         print("ticks unavailable", e)
