@@ -46,7 +46,7 @@ constexpr int kLeavesPerThread = kFieldElementsPerBlob / kEvalThreads;  // 32
 constexpr int kTreeGroup = 16;      // transcript entries (160 B each) per leaf hash: 40 compressions
 constexpr int kTreeMid = 32;        // leaf digests per middle-level hash: 17 compressions
 constexpr int kWindows = 16, kBuckets = 256, kMsmSets = 3, kDigitRows = 4 * kWindows;   // rows: (kind r|rz) x (half lo|hi) x window
-constexpr int kSlice = 32, kMsmRows = kMsmSets * 2 * kWindows;   // bucket accumulation: entries per thread; rows = (set, GLV half, window)
+constexpr int kSlice = 16, kMsmRows = kMsmSets * 2 * kWindows;   // bucket accumulation: entries per thread; rows = (set, GLV half, window)
 constexpr int kWinLanes = 64, kWinPer = kBuckets / kWinLanes;     // 64 lanes x 4 buckets: 48 CTAs still fit the tail's 8 SMs in one wave
 constexpr int kCombineThreads = 544;    // msm_combine_kernel: 384 engine threads (three Horner chains in lockstep) + 160 helpers
 constexpr int kCombineSmemBytes = 48 * 1024;
