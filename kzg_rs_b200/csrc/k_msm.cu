@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) msm_sort_kernel(const uint8_t* __restrict
     for (int i = t; i < n; i += blockDim.x) ord[atomicAdd(&cursor[row[i]], 1u)] = (uint32_t)i;
 }
 // Bucket accumulation, balanced.  A "row" = (point set, GLV half, window): its sorted index list (n entries, grouped by digit) is
-// cut into slices of kSlice consecutive entries and every thread sums exactly one slice -- round 1 gave whole bucket lists to
+// cut into slices of `slice` consecutive entries (msm_slice_len) and every thread sums exactly one slice -- round 1 gave whole bucket lists to
 // threads (Poisson-sized: a warp ran at the pace of its longest lane, +40 %).  A slice spans one or a few digit runs: a run that
 // lies entirely inside the slice is a finished half-bucket and goes to `halfsum`; the slice's first / last run may continue in
 // the neighbouring slices and goes to `part` slot 0 / 1 (a slice that is one single run: slot 0).  msm_bucket_join_kernel adds
@@ -68,10 +68,11 @@ __device__ __forceinline__ G1Affine ldg_point(const G1Affine* p) {
     a.inf = __ldg(w + 24);
     return a;
 }
-__global__ void __launch_bounds__(128) msm_bucket_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P, int n,
+template <int kCtasPerSm>
+__global__ void __launch_bounds__(128, kCtasPerSm) msm_bucket_kernel(const G1Affine* __restrict__ C, const G1Affine* __restrict__ P, int n,
                                                          const uint32_t* __restrict__ order, const uint32_t* __restrict__ start,
-                                                         G1* __restrict__ halfsum /* [96][256] */, G1* __restrict__ part /* [96][slices][2] */) {
-    const int slices = (n + kSlice - 1) / kSlice;
+                                                         G1* __restrict__ halfsum /* [96][256] */, G1* __restrict__ part /* [96][slices][2] */, int slice) {
+    const int slices = (n + slice - 1) / slice;
     int tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= kMsmRows * slices) return;
     int row = tid / slices, s = tid % slices;                 // row = (set * 2 + half) * kWindows + w
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(128) msm_bucket_kernel(const G1Affine* __restr
     int digit_row = ((set == 2 ? 1 : 0) * 2 + half) * kWindows + w;
     const uint32_t* ord = order + (size_t)digit_row * n;
     const uint32_t* st = start + (size_t)digit_row * (kBuckets + 1);
-    const uint32_t pos0 = (uint32_t)s * kSlice, end0 = pos0 + kSlice < (uint32_t)n ? pos0 + kSlice : (uint32_t)n;
+    const uint32_t pos0 = (uint32_t)s * slice, end0 = pos0 + slice < (uint32_t)n ? pos0 + slice : (uint32_t)n;
     // digit of the first entry: the largest b with st[b] <= pos0
     int b = 0;
 #pragma unroll
@@ -111,46 +112,88 @@ __global__ void __launch_bounds__(128) msm_bucket_kernel(const G1Affine* __restr
     }
     flush(b);
 }
-// one thread per (set, window, bucket): the bucket's partial sums of both GLV halves -> buckets[set][window][bucket]
+// occupancy variants: 2 CTAs per SM keep everything in registers (216), 3 / 4 trade a few spilled words for more chains in flight
+void launch_msm_bucket(int ctas_per_sm, int n, int slice, cudaStream_t st, const G1Affine* C, const G1Affine* P, const uint32_t* order,
+                       const uint32_t* start, G1* halfsum, G1* part) {
+    const int slices = (n + slice - 1) / slice, grid = (kMsmRows * slices + 127) / 128;
+    if (ctas_per_sm >= 4) msm_bucket_kernel<4><<<grid, 128, 0, st>>>(C, P, n, order, start, halfsum, part, slice);
+    else if (ctas_per_sm == 3) msm_bucket_kernel<3><<<grid, 128, 0, st>>>(C, P, n, order, start, halfsum, part, slice);
+    else msm_bucket_kernel<2><<<grid, 128, 0, st>>>(C, P, n, order, start, halfsum, part, slice);
+}
+// kJoinLanes threads per (set, window, bucket): the bucket's partial sums of both GLV halves -> buckets[set][window][bucket].
+// A bucket of ~n/256 entries spans several slices per half (about 10 partial sums at n = 16384); a lone thread's
+// Jacobian addition takes ~30 us, so the list is dealt round-robin to the lanes (one call site: no divergent copies of the
+// addition) and the lane sums are folded by a shuffle tree: 2 + 3 additions deep instead of ~12.
+__device__ __forceinline__ G1 shfl_xor_point(const G1& p, int m) {
+    G1 r;
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        r.x.l[k] = __shfl_xor_sync(0xffffffffu, p.x.l[k], m);
+        r.y.l[k] = __shfl_xor_sync(0xffffffffu, p.y.l[k], m);
+        r.z.l[k] = __shfl_xor_sync(0xffffffffu, p.z.l[k], m);
+    }
+    return r;
+}
 __global__ void __launch_bounds__(128) msm_bucket_join_kernel(int n, const uint32_t* __restrict__ start, const G1* __restrict__ halfsum,
-                                                              const G1* __restrict__ part, G1* __restrict__ buckets /* [3][16][256] */) {
-    const int slices = (n + kSlice - 1) / kSlice;
-    int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= kMsmSets * kWindows * kBuckets) return;
+                                                              const G1* __restrict__ part, G1* __restrict__ buckets /* [3][16][256] */, int slice) {
+    const int slices = (n + slice - 1) / slice;
+    const uint32_t usl = (uint32_t)slice;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;       // the grid is exactly kMsmSets * kWindows * kBuckets * kJoinLanes threads
+    const int tid = gt / kJoinLanes, j = gt % kJoinLanes;
     int b = tid % kBuckets, w = (tid / kBuckets) % kWindows, set = tid / (kBuckets * kWindows);
     G1 acc = G1::identity();
     if (b != 0) {
+        uint32_t lo[2], s0[2], cnt[2];
+        int row[2];
+#pragma unroll
         for (int half = 0; half < 2; half++) {
-            int row = (set * 2 + half) * kWindows + w, digit_row = ((set == 2 ? 1 : 0) * 2 + half) * kWindows + w;
+            row[half] = (set * 2 + half) * kWindows + w;
+            const int digit_row = ((set == 2 ? 1 : 0) * 2 + half) * kWindows + w;
             const uint32_t* st = start + (size_t)digit_row * (kBuckets + 1);
-            uint32_t lo = __ldg(st + b), hi = __ldg(st + b + 1);
-            if (hi <= lo) continue;
-            uint32_t s0 = lo / kSlice, s1 = (hi - 1) / kSlice;
-            if (s0 == s1) { acc = acc.add(halfsum[(size_t)row * kBuckets + b]); continue; }
-            for (uint32_t s = s0; s <= s1; s++) {
-                int slot = (s == s0 && lo != s0 * kSlice) ? 1 : 0;     // the bucket opens inside slice s0: that slice's last run
-                acc = acc.add(part[((size_t)row * slices + s) * 2 + slot]);
+            const uint32_t l = __ldg(st + b), h = __ldg(st + b + 1);
+            lo[half] = l; s0[half] = l / usl;
+            cnt[half] = h > l ? (h - 1) / usl - l / usl + 1 : 0u;
+        }
+        const uint32_t total = cnt[0] + cnt[1];
+        for (uint32_t i = (uint32_t)j; i < total; i += kJoinLanes) {
+            const int half = i >= cnt[0] ? 1 : 0;
+            const uint32_t k = half ? i - cnt[0] : i;
+            const G1* src;
+            if (cnt[half] == 1) src = halfsum + (size_t)row[half] * kBuckets + b;          // the run lies inside one slice
+            else {
+                const uint32_t s = s0[half] + k;
+                const int slot = (k == 0 && lo[half] != s0[half] * usl) ? 1 : 0;        // the bucket opens inside slice s0: that slice's last run
+                src = part + ((size_t)row[half] * slices + s) * 2 + slot;
             }
+            acc = acc.add(*src);
         }
     }
-    buckets[tid] = acc;
-}
-// two warps per (set, window): W = sum_b b * bucket[b].  Lane l owns buckets 4l .. 4l+3 (running-sum trick inside
-// the segment, then the segment's offset 8l by a short double-and-add), then a shared-memory tree over the lanes.
-__global__ void __launch_bounds__(kWinLanes) msm_window_kernel(const G1* __restrict__ buckets, G1* __restrict__ windows /* [3][16] */) {
-    __shared__ G1 sm[kWinLanes];
-    int l = threadIdx.x, sw = blockIdx.x;          // sw = set * kWindows + window
-    const G1* bk = buckets + (size_t)sw * kBuckets + kWinPer * l;
-    G1 run = G1::identity(), acc = G1::identity();
-    for (int j = kWinPer - 1; j >= 0; j--) {
-        run = run.add(bk[j]);                      // bucket 0 holds the identity
-        acc = acc.add(run);                        // after the loop: acc = sum_j (j+1) bk[j], run = sum_j bk[j]
+#pragma unroll 1
+    for (int m = 1; m < kJoinLanes; m <<= 1) {
+        const G1 o = shfl_xor_point(acc, m);
+        if ((j & (2 * m - 1)) == 0) acc = acc.add(o);
     }
-    // sum_j (kWinPer l + j) bk[j] = acc + (kWinPer l - 1) run
-    uint32_t k[1] = {(uint32_t)(kWinPer * l)};
-    G1 off = scalar_mul(run, k, 8);
-    sm[l] = acc.add(off).add(run.neg());
+    if (j == 0) buckets[tid] = acc;
+}
+// one CTA per (set, window), one thread per bucket: W = sum_b b * bucket[b] = sum_{b >= 1} T_b with the suffix sums
+// T_b = sum_{c >= b} bucket[c].  Suffix scan (8 steps) + tree (8 steps) through shared memory: 16 additions deep, no doublings
+// (round 2 first ran 4 buckets per lane with the running-sum trick and a double-and-add for the segment offset: ~26 deep).
+static_assert(sizeof(G1) * kWinLanes == kWinSmemBytes, "keep kWinSmemBytes (common.cuh) in step with G1");
+__global__ void __launch_bounds__(kWinLanes) msm_window_kernel(const G1* __restrict__ buckets, G1* __restrict__ windows /* [3][16] */) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    G1* sm = reinterpret_cast<G1*>(dyn_smem);      // [kWinLanes]
+    const int l = threadIdx.x, sw = blockIdx.x;   // sw = set * kWindows + window
+    G1 mine = buckets[(size_t)sw * kBuckets + l];  // bucket 0 holds the identity
+#pragma unroll 1
+    for (int d = 1; d < kWinLanes; d <<= 1) {
+        sm[l] = mine;
+        __syncthreads();
+        if (l + d < kWinLanes) mine = mine.add(sm[l + d]);
+        __syncthreads();
+    }
+    sm[l] = l ? mine : G1::identity();
     __syncthreads();
+#pragma unroll 1
     for (int span = kWinLanes / 2; span >= 1; span >>= 1) {
         if (l < span) sm[l] = sm[l].add(sm[l + span]);
         __syncthreads();

@@ -75,7 +75,7 @@ int ensure_capacity(kzgb200_ctx* ctx, size_t n, bool need_blob_staging) {
         CK(regrow(ctx->d_status, c)); CK(regrow(ctx->d_ry, c));
         CK(regrow(ctx->d_digits, c * kDigitRows)); CK(regrow(ctx->d_order, c * kDigitRows));
         CK(regrow(ctx->d_zout, c * 32)); CK(regrow(ctx->d_yout, c * 32));
-        CK(regrow(ctx->d_part, (size_t)kMsmRows * ((c + kSlice - 1) / kSlice) * 2));
+        CK(regrow(ctx->d_part, (size_t)kMsmRows * ((c + kMinSlice - 1) / kMinSlice) * 2));
         ctx->cap = c;
     }
     if (n > ctx->host_cap) {
@@ -375,6 +375,17 @@ int launch_phase1(kzgb200_ctx* ctx, const uint8_t* d_blobs, const uint8_t* h_blo
     ctx->cur_c = d_c; ctx->cur_p = d_p; ctx->cur_n = n;
     return KZGB200_OK;
 }
+// Entries per thread of the bucket kernel.  Its kMsmRows * ceil(n / slice) threads run as 128-thread CTAs, two per SM (216
+// registers), and every thread is one chain of mixed additions: the slice length is chosen so that the CTAs fill whole waves of
+// the machine, about 16 entries each (16384 blobs on 148 SMs: 14 entries, 878 CTAs = 2.97 waves; 16 entries were 2.6 waves).
+static int msm_slice_len(const kzgb200_ctx* ctx, int n) {
+    if (ctx->msm_slice > 0) return ctx->msm_slice < kMinSlice ? kMinSlice : ctx->msm_slice;      // KZGB200_MSM_SLICE (experiments)
+    const double wave = (double)ctx->msm_occ * ctx->num_sms * 128, work = (double)kMsmRows * n;
+    int waves = (int)(work / 16.0 / wave + 0.5);
+    if (waves < 1) waves = 1;
+    int slice = (int)((work + waves * wave - 1) / (waves * wave));
+    return slice < kMinSlice ? kMinSlice : slice;
+}
 // K6: digits, counting sort, buckets, window sums, Horner -> partial (optionally stored into a peer's exchange buffer + flag)
 int launch_lincomb(kzgb200_ctx* ctx, size_t offset, Partial* d_out, bool wait_subgroup, uint32_t* d_flag, uint32_t epoch) {
     int n = (int)ctx->cur_n;
@@ -382,14 +393,17 @@ int launch_lincomb(kzgb200_ctx* ctx, size_t offset, Partial* d_out, bool wait_su
     msm_scalars_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_z_mont, ctx->d_zy, ctx->d_r, (uint64_t)offset, n, ctx->d_digits, ctx->d_ry);
     msm_sort_kernel<<<kDigitRows, 256, 0, ctx->stream>>>(ctx->d_digits, n, ctx->d_order, ctx->d_start);
     {
-        const int slices = (n + kSlice - 1) / kSlice;
-        msm_bucket_kernel<<<(kMsmRows * slices + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_C, ctx->d_P, n, ctx->d_order, ctx->d_start, ctx->d_halfsum, ctx->d_part);
-        msm_bucket_join_kernel<<<(kMsmSets * kWindows * kBuckets + 127) / 128, 128, 0, ctx->stream>>>(n, ctx->d_start, ctx->d_halfsum, ctx->d_part, ctx->d_buckets);
+        const int slice = msm_slice_len(ctx, n);
+        launch_msm_bucket(ctx->msm_occ, n, slice, ctx->stream, ctx->d_C, ctx->d_P, ctx->d_order, ctx->d_start, ctx->d_halfsum, ctx->d_part);
+        msm_bucket_join_kernel<<<kMsmSets * kWindows * kBuckets * kJoinLanes / 128, 128, 0, ctx->stream>>>(n, ctx->d_start, ctx->d_halfsum, ctx->d_part, ctx->d_buckets, slice);
     }
     phase_end(ctx, kPhLincomb, ctx->stream);
+    phase_begin(ctx, kPhReduce, ctx->stream);
+    // window sums: 48 CTAs of one thread per bucket, still with the whole machine (the deferred checks start behind them)
+    msm_window_kernel<<<kMsmSets * kWindows, kWinLanes, kWinSmemBytes, ctx->stream>>>(ctx->d_buckets, ctx->d_windows);
     if (ctx->subgroup_pending) {
-        // Deferred subgroup checks: from here on the batch is latency-bound (window sums, Horner combination, one pairing: a
-        // few CTAs), so the checks get the rest of the machine.  They run one CTA per SM on all but kTailSms SMs -- each CTA
+        // Deferred subgroup checks: from here on the batch is latency-bound (Horner combination, one pairing: single
+        // CTAs), so the checks get the rest of the machine.  They run one CTA per SM on all but kTailSms SMs -- each CTA
         // asks for kTailHogSmem of shared memory it never touches, and the tail kernels ask for kTailPadSmem, so that the two
         // cannot share an SM: the tail keeps SMs of its own and is not slowed down (sharing SMs cost more than the deferral saved).
         CK(cudaEventRecord(ctx->ev_bucket, ctx->stream));
@@ -400,8 +414,6 @@ int launch_lincomb(kzgb200_ctx* ctx, size_t offset, Partial* d_out, bool wait_su
         CK(cudaEventRecord(ctx->ev_parse, ctx->s_aux));
         ctx->subgroup_pending = false;
     }
-    phase_begin(ctx, kPhReduce, ctx->stream);
-    msm_window_kernel<<<kMsmSets * kWindows, kWinLanes, kTailPadSmem, ctx->stream>>>(ctx->d_buckets, ctx->d_windows);
     if (wait_subgroup) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_parse, 0));    // combine ORs the per-blob error flags
     msm_combine_kernel<<<1, kCombineThreads, kCombineSmemBytes, ctx->stream>>>(ctx->d_windows, ctx->d_ry, ctx->d_status, n, ctx->tables, d_out, d_flag, epoch);
     phase_end(ctx, kPhReduce, ctx->stream);
@@ -446,6 +458,8 @@ extern "C" int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_p
         if (const char* v = getenv("KZGB200_SHA_STAGES")) ctx->sha_stages = atoi(v);
         if (const char* v = getenv("KZGB200_SLAB_TAIL")) ctx->slab_tail = atoi(v) != 0;
         if (const char* v = getenv("KZGB200_PAGEABLE")) ctx->pageable_mode = !strcmp(v, "direct") ? 1 : (!strcmp(v, "register") ? 2 : 0);
+        if (const char* v = getenv("KZGB200_MSM_SLICE")) ctx->msm_slice = atoi(v);
+        if (const char* v = getenv("KZGB200_MSM_OCC")) { int o = atoi(v); if (o >= 2 && o <= 4) ctx->msm_occ = o; }
         if (const char* v = getenv("KZGB200_TRANSCRIPT")) ctx->transcript_mode = !strcmp(v, "tree") ? KZGB200_TRANSCRIPT_TREE : (!strcmp(v, "device") ? KZGB200_TRANSCRIPT_EXACT_DEVICE : KZGB200_TRANSCRIPT_EXACT);
         CK(cudaFuncSetAttribute(g1_subgroup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailHogSmem));
         CK(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
