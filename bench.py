@@ -358,7 +358,7 @@ def count_launches(n, resident, mode, world=1, leader=True):
 
 
 def load_profiled_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels, from the committed ncu --set full summary of this round"""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels, from the committed ncu capture of this round (profiles/traffic_r02.csv)"""
     try:
         return json.load(open(os.path.join(ROOT, "profiles", "ncu_full_r02_traffic.json")))
     except Exception:
@@ -548,7 +548,7 @@ def main():
         traffic = load_profiled_traffic()
         ach = n * ALGO_BYTES_PER_BLOB / (phases[top] / 1e3) / 1e9
         roof = {"bound": "hbm", "kernel": PHASES[top], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic.get(PHASES[top]), "traffic_source": "profiles/ncu_full_r02_traffic.json (ncu --set full, same workload)" if traffic.get(PHASES[top]) else None,
+                "traffic": traffic.get(PHASES[top]), "traffic_source": "profiles/ncu_full_r02_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of this launch on the same workload: profiles/traffic_r02.csv)" if traffic.get(PHASES[top]) else None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
                 "note": "the path is integer-pipe / latency bound, not HBM bound; see int_pipe and DESIGN.md section 4"}
         # algorithmic integer work of the two blob-streaming kernels against the MEASURED pipe peaks (tools/microbench/intpipe.cu,

@@ -48,7 +48,6 @@ constexpr int kTreeMid = 32;        // leaf digests per middle-level hash: 17 co
 constexpr int kWindows = 16, kBuckets = 256, kMsmSets = 3, kDigitRows = 4 * kWindows;   // rows: (kind r|rz) x (half lo|hi) x window
 constexpr int kMinSlice = 8, kMsmRows = kMsmSets * 2 * kWindows;   // bucket accumulation: fewest entries per thread (msm_slice_len); rows = (set, GLV half, window)
 constexpr int kWinLanes = kBuckets;                                 // window sums: one thread per bucket (suffix scan + tree in shared memory)
-constexpr int kJoinLanes = 8;                                        // threads per bucket in msm_bucket_join_kernel
 constexpr int kWinSmemBytes = kWinLanes * 144;                      // one Jacobian point per thread
 constexpr int kCombineThreads = 544;    // msm_combine_kernel: 384 engine threads (three Horner chains in lockstep) + 160 helpers
 constexpr int kCombineSmemBytes = 48 * 1024;
@@ -128,8 +127,7 @@ __global__ void msm_scalars_kernel(const Fr* __restrict__ z_mont, const ZY* __re
 __global__ void msm_sort_kernel(const uint8_t* __restrict__ digits, int n, uint32_t* __restrict__ order, uint32_t* __restrict__ start);
 void launch_msm_bucket(int ctas_per_sm, int n, int slice, cudaStream_t st, const G1Affine* C, const G1Affine* P, const uint32_t* order,
                        const uint32_t* start, G1* halfsum, G1* part);
-__global__ void msm_bucket_join_kernel(int n, const uint32_t* __restrict__ start, const G1* __restrict__ halfsum, const G1* __restrict__ part,
-                                       G1* __restrict__ buckets, int slice);
+void launch_msm_bucket_join(int lanes, int n, int slice, cudaStream_t st, const uint32_t* start, const G1* halfsum, const G1* part, G1* buckets);
 __global__ void msm_window_kernel(const G1* __restrict__ buckets, G1* __restrict__ windows);
 __global__ void msm_combine_kernel(const G1* __restrict__ windows, const Fr* __restrict__ ry, const uint32_t* __restrict__ status, int n,
                                    const DeviceTables* __restrict__ T, Partial* __restrict__ out, uint32_t* flag, uint32_t epoch);

@@ -120,10 +120,12 @@ void launch_msm_bucket(int ctas_per_sm, int n, int slice, cudaStream_t st, const
     else if (ctas_per_sm == 3) msm_bucket_kernel<3><<<grid, 128, 0, st>>>(C, P, n, order, start, halfsum, part, slice);
     else msm_bucket_kernel<2><<<grid, 128, 0, st>>>(C, P, n, order, start, halfsum, part, slice);
 }
-// kJoinLanes threads per (set, window, bucket): the bucket's partial sums of both GLV halves -> buckets[set][window][bucket].
-// A bucket of ~n/256 entries spans several slices per half (about 10 partial sums at n = 16384); a lone thread's
-// Jacobian addition takes ~30 us, so the list is dealt round-robin to the lanes (one call site: no divergent copies of the
-// addition) and the lane sums are folded by a shuffle tree: 2 + 3 additions deep instead of ~12.
+// kJoinLanes (2, 4 or 8; kzgb200_ctx::msm_join) threads per (set, window, bucket): the bucket's partial sums of both GLV halves ->
+// buckets[set][window][bucket].  A bucket of ~n/256 entries spans several slices per half (about 10 partial sums at n = 16384).
+// The list is dealt round-robin to the lanes -- ONE call site of the addition, so lanes with different list shapes do not run
+// divergent copies of it (round 2's first form, one thread per bucket with a branch per half, took 0.40 ms) -- and the lane sums
+// are folded by a shuffle tree.  Two lanes measured best (0.20 ms): more lanes shorten the chain but every tree step costs a
+// whole warp an addition for a few active lanes.
 __device__ __forceinline__ G1 shfl_xor_point(const G1& p, int m) {
     G1 r;
 #pragma unroll
@@ -134,6 +136,7 @@ __device__ __forceinline__ G1 shfl_xor_point(const G1& p, int m) {
     }
     return r;
 }
+template <int kJoinLanes>
 __global__ void __launch_bounds__(128) msm_bucket_join_kernel(int n, const uint32_t* __restrict__ start, const G1* __restrict__ halfsum,
                                                               const G1* __restrict__ part, G1* __restrict__ buckets /* [3][16][256] */, int slice) {
     const int slices = (n + slice - 1) / slice;
@@ -174,6 +177,12 @@ __global__ void __launch_bounds__(128) msm_bucket_join_kernel(int n, const uint3
         if ((j & (2 * m - 1)) == 0) acc = acc.add(o);
     }
     if (j == 0) buckets[tid] = acc;
+}
+void launch_msm_bucket_join(int lanes, int n, int slice, cudaStream_t st, const uint32_t* start, const G1* halfsum, const G1* part, G1* buckets) {
+    const int items = kMsmSets * kWindows * kBuckets;
+    if (lanes >= 8) msm_bucket_join_kernel<8><<<items * 8 / 128, 128, 0, st>>>(n, start, halfsum, part, buckets, slice);
+    else if (lanes >= 4) msm_bucket_join_kernel<4><<<items * 4 / 128, 128, 0, st>>>(n, start, halfsum, part, buckets, slice);
+    else msm_bucket_join_kernel<2><<<items * 2 / 128, 128, 0, st>>>(n, start, halfsum, part, buckets, slice);
 }
 // one CTA per (set, window), one thread per bucket: W = sum_b b * bucket[b] = sum_{b >= 1} T_b with the suffix sums
 // T_b = sum_{c >= b} bucket[c].  Suffix scan (8 steps) + tree (8 steps) through shared memory: 16 additions deep, no doublings

@@ -395,7 +395,7 @@ int launch_lincomb(kzgb200_ctx* ctx, size_t offset, Partial* d_out, bool wait_su
     {
         const int slice = msm_slice_len(ctx, n);
         launch_msm_bucket(ctx->msm_occ, n, slice, ctx->stream, ctx->d_C, ctx->d_P, ctx->d_order, ctx->d_start, ctx->d_halfsum, ctx->d_part);
-        msm_bucket_join_kernel<<<kMsmSets * kWindows * kBuckets * kJoinLanes / 128, 128, 0, ctx->stream>>>(n, ctx->d_start, ctx->d_halfsum, ctx->d_part, ctx->d_buckets, slice);
+        launch_msm_bucket_join(ctx->msm_join, n, slice, ctx->stream, ctx->d_start, ctx->d_halfsum, ctx->d_part, ctx->d_buckets);
     }
     phase_end(ctx, kPhLincomb, ctx->stream);
     phase_begin(ctx, kPhReduce, ctx->stream);
@@ -459,6 +459,7 @@ extern "C" int kzgb200_create(kzgb200_ctx** out, int device, const uint8_t* g2_p
         if (const char* v = getenv("KZGB200_SLAB_TAIL")) ctx->slab_tail = atoi(v) != 0;
         if (const char* v = getenv("KZGB200_PAGEABLE")) ctx->pageable_mode = !strcmp(v, "direct") ? 1 : (!strcmp(v, "register") ? 2 : 0);
         if (const char* v = getenv("KZGB200_MSM_SLICE")) ctx->msm_slice = atoi(v);
+        if (const char* v = getenv("KZGB200_MSM_JOIN")) ctx->msm_join = atoi(v);
         if (const char* v = getenv("KZGB200_MSM_OCC")) { int o = atoi(v); if (o >= 2 && o <= 4) ctx->msm_occ = o; }
         if (const char* v = getenv("KZGB200_TRANSCRIPT")) ctx->transcript_mode = !strcmp(v, "tree") ? KZGB200_TRANSCRIPT_TREE : (!strcmp(v, "device") ? KZGB200_TRANSCRIPT_EXACT_DEVICE : KZGB200_TRANSCRIPT_EXACT);
         CK(cudaFuncSetAttribute(g1_subgroup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailHogSmem));

@@ -92,6 +92,7 @@ struct kzgb200_ctx {
     int transcript_mode = KZGB200_TRANSCRIPT_EXACT;
     int num_sms = 148;
     int msm_occ = 3;                   // CTAs per SM of the bucket kernel variant in use (KZGB200_MSM_OCC: 2, 3, 4)
+    int msm_join = 2;                  // threads per bucket of the join kernel (KZGB200_MSM_JOIN: 2, 4, 8; measured 1.08 / 1.18 / 1.15 ms lincomb phase)
     int msm_slice = 0;                 // > 0: fixed slice length of the bucket kernel (KZGB200_MSM_SLICE), else msm_slice_len()
     int parse_fused = 0;            // tuning: decompression + subgroup check in one kernel (env KZGB200_PARSE_FUSED; measured slower)
     int defer_subgroup = 1;         // subgroup checks run beside the latency-bound tail on their own SMs (env KZGB200_DEFER_SUBGROUP)
