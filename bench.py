@@ -543,14 +543,18 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        # dominant kernel = the longest phase of the blocking call (rank 0's phases at N > 1)
-        top = max(range(0, 7), key=lambda i: phases[i])
+        # dominant kernel = the longest KERNEL phase of the blocking call (rank 0's phases at N > 1).  Phase 0 (G1 decompression) runs
+        # beside the hash and phase 3 is the host's transcript hash, not a kernel: when it is the longest phase of the step (exact
+        # transcript at N = 8: one SHA-256 stream over all ranks' entries) the roofline says so in `step_bound`.
+        top = max((1, 2, 4, 5, 6), key=lambda i: phases[i])
         traffic = load_profiled_traffic()
         ach = n * ALGO_BYTES_PER_BLOB / (phases[top] / 1e3) / 1e9
         roof = {"bound": "hbm", "kernel": PHASES[top], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic.get(PHASES[top]), "traffic_source": "profiles/ncu_full_r02_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of this launch on the same workload: profiles/traffic_r02.csv)" if traffic.get(PHASES[top]) else None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
                 "note": "the path is integer-pipe / latency bound, not HBM bound; see int_pipe and DESIGN.md section 4"}
+        if phases[3] > phases[top]:
+            roof["step_bound"] = "host transcript hash (%.2f ms exposed): compute_r_powers is one SHA-256 chain over every rank's entries" % phases[3]
         # algorithmic integer work of the two blob-streaming kernels against the MEASURED pipe peaks (tools/microbench/intpipe.cu,
         # profiles/intpipe_r01.txt): ALU 69.2 thread-ops/clk/SM, carry-chained IMAD.WIDE.X 31.0 /clk/SM, 148 SMs
         clk = 1.965e9
